@@ -1,0 +1,241 @@
+/*
+ * npt.h — C ABI of the B200-native npTranscript read→transcript-cluster hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own; the seam this
+ * ABI replaces is the three-method surface of IdentityProfileHolder
+ * (J = /root/reference/java/src/main/java/npTranscript):
+ *
+ *   npt_create        <- the static configuration copied in J/run/ViralTranscriptAnalysisCmd2.java:221-386, 496-511
+ *   npt_begin_chrom   <- new Annotation(...) + new IdentityProfileHolder(genomes, chr, outp, in_nmes,
+ *                        calcBreaks1, currentIndex, annot)   J/run/ViralTranscriptAnalysisCmd2.java:872-886,
+ *                        J/cluster/IdentityProfileHolder.java:106-128
+ *   npt_submit        <- profile.identity1(readSeq, sam, source_index, ...) called once per surviving record
+ *                        J/run/ViralTranscriptAnalysisCmd2.java:967, J/cluster/IdentityProfileHolder.java:170-196
+ *                        (batched: one call carries n records as structure-of-arrays)
+ *   npt_end_chrom     <- waitOnThreads + printBreakPoints() + getConsensus()
+ *                        J/run/ViralTranscriptAnalysisCmd2.java:840-843, 989-991,
+ *                        J/cluster/IdentityProfileHolder.java:101-104, 152-157
+ *   npt_fetch_results <- what the writers consume: Outputs.printRead rows (J/cluster/IdentityProfile1.java:128-144),
+ *                        CigarClusters.process1 (J/cluster/CigarClusters.java:138-196), Outputs.writeDepthH5
+ *                        (J/cluster/Outputs.java:559-593), Outputs.printMatrix (J/cluster/Outputs.java:461-489),
+ *                        Annotation.print (J/cluster/Annotation.java:40-58)
+ *   npt_destroy       <- IdentityProfileHolder.shutDownExecutor()  J/cluster/IdentityProfileHolder.java:198-204
+ *
+ * Semantics: results are defined as if the submitted records were processed one at a time in
+ * submit order (the reference's --maxThreads=1 behaviour; with its default thread pool the
+ * reference's own cluster numbering is a race, J/cluster/IdentityProfileHolder.java:180-193).
+ *
+ * There is no CPU fallback: every entry point that computes needs an sm_100 device and
+ * returns NPT_ENODEVICE without one.
+ *
+ * Plain C: pointers and sizes only.  All integers little-endian host order.
+ */
+#ifndef NPT_H
+#define NPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPT_ABI_VERSION 1
+#define NPT_MAX_SOURCES 16
+
+/* error codes (every call returns 0 or one of these; text via npt_last_error) */
+#define NPT_OK 0
+#define NPT_EINVAL -1     /* bad argument / unsupported flag combination          */
+#define NPT_ENODEVICE -2  /* no usable CUDA device (no CPU fallback)              */
+#define NPT_ECUDA -3      /* CUDA runtime error                                   */
+#define NPT_ENOMEM -4     /* host or device allocation failed                     */
+#define NPT_ECAPACITY -5  /* a table (clusters, sub-clusters, pairs, ...) is full */
+#define NPT_ESTATE -6     /* call out of order                                    */
+
+/* annotation kinds: J/cluster/Annotation.java (CSV ORF table), J/cluster/EmptyAnnotation.java */
+#define NPT_ANNOT_CSV 0
+#define NPT_ANNOT_EMPTY 1
+
+/* where the arrays of an npt_batch live */
+#define NPT_MEM_HOST 0
+#define NPT_MEM_DEVICE 1
+
+/* key tokens.  A cluster key (CigarHash.secondKey, J/cluster/CigarHash.java:42-62) is a string built
+ * from annotation names; on the device it is the list of these int32 tokens and the host renders it.
+ *   token >= 0          CSV: canonical name id of the ORF row; EMPTY: floor(pos/bin)
+ *   NPT_TOK_ST / _END   the "st"/"end" fall-through names of J/cluster/Annotation.java:71,96
+ *   NPT_TOK_PLUS/_MINUS the '+'/'-' suffix appended when enforceStrand (J/cluster/IdentityProfile1.java:325-327)
+ * The position inside the list decides the delimiter (J/cluster/IdentityProfile1.java:266-292). */
+#define NPT_TOK_ST (-1)
+#define NPT_TOK_END (-2)
+#define NPT_TOK_PLUS (-3)
+#define NPT_TOK_MINUS (-4)
+/* first token when the 5'/3' end names are left out of the key (!includeStart and more than two breaks,
+ * IdentityProfile1.java:267,289): "a,b_" (4 breaks) must not collide with "a_b" (2 breaks). */
+#define NPT_TOK_NOENDS (-5)
+
+/* per-read flag bits in npt_results.read_flags */
+#define NPT_RF_TYPE_MASK 0x3u  /* Annotation.getTypeInd: 0=5_3 1=5_no3 2=no5_3 3=no5_no3 (J/cluster/Annotation.java:233-236) */
+#define NPT_RF_LEADER 0x4u     /* hasLeaderBreak (J/cluster/IdentityProfile1.java:256, 281) */
+#define NPT_RF_NEG 0x8u        /* read negative strand flag (SAM flag 0x10) */
+#define NPT_RF_BADCIGAR 0x10u  /* CIGAR op > 8: the reference throws (J/cluster/IdentityProfile1.java:577-578); read not clustered */
+#define NPT_RF_SLOWPATH 0x20u  /* diagnostic: read was walked by the exact serial device path */
+
+typedef struct npt_config {
+  int32_t abi_version;            /* NPT_ABI_VERSION */
+  int32_t bin;                    /* --bin: CigarHash2.round = Annotation.tolerance (ViralTranscriptAnalysisCmd2.java:496-497) */
+  int32_t break_thresh;           /* --breakThresh: IdentityProfile1.break_thresh (:565) */
+  int32_t include_start;          /* --includeStart: IdentityProfile1.includeStartEnd (:300) */
+  int32_t coronavirus;            /* --coronavirus (:302); also selects min_first_last_exon_length 0/10 (:339,360) */
+  int32_t start_thresh;           /* --startThresh (:508) */
+  int32_t end_thresh;             /* --endThresh (:509) */
+  int32_t enforce_strand;         /* --enforceStrand: Annotation.enforceStrand (:241) */
+  int32_t record_depth;           /* --recordDepthByPosition: CigarCluster.recordDepthByPosition = recordStartEnd (:333-334) */
+  int32_t calc_breaks;            /* calcBreaks (:346,370); the library additionally requires break_thresh < seqlen (:882) */
+  int32_t first_is_transcriptome; /* --firstIsTranscriptome: Outputs.firstIsTranscriptome (:376) */
+  int32_t track_break_sums;       /* writeGFF || writeIsoforms: Count.addBreaks is called (CigarCluster.java:384,676) */
+  int32_t num_sources;            /* number of input BAMs (in_nmes.length) */
+  int32_t rna[NPT_MAX_SOURCES];   /* ViralTranscriptAnalysisCmd2.RNA[src] (:243-257) */
+  int32_t device;                 /* CUDA device ordinal */
+  /* capacities of the device tables; 0 = library default.  Exceeding one is NPT_ECAPACITY, never a silent drop. */
+  int32_t max_clusters;
+  int32_t max_subclusters;
+  int32_t max_break_pairs;
+  int32_t max_coverage_clusters;  /* clusters that get dense coverage rows when record_depth */
+} npt_config;
+
+/* ORF table of one chromosome (J/cluster/Annotation.java:138-179) as parallel arrays, in file row order
+ * (rows with Direction=both are already duplicated by the caller when enforce_strand, :160-164). */
+typedef struct npt_annotation {
+  int32_t kind;            /* NPT_ANNOT_* */
+  int32_t n;               /* rows (0 for EMPTY) */
+  const int32_t* start;    /* Minimum */
+  const int32_t* end;      /* Maximum */
+  const uint8_t* strand;   /* 1 = forward */
+  const int32_t* name_id;  /* rows with equal gene strings share an id (index of first row with that string) */
+} npt_annotation;
+
+/* One batch of surviving records (after the filter chain of ViralTranscriptAnalysisCmd2.java:712-959),
+ * structure-of-arrays, exactly the fields the path reads from SAMRecord:
+ *   pos        sam.getAlignmentStart(), 1-based
+ *   flag       SAM flag word (only 0x10 is read: getReadNegativeStrandFlag)
+ *   src        source_index (SequenceUtils.src_tag, :756)
+ *   cigar      BAM encoding (len<<4)|op, op in MIDNSHP=X = 0..8
+ *   seq4       BAM 4-bit bases "=ACMGRSVTWYHKDBN", two per byte, high nibble first, each read byte-aligned
+ * cigar_off/seq_off are batch-relative element/byte offsets with n+1 entries. */
+typedef struct npt_batch {
+  int64_t n;
+  int32_t location;        /* NPT_MEM_HOST or NPT_MEM_DEVICE */
+  int32_t reserved;
+  const int32_t* pos;
+  const uint16_t* flag;
+  const uint16_t* src;
+  const uint32_t* cigar_off;
+  const uint32_t* cigar;
+  const uint64_t* seq_off;
+  const uint8_t* seq4;
+} npt_batch;
+
+/* Everything the reference's writers need, in host memory owned by the context
+ * (valid until npt_release_results / npt_begin_chrom / npt_destroy). */
+typedef struct npt_results {
+  /* ---- per read, in submit order (the 0.readToCluster row, IdentityProfile1.java:133-136) ---- */
+  int64_t n_reads;
+  const int32_t* cluster_id;    /* n of "ID<chr>.<n>": first-appearance rank (CigarClusters.java:83); -1 if not clustered */
+  const int32_t* sub_id;        /* k of ".t<k>": first-appearance rank inside the cluster (CigarCluster.java:660) */
+  const int32_t* start_pos;     /* breaks[0] after trimming */
+  const int32_t* end_pos;       /* breaks[last] */
+  const int32_t* read_st;       /* sam.getReadPositionAtReferencePosition(alignmentStart) (:634) */
+  const int32_t* read_en;       /* ... (alignmentEnd) (:635) */
+  const uint32_t* read_flags;   /* NPT_RF_* */
+  const int32_t* maps_sum;      /* maps[src].valsum of the read's scratch (errorRatio denominator); 0 if !record_depth */
+  const int32_t* err_sum;       /* errors[src].valsum (numerator) */
+  const uint64_t* break_off;    /* n_reads+1 offsets into breaks */
+  const int32_t* breaks;        /* CigarCluster.breaks of each read (1-based positions) */
+  /* ---- per cluster, index = cluster_id ---- */
+  int32_t n_clusters;
+  const int64_t* cl_first_read; /* global submit index of the read that created it */
+  const uint32_t* cl_key_off;   /* n_clusters+1 offsets into cl_key_tok */
+  const int32_t* cl_key_tok;    /* key tokens */
+  const int32_t* cl_read_count; /* [n_clusters][num_sources] readCount */
+  const uint32_t* cl_sub_off;   /* n_clusters+1 offsets into the sub-cluster arrays (subs of a cluster are contiguous, in .t order) */
+  /* ---- per sub-cluster ---- */
+  int32_t n_subs;
+  const int64_t* sub_first_read;
+  const uint32_t* sub_key_off;  /* n_subs+1 offsets into sub_key */
+  const int32_t* sub_key;       /* binned breaks, CigarCluster.cloneBreaks (CigarCluster.java:620-631) */
+  const int32_t* sub_count;     /* [n_subs][num_sources] Count.count */
+  const int32_t* sub_break_sum; /* Count.break_sum */
+  const uint32_t* sub_sum_off;  /* n_subs+1 offsets into sub_sums */
+  const int64_t* sub_sums;      /* exact integer sums of the raw breaks of the reads counted in break_sum */
+  const uint8_t* sub_flags;     /* bit0: forward of the first read, bit1: neg-strand flag of the first read */
+  /* ---- per chromosome aggregates ---- */
+  const int32_t* total_counts;  /* [num_sources] CigarClusters.totalCounts */
+  int32_t n_orf;
+  const int32_t* spliced;       /* [num_sources][n_orf] Annotation.spliced_count */
+  const int32_t* unspliced;     /* [num_sources][n_orf] */
+  int64_t n_pairs;              /* break-point matrix entries (BreakPoints.java:102-108), sorted by (src, level, start, end) */
+  const int32_t* pair_src;
+  const int32_t* pair_level;
+  const int32_t* pair_start;
+  const int32_t* pair_end;
+  const int32_t* pair_count;
+  /* ---- coverage (record_depth only): dense rows of seqlen+2 ints, index = 1-based position ---- */
+  int32_t cov_stride;           /* seqlen + 2 */
+  const int32_t* depth;         /* [n_clusters][num_sources][cov_stride] maps[src] */
+  const int32_t* errors;        /* [n_clusters][num_sources][cov_stride] errors[src] */
+  const int32_t* map_start;     /* [n_clusters][num_sources][cov_stride] mapStart */
+  const int32_t* map_end;       /* [n_clusters][num_sources][cov_stride] mapEnd */
+  int64_t n_slow_reads;         /* diagnostic: reads that took the serial device path */
+} npt_results;
+
+typedef struct npt_ctx npt_ctx;
+
+int npt_abi_version(void);
+int npt_create(const npt_config* cfg, npt_ctx** out);
+void npt_destroy(npt_ctx* ctx);
+const char* npt_last_error(const npt_ctx* ctx); /* ctx may be NULL: error of the last failed npt_create on this thread */
+
+/* ref_codes: one BAM 4-bit code per reference base (same code table as seq4), host memory. */
+int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot);
+/* Asynchronous: returns once the batch is enqueued.  Host arrays must stay untouched until npt_wait. */
+int npt_submit(npt_ctx* ctx, const npt_batch* batch);
+int npt_wait(npt_ctx* ctx);
+/* Drains, assigns first-appearance ids (sort-and-rank), rewrites per-read ids, scans the coverage difference arrays. */
+int npt_end_chrom(npt_ctx* ctx);
+/* Copies results to host buffers owned by ctx.  what = bitmask of NPT_FETCH_*. */
+#define NPT_FETCH_READS 1
+#define NPT_FETCH_TABLES 2
+#define NPT_FETCH_COVERAGE 4
+#define NPT_FETCH_ALL 7
+int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out);
+int npt_release_results(npt_ctx* ctx);
+
+/* Multi-GPU hooks (reads shard across ranks; tables merge by key on the host; aggregates are summed by the
+ * caller's collective, e.g. NCCL all-reduce on these device pointers). */
+typedef struct npt_device_view {
+  int32_t n_clusters;           /* local clusters after npt_end_chrom */
+  int32_t cov_stride;
+  void* coverage;               /* device int32 [4][n_slots][num_sources][cov_stride] in GLOBAL cluster order once npt_remap_clusters ran */
+  int64_t coverage_elems;
+  void* small_counts;           /* device int32: total_counts[S], spliced[S][n_orf], unspliced[S][n_orf] */
+  int64_t small_elems;
+} npt_device_view;
+/* Reorders/zero-extends coverage rows so that local cluster i lands at row global_id[i] of n_global rows. */
+int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global);
+int npt_device_view_get(npt_ctx* ctx, npt_device_view* out);
+/* Offset added to the batch-relative read index to form the global submit index (sharded runs). */
+int npt_set_read_index_base(npt_ctx* ctx, int64_t base);
+
+/* pinned host memory for batches (cudaHostAlloc) */
+void* npt_alloc_pinned(size_t bytes);
+void npt_free_pinned(void* p);
+
+/* timing of the device work of the last npt_submit..npt_end_chrom span, measured with CUDA events
+ * on the library's compute stream (milliseconds); used by bench.py for the roofline numbers. */
+int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPT_H */

@@ -1,0 +1,66 @@
+"""In-tree builds: nvcc for the CUDA library (sm_100a), g++ for the synthetic-workload generator.
+The built .so files live next to their sources (git-ignored, shipped to the GPU box by gpurun)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIBNPT = os.path.join(CSRC, "libnpt.so")
+LIBSYNTH = os.path.join(HERE, "synth", "libnptsynth.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    return None
+
+
+def build_libnpt(force=False, verbose=False):
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    srcs.append(os.path.join(ROOT, "include", "npt.h"))
+    cus = [s for s in srcs if s.endswith(".cu")]
+    if not force and not _stale(LIBNPT, srcs):
+        return LIBNPT
+    nvcc = _nvcc()
+    if nvcc is None:
+        if os.path.exists(LIBNPT):
+            return LIBNPT  # GPU box without a toolchain on PATH: use the shipped build
+        raise RuntimeError("nvcc not found and libnpt.so not built")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIBNPT] + cus
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIBNPT
+
+
+def build_synth(force=False):
+    src = os.path.join(HERE, "synth", "synth.cpp")
+    if not force and not _stale(LIBSYNTH, [src]):
+        return LIBSYNTH
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", LIBSYNTH, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return LIBSYNTH
+
+
+def build_all(force=False):
+    return build_libnpt(force), build_synth(force)

@@ -1,0 +1,108 @@
+"""Named workloads: genome shape, ORF table and read-model parameters of the BASELINE.json configs.
+
+The ORF tables restate /root/reference/data/SARS-Cov2/VIC01/Coordinates.csv:1-13 and
+/root/reference/data/229E_CoV/Coordinates.csv:1-10 (gene, Minimum, Maximum; all rows Direction=forward).
+The genome sequence itself is synthetic (uniform ACGT + polyA tail, seeded): reads are generated against it, so
+only its length and tail matter to the path."""
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+
+
+@dataclass
+class Annotation:
+    """Host-side mirror of J/cluster/Annotation.java:138-179 (CSV ORF table) / EmptyAnnotation."""
+    kind: int  # abi.NPT_ANNOT_*
+    genes: List[str] = field(default_factory=list)
+    start: List[int] = field(default_factory=list)
+    end: List[int] = field(default_factory=list)
+    strand: List[bool] = field(default_factory=list)
+
+    @property
+    def name_id(self):
+        first = {}
+        return [first.setdefault(g, i) for i, g in enumerate(self.genes)]
+
+    @classmethod
+    def from_csv(cls, path, enforce_strand=False):
+        """Parse a Coordinates.csv exactly as Annotation.java:138-179 does (header-located columns, 'both' rows duplicated)."""
+        a = cls(kind=0)
+        with open(path) as f:
+            header = f.readline().rstrip("\n").split(",")
+            gi, si, ei, di = (header.index(k) for k in ("gene", "Minimum", "Maximum", "Direction"))
+            for line in f:
+                line = line.rstrip("\n")
+                if not line:
+                    continue
+                t = line.split(",")
+                both, fwd = t[di] == "both", t[di] == "forward"
+                a.genes.append(t[gi]); a.start.append(int(t[si])); a.end.append(int(t[ei]))
+                if both and enforce_strand:
+                    a.strand += [True, False]
+                    a.genes.append(t[gi]); a.start.append(int(t[si])); a.end.append(int(t[ei]))
+                else:
+                    a.strand.append(fwd)
+        return a
+
+    @classmethod
+    def empty(cls):
+        return cls(kind=1)
+
+
+def _csv(rows):
+    return Annotation(kind=0, genes=[r[0] for r in rows], start=[r[1] for r in rows], end=[r[2] for r in rows],
+                      strand=[True] * len(rows))
+
+
+SARS2_VIC01 = _csv([
+    ("leader", 1, 75), ("ORF1ab", 266, 21555), ("S", 21563, 25384), ("ORF3a", 25393, 26220), ("E", 26245, 26472),
+    ("M", 26523, 27191), ("ORF6", 27202, 27387), ("ORF7a", 27394, 27759), ("ORF8", 27894, 28259), ("N", 28274, 29533),
+    ("ORF10", 29558, 29674), ("3UTR", 29675, 29893)])
+
+COV_229E = _csv([
+    ("leader", 1, 100), ("ORF1ab", 293, 20568), ("S", 20570, 24091), ("ORF4a", 24091, 24492), ("ORF4b", 24482, 24748),
+    ("E", 24750, 24983), ("M", 24995, 25672), ("N", 25686, 26855), ("3UTR", 26856, 27317)])
+
+
+@dataclass
+class Workload:
+    name: str
+    genome_len: int
+    polya_len: int
+    annotation: Annotation
+    donor: int
+    acceptors: List[int]
+    acceptor_w: List[float]
+    genome_seed: int = 20200101
+    w_mix: tuple = (0.60, 0.25, 0.10, 0.05)  # canonical, leaderless, genomic, double-junction
+    p_mismatch: float = 0.04
+    p_ins: float = 0.03
+    p_del: float = 0.03
+    indel_mean: float = 1.5
+    p_neg: float = 0.02
+    leaderless_len: float = 600.0
+    genomic_len: float = 1000.0
+
+
+# TRS-B acceptor sites: N 28260 (the KAT of SURVEY §8c), the others ~14 nt upstream of each ORF start
+# (fimo TRS hits /root/reference/data/SARS-Cov2/VIC01/fimo.tsv: 21556, 25385, 26237 ...).
+SARS2 = Workload(
+    name="sars2_vic01_drna", genome_len=29893, polya_len=33, annotation=SARS2_VIC01, donor=69,
+    acceptors=[28260, 26473, 25385, 27388, 27888, 21556, 26237, 27041, 29530],
+    acceptor_w=[0.65, 0.08, 0.03, 0.06, 0.07, 0.01, 0.03, 0.03, 0.04])
+
+HCOV229E = Workload(
+    name="hcov229e_drna", genome_len=27317, polya_len=20, annotation=COV_229E, donor=65,
+    acceptors=[25672, 24983, 24740, 24480, 24080, 20560],
+    acceptor_w=[0.40, 0.20, 0.10, 0.10, 0.10, 0.10])
+
+
+def ref_char_to_code(seq: str) -> np.ndarray:
+    """Reference letters → BAM 4-bit codes (=ACMGRSVTWYHKDBN), case-insensitive; anything else → N(15).
+    This is the comparison domain of refSeq.getBase(..) == readSeq.getBase(..) (IdentityProfile1.java:534)."""
+    table = np.full(256, 15, dtype=np.uint8)
+    for i, ch in enumerate("=ACMGRSVTWYHKDBN"):
+        table[ord(ch)] = i
+        table[ord(ch.lower())] = i
+    return table[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)]
