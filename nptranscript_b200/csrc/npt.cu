@@ -1,0 +1,959 @@
+// npt.cu — host side of libnpt.so: context, device memory, batch staging, end-of-chromosome finalisation, C ABI.
+// Product code.  Never includes or links anything under oracle/.  No CPU compute fallback: without an sm_100 device
+// every computing entry point fails with NPT_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/npt.h"
+#include "npt_device.cuh"
+#include "walk.cuh"
+
+using namespace npt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DBuf {  // grow-only device buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct HBuf {  // grow-only pinned host buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t n) {
+    if (n <= cap && p) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    if (cudaHostAlloc(&p, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { p = nullptr; return false; }
+    cap = std::max<size_t>(n, 1);
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Staging {  // device copy of one host batch
+  DBuf<unsigned char> buf;
+  cudaEvent_t done = nullptr;  // kernel that consumed it finished
+  bool busy = false;
+  int batch_index = -1;
+};
+
+struct Batch {
+  BatchDev d{};
+  int64_t n = 0;
+  void* out_block = nullptr;  // one allocation for all per-read outputs
+  unsigned* bctr = nullptr;
+  int staging = -1;           // index into ctx->stg, or -1 for caller-owned device memory
+  bool retired = false;
+  cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct npt_ctx {
+  npt_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  std::string err;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  bool in_chrom = false, finalized = false;
+  // chromosome state
+  int chrom_index = 0;
+  int64_t G = 0;
+  int n_orf = 0;
+  DevCfg dc{};
+  bool ref_smem = false;
+  size_t smem_bytes = 0;
+  DBuf<uint32_t> d_ref;
+  DBuf<int> d_ostart, d_oname;
+  DBuf<uint8_t> d_ostrand;
+  DBuf<ClEntry> d_cl;
+  DBuf<int> d_cl_tok;
+  DBuf<SubEntry> d_sb;
+  DBuf<int> d_sb_key, d_sub_count, d_sub_break_sum;
+  DBuf<unsigned> d_sub_sum_off, d_sub_nsum;
+  DBuf<unsigned char> d_sub_flags;
+  DBuf<unsigned long long> d_sub_sums;
+  DBuf<PairEntry> d_pr;
+  DBuf<int> d_cov, d_cov_out;
+  DBuf<int> d_small;
+  DBuf<unsigned> d_counters;
+  // finalize scratch
+  DBuf<unsigned long long> d_keys, d_keys2;
+  DBuf<int> d_vals, d_vals2, d_cl_slot, d_sb_slot, d_cl_rank, d_sb_grank, d_cl_sub_off;
+  DBuf<unsigned char> d_cub;
+  DBuf<long long> d_break_off;
+  DBuf<int> d_breaks_out;
+  DBuf<int> d_pairs_out;
+  // batches
+  std::vector<Batch> batches;
+  Staging stg[2];
+  int64_t idx_base = 0;       // global index of the next read
+  int64_t idx_user_base = 0;  // npt_set_read_index_base
+  // finalize products
+  unsigned h_counters[CN_COUNT]{};
+  int n_clusters = 0, n_subs = 0;
+  int cov_rows = 0;           // rows of d_cov_out (n_clusters, or n_global after npt_remap_clusters)
+  int64_t n_pairs = 0;
+  int64_t n_total = 0;
+  long long total_breaks = 0;
+  DBuf<long long> d_ex_first;
+  DBuf<unsigned> d_ex_u[5];
+  DBuf<int> d_ex_i[2];
+  DBuf<unsigned char> d_ex_flags;
+  npt_results res{};
+  // host results (pinned for the large per-read arrays)
+  HBuf<int> r_cluster, r_sub, r_start, r_end, r_rst, r_ren, r_maps, r_err, r_breaks;
+  HBuf<unsigned> r_flags;
+  HBuf<unsigned long long> r_boff;
+  HBuf<int> r_cov;
+  std::vector<int64_t> t_cl_first, t_sub_first, t_sub_sums;
+  std::vector<uint32_t> t_cl_key_off, t_cl_sub_off, t_sub_key_off, t_sub_sum_off;
+  std::vector<int32_t> t_cl_key_tok, t_cl_read_count, t_sub_key, t_sub_count, t_sub_break_sum, t_small;
+  std::vector<uint8_t> t_sub_flags;
+  std::vector<int32_t> t_pair[5];
+  // timing
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  float walk_ms = 0, fin_ms = 0;
+  int64_t walk_launches = 0, total_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> walk_events;
+};
+
+namespace {
+
+int fail(npt_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+#define CK(call)                                                                                           \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess)                                                                                \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? NPT_ENOMEM : NPT_ECUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                            \
+  } while (0)
+
+unsigned pow2_at_least(unsigned long long v) { unsigned p = 1; while (p < v && p < (1u << 31)) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------ small kernels
+__global__ void init_tables_kernel(ClEntry* cl, unsigned ncl, SubEntry* sb, unsigned nsb, PairEntry* pr, unsigned npr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = i; k < ncl; k += stride) { cl[k].tag = 0; cl[k].min_idx = ~0ULL; cl[k].prov = -1; cl[k].tok_off = 0; cl[k].ntok = 0; cl[k].pad = 0; }
+  for (size_t k = i; k < nsb; k += stride) { sb[k].tag = 0; sb[k].min_idx = ~0ULL; sb[k].prov = -1; sb[k].key_off = 0; sb[k].nkey = 0; sb[k].cl_prov = -1; }
+  for (size_t k = i; k < npr; k += stride) { pr[k].key = 0; pr[k].count = 0; pr[k].pad = 0; }
+}
+
+// table slots -> dense arrays indexed by provisional id
+__global__ void collect_clusters_kernel(const ClEntry* cl, unsigned nslots, int n, unsigned long long* keys, int* vals, int* slot_of) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const int p = cl[s].prov;
+    if (p >= 0 && p < n) { keys[p] = cl[s].min_idx; vals[p] = p; slot_of[p] = (int)s; }
+  }
+}
+__global__ void collect_subs_kernel(const SubEntry* sb, unsigned nslots, int n, const int* cl_rank, unsigned long long* keys, int* vals,
+                                    int* slot_of, unsigned char* flags) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const int p = sb[s].prov;
+    if (p >= 0 && p < n) {
+      const unsigned long long m = sb[s].min_idx;
+      keys[p] = ((unsigned long long)(unsigned)cl_rank[sb[s].cl_prov] << 40) | ((m >> 2) & ((1ULL << 40) - 1));
+      vals[p] = p; slot_of[p] = (int)s; flags[p] = (unsigned char)(m & 3);
+    }
+  }
+}
+__global__ void ranks_kernel(const int* sorted_vals, int n, int* rank_of) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) rank_of[sorted_vals[r]] = r;
+}
+__global__ void sub_offsets_kernel(const unsigned long long* sorted_keys, int n, int n_clusters, int* cl_sub_off) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int c = (int)(sorted_keys[r] >> 40);
+    if (r == 0 || (int)(sorted_keys[r - 1] >> 40) != c) cl_sub_off[c] = r;
+    if (r == n - 1) cl_sub_off[n_clusters] = n;
+  }
+}
+__global__ void remap_reads_kernel(int64_t n, int* cluster, int* sub, const int* cl_rank, const int* sb_grank, const int* cl_sub_off) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const int cp = cluster[r], sp = sub[r];
+    int cr = -1, sr = -1;
+    if (cp >= 0) { cr = cl_rank[cp]; if (sp >= 0) sr = sb_grank[sp] - cl_sub_off[cr]; }
+    cluster[r] = cr; sub[r] = sr;
+  }
+}
+__global__ void gather_breaks_kernel(int64_t n, const int* nbreaks, const unsigned* break_loc, const int* arena, long long* off,
+                                     long long off_base, int* out) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const int nb = nbreaks[r];
+    const unsigned loc = break_loc[r];
+    const int* src = (loc == 0xFFFFFFFFu) ? arena + r * BRK_INLINE : arena + n * BRK_INLINE + loc;
+    const long long o = off_base + off[r];
+    off[r] = o;  // batch-relative -> absolute
+    int* dst = out + o;
+    for (int i = 0; i < nb; i++) dst[i] = src[i];
+  }
+}
+// dense, rank-ordered copies of the table columns the host needs
+__global__ void export_clusters_kernel(const ClEntry* cl, const int* slot_of, const int* rank_of, int n, long long* first, unsigned* tok_off,
+                                       unsigned* ntok) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const ClEntry& e = cl[slot_of[p]];
+    const int r = rank_of[p];
+    first[r] = (long long)e.min_idx; tok_off[r] = e.tok_off; ntok[r] = e.ntok;
+  }
+}
+__global__ void export_subs_kernel(const SubEntry* sb, const int* slot_of, const int* grank_of, int n, int S, const int* sub_count,
+                                   const int* sub_break_sum, const unsigned* sub_sum_off, const unsigned* sub_nsum, const unsigned char* sub_flags,
+                                   long long* first, unsigned* key_off, unsigned* nkey, int* count, int* break_sum, unsigned* sum_off,
+                                   unsigned* nsum, unsigned char* flags) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const SubEntry& e = sb[slot_of[p]];
+    const int r = grank_of[p];
+    first[r] = (long long)(e.min_idx >> 2); key_off[r] = e.key_off; nkey[r] = e.nkey;
+    for (int s = 0; s < S; s++) count[(size_t)r * S + s] = sub_count[(size_t)p * S + s];
+    break_sum[r] = sub_break_sum[p]; sum_off[r] = sub_sum_off[p]; nsum[r] = sub_nsum[p]; flags[r] = sub_flags[p];
+  }
+}
+__global__ void compact_pairs_kernel(const PairEntry* pr, unsigned nslots, int* out, unsigned* counter, int cap) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long k = pr[s].key;
+    if (k) {
+      const unsigned o = atomicAdd(counter, 1u);
+      if ((int)o < cap) {
+        out[o * 5 + 0] = (int)((k >> 59) & 0xF); out[o * 5 + 1] = (int)((k >> 58) & 1);
+        out[o * 5 + 2] = (int)((k >> 29) & 0x1FFFFFFF); out[o * 5 + 3] = (int)(k & 0x1FFFFFFF); out[o * 5 + 4] = pr[s].count;
+      }
+    }
+  }
+}
+
+// Coverage rows: out[arr][row_of(prov)][src][:] = arr == 0 ? inclusive scan of the difference row : copy.
+// One block per (arr, prov, src) row; the "segmented prefix scan" of the design (segments = rows).
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8;
+__global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* cov, int cov_cap, int n_prov, int S, int stride,
+                                                                     const int* row_of_prov, int n_rows, int* out) {
+  const int row = blockIdx.x;  // over arr * n_prov * S
+  const int src = row % S, prov = (row / S) % n_prov, arr = row / (S * n_prov);
+  const int orow = row_of_prov[prov];
+  if (orow < 0) return;
+  const int* in = cov + (((size_t)arr * cov_cap + prov) * S + src) * stride;
+  int* o = out + (((size_t)arr * n_rows + orow) * S + src) * stride;
+  if (arr != 0) {
+    for (int i = threadIdx.x; i < stride; i += SCAN_THREADS) o[i] = in[i];
+    return;
+  }
+  __shared__ int warp_tot[SCAN_THREADS / 32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < stride; base += SCAN_THREADS * SCAN_ITEMS) {
+    int v[SCAN_ITEMS];
+    int sum = 0;
+    const int i0 = base + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (i0 + j < stride) ? in[i0 + j] : 0; sum += v[j]; v[j] = sum; }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (unsigned w2 = 0; w2 < warp; w2++) woff += warp_tot[w2];
+    const int carry = carry_s;
+    const int excl = carry + woff + incl - sum;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) if (i0 + j < stride) o[i0 + j] = excl + v[j];
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + sum;
+    __syncthreads();
+  }
+}
+
+size_t walk_smem_bytes(const DevCfg& dc, bool ref_smem) {
+  size_t b = (ref_smem ? (size_t)dc.ref_nwords * 4 : 0) + (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4;
+  b = (b + 15) & ~(size_t)15;
+  return b + sizeof(WarpScratch) * WARPS_PER_BLOCK + 16;
+}
+
+int launch_walk(npt_ctx* ctx, const BatchDev& bd, int mode) {
+  const int blocks_per_sm = std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / std::max<size_t>(ctx->smem_bytes, 1)));
+  long long want = (bd.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+  int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * blocks_per_sm));
+  if (ctx->ref_smem) walk_kernel<true><<<grid, WARPS_PER_BLOCK * 32, ctx->smem_bytes, ctx->s_comp>>>(ctx->dc, bd, mode);
+  else walk_kernel<false><<<grid, WARPS_PER_BLOCK * 32, ctx->smem_bytes, ctx->s_comp>>>(ctx->dc, bd, mode);
+  ctx->total_launches++;
+  CK(cudaGetLastError());
+  return NPT_OK;
+}
+
+int retire_batch(npt_ctx* ctx, size_t bi) {
+  Batch& B = ctx->batches[bi];
+  if (B.retired) return NPT_OK;
+  CK(cudaEventSynchronize(B.done));
+  unsigned h[2];
+  CK(cudaMemcpy(h, B.bctr, sizeof h, cudaMemcpyDeviceToHost));
+  if (h[1]) {
+    // the overflow area for reads with more than BRK_INLINE breaks was too small: re-emit exactly (no side effects)
+    const unsigned need = h[0];
+    int* bigger = nullptr;
+    CK(cudaMalloc(&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int)));
+    CK(cudaMemcpyAsync(bigger, B.d.break_arena, (size_t)B.n * BRK_INLINE * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
+    CK(cudaMemsetAsync(B.bctr, 0, 2 * sizeof(unsigned), ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    cudaFree(B.d.break_arena);
+    B.d.break_arena = bigger; B.d.break_cap = need;
+    int rc = launch_walk(ctx, B.d, 1);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->s_comp));
+  }
+  if (B.staging >= 0) { ctx->stg[B.staging].busy = false; ctx->stg[B.staging].batch_index = -1; }
+  B.retired = true;
+  return NPT_OK;
+}
+
+void free_batches(npt_ctx* ctx) {
+  for (auto& B : ctx->batches) {
+    if (B.out_block) cudaFree(B.out_block);
+    if (B.d.break_arena) cudaFree(B.d.break_arena);
+    if (B.bctr) cudaFree(B.bctr);
+    if (B.done) cudaEventDestroy(B.done);
+  }
+  ctx->batches.clear();
+  for (auto& s : ctx->stg) { s.busy = false; s.batch_index = -1; }
+  for (auto& e : ctx->walk_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  ctx->walk_events.clear();
+}
+
+}  // namespace
+
+// ================================================================================================= C ABI
+extern "C" {
+
+int npt_abi_version(void) { return NPT_ABI_VERSION; }
+
+const char* npt_last_error(const npt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int npt_create(const npt_config* cfg, npt_ctx** out) {
+  npt_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, NPT_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != NPT_ABI_VERSION) return fail(nullptr, NPT_EINVAL, "abi_version %d != %d", cfg->abi_version, NPT_ABI_VERSION);
+  if (cfg->num_sources < 1 || cfg->num_sources > NPT_MAX_SOURCES) return fail(nullptr, NPT_EINVAL, "num_sources out of range");
+  if (cfg->bin < 1) return fail(nullptr, NPT_EINVAL, "bin must be >= 1");
+  if (cfg->break_thresh < 0) return fail(nullptr, NPT_EINVAL, "break_thresh must be >= 0");
+  if (cfg->first_is_transcriptome)
+    return fail(nullptr, NPT_EINVAL, "first_is_transcriptome is not supported yet (order-dependent Count.addBreaks, CigarCluster.java:85)");
+  if (cfg->coronavirus)
+    for (int s = 0; s < cfg->num_sources; s++)
+      if (!cfg->rna[s])
+        return fail(nullptr, NPT_EINVAL, "coronavirus mode needs rna[src]=1 (the reference unboxes a null Boolean, IdentityProfile1.java:165-170,268)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, NPT_ENODEVICE, "no CUDA device (there is no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, NPT_ENODEVICE, "device %d of %d", cfg->device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, NPT_ECUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, NPT_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  ctx = new npt_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ctx->ev_a));
+  CK(cudaEventCreate(&ctx->ev_b));
+  for (auto& s : ctx->stg) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  *out = ctx;
+  return NPT_OK;
+}
+
+void npt_destroy(npt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_batches(ctx);
+  DBuf<unsigned char>* dummy = nullptr; (void)dummy;
+  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_cl.release();
+  ctx->d_cl_tok.release(); ctx->d_sb.release(); ctx->d_sb_key.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
+  ctx->d_sub_sum_off.release(); ctx->d_sub_nsum.release(); ctx->d_sub_flags.release(); ctx->d_sub_sums.release(); ctx->d_pr.release();
+  ctx->d_cov.release(); ctx->d_cov_out.release(); ctx->d_small.release(); ctx->d_counters.release(); ctx->d_keys.release();
+  ctx->d_keys2.release(); ctx->d_vals.release(); ctx->d_vals2.release(); ctx->d_cl_slot.release(); ctx->d_sb_slot.release();
+  ctx->d_cl_rank.release(); ctx->d_sb_grank.release(); ctx->d_cl_sub_off.release(); ctx->d_cub.release(); ctx->d_break_off.release();
+  ctx->d_breaks_out.release(); ctx->d_pairs_out.release(); ctx->d_ex_first.release(); ctx->d_ex_flags.release();
+  for (auto& b : ctx->d_ex_u) b.release();
+  for (auto& b : ctx->d_ex_i) b.release();
+  for (auto& s : ctx->stg) { s.buf.release(); if (s.done) cudaEventDestroy(s.done); }
+  ctx->r_cluster.release(); ctx->r_sub.release(); ctx->r_start.release(); ctx->r_end.release(); ctx->r_rst.release(); ctx->r_ren.release();
+  ctx->r_maps.release(); ctx->r_err.release(); ctx->r_breaks.release(); ctx->r_flags.release(); ctx->r_boff.release(); ctx->r_cov.release();
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+  if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+  delete ctx;
+}
+
+int npt_set_read_index_base(npt_ctx* ctx, int64_t base) {
+  if (!ctx) return NPT_EINVAL;
+  if (base < 0 || base >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "read index base out of range");
+  ctx->idx_user_base = base;
+  return NPT_OK;
+}
+
+int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot) {
+  if (!ctx || !ref_codes || !annot || ref_len < 1) return fail(ctx, NPT_EINVAL, "bad argument");
+  const npt_config& cf = ctx->cfg;
+  if (ref_len > (1LL << 31) - 64) return fail(ctx, NPT_EINVAL, "reference too long");
+  if (annot->kind != NPT_ANNOT_CSV && annot->kind != NPT_ANNOT_EMPTY) return fail(ctx, NPT_EINVAL, "unknown annotation kind");
+  if (annot->kind == NPT_ANNOT_CSV && cf.coronavirus && annot->n < 2)
+    return fail(ctx, NPT_EINVAL, "coronavirus mode needs >= 2 annotation rows (Annotation.isLeader reads start.get(1), Annotation.java:214-216)");
+  if (annot->n < 0 || annot->n > 4096) return fail(ctx, NPT_EINVAL, "annotation rows out of range");
+  const bool calc_breaks1 = cf.calc_breaks && cf.coronavirus && (int64_t)cf.break_thresh < ref_len;  // ViralTranscriptAnalysisCmd2.java:882
+  if ((cf.record_depth || calc_breaks1) && ref_len + 2 >= (1LL << 29))
+    return fail(ctx, NPT_EINVAL, "dense coverage / break-point matrix need seqlen < 2^29");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  free_batches(ctx);
+  ctx->in_chrom = true; ctx->finalized = false;
+  ctx->chrom_index = chrom_index; ctx->G = ref_len; ctx->n_orf = annot->n;
+  ctx->idx_base = ctx->idx_user_base;
+  ctx->walk_ms = ctx->fin_ms = 0; ctx->walk_launches = ctx->total_launches = 0;
+
+  DevCfg& dc = ctx->dc;
+  memset(&dc, 0, sizeof dc);
+  dc.T = cf.break_thresh; dc.bin = cf.bin; dc.include_start = cf.include_start; dc.coronavirus = cf.coronavirus;
+  dc.start_thresh = cf.start_thresh; dc.end_thresh = cf.end_thresh; dc.enforce_strand = cf.enforce_strand;
+  dc.record_depth = cf.record_depth; dc.calc_breaks1 = calc_breaks1; dc.fit = 0; dc.track_sums = cf.track_break_sums;
+  dc.S = cf.num_sources; dc.min_fl_exon = cf.coronavirus ? 0 : 10;
+  dc.rna_mask = 0;
+  for (int s = 0; s < cf.num_sources; s++) if (cf.rna[s]) dc.rna_mask |= 1u << s;
+  dc.annot_kind = annot->kind; dc.n_orf = annot->n; dc.G = (int)ref_len; dc.stride = (int)ref_len + 2;
+  dc.force_serial = cf.break_thresh < 8;
+
+  // reference: 8 bases per word, first base in the top nibble, 4 words of padding
+  const int nwords = (int)((ref_len + 7) / 8) + 4;
+  std::vector<uint32_t> words(nwords, 0);
+  for (int64_t i = 0; i < ref_len; i++) words[i >> 3] |= (uint32_t)(ref_codes[i] & 0xF) << (28 - 4 * (i & 7));
+  CK(ctx->d_ref.ensure(nwords));
+  CK(cudaMemcpy(ctx->d_ref.p, words.data(), (size_t)nwords * 4, cudaMemcpyHostToDevice));
+  dc.ref_words = ctx->d_ref.p; dc.ref_nwords = nwords;
+  CK(ctx->d_ostart.ensure(annot->n)); CK(ctx->d_oname.ensure(annot->n)); CK(ctx->d_ostrand.ensure(annot->n));
+  if (annot->n) {
+    CK(cudaMemcpy(ctx->d_ostart.p, annot->start, (size_t)annot->n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_oname.p, annot->name_id, (size_t)annot->n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ostrand.p, annot->strand, (size_t)annot->n, cudaMemcpyHostToDevice));
+  }
+  dc.orf_start = ctx->d_ostart.p; dc.orf_name = ctx->d_oname.p; dc.orf_strand = ctx->d_ostrand.p;
+
+  // tables
+  const int max_cl = cf.max_clusters > 0 ? cf.max_clusters : (1 << 16);
+  const int max_sb = cf.max_subclusters > 0 ? cf.max_subclusters : (1 << 21);
+  const int max_pr = cf.max_break_pairs > 0 ? cf.max_break_pairs : (1 << 20);
+  const int max_cov = cf.record_depth ? (cf.max_coverage_clusters > 0 ? cf.max_coverage_clusters : 1024) : 0;
+  const unsigned ncl = pow2_at_least(2ull * max_cl), nsb = pow2_at_least(2ull * max_sb), npr = calc_breaks1 ? pow2_at_least(2ull * max_pr) : 1;
+  CK(ctx->d_cl.ensure(ncl)); CK(ctx->d_sb.ensure(nsb)); CK(ctx->d_pr.ensure(npr));
+  dc.cl = ctx->d_cl.p; dc.cl_mask = ncl - 1; dc.cl_cap = max_cl;
+  dc.sb = ctx->d_sb.p; dc.sb_mask = nsb - 1; dc.sb_cap = max_sb;
+  dc.pr = ctx->d_pr.p; dc.pr_mask = npr - 1; dc.pr_cap = max_pr;
+  dc.tok_cap = (unsigned)std::min<unsigned long long>(16ull * max_cl, 1ull << 30);
+  dc.sbkey_cap = (unsigned)std::min<unsigned long long>(8ull * max_sb, 1ull << 30);
+  dc.sums_cap = cf.track_break_sums ? dc.sbkey_cap : 0;
+  CK(ctx->d_cl_tok.ensure(dc.tok_cap)); CK(ctx->d_sb_key.ensure(dc.sbkey_cap));
+  CK(ctx->d_sub_count.ensure((size_t)max_sb * dc.S)); CK(ctx->d_sub_break_sum.ensure(max_sb));
+  CK(ctx->d_sub_sum_off.ensure(max_sb)); CK(ctx->d_sub_nsum.ensure(max_sb)); CK(ctx->d_sub_flags.ensure(max_sb));
+  CK(ctx->d_sub_sums.ensure(std::max<unsigned>(dc.sums_cap, 1)));
+  dc.cl_tok = ctx->d_cl_tok.p; dc.sb_key = ctx->d_sb_key.p; dc.sub_count = ctx->d_sub_count.p; dc.sub_break_sum = ctx->d_sub_break_sum.p;
+  dc.sub_sum_off = ctx->d_sub_sum_off.p; dc.sub_nsum = ctx->d_sub_nsum.p; dc.sub_flags = ctx->d_sub_flags.p; dc.sub_sums = ctx->d_sub_sums.p;
+  CK(cudaMemsetAsync(ctx->d_sub_count.p, 0, (size_t)max_sb * dc.S * 4, ctx->s_comp));
+  CK(cudaMemsetAsync(ctx->d_sub_break_sum.p, 0, (size_t)max_sb * 4, ctx->s_comp));
+  CK(cudaMemsetAsync(ctx->d_sub_sums.p, 0, (size_t)std::max<unsigned>(dc.sums_cap, 1) * 8, ctx->s_comp));
+  const size_t cov_elems = 4ull * max_cov * dc.S * dc.stride;
+  if (cf.record_depth) {
+    cudaError_t e = ctx->d_cov.ensure(cov_elems);
+    if (e != cudaSuccess) return fail(ctx, NPT_ENOMEM, "coverage rows: %zu bytes for %d clusters (lower max_coverage_clusters)", cov_elems * 4, max_cov);
+    CK(cudaMemsetAsync(ctx->d_cov.p, 0, cov_elems * 4, ctx->s_comp));
+  }
+  dc.cov = ctx->d_cov.p; dc.cov_cap = max_cov;
+  const int nsmall = dc.S * (1 + 2 * dc.n_orf);
+  CK(ctx->d_small.ensure(nsmall));
+  CK(cudaMemsetAsync(ctx->d_small.p, 0, (size_t)nsmall * 4, ctx->s_comp));
+  dc.small = ctx->d_small.p;
+  CK(ctx->d_counters.ensure(CN_COUNT));
+  CK(cudaMemsetAsync(ctx->d_counters.p, 0, CN_COUNT * 4, ctx->s_comp));
+  dc.counters = ctx->d_counters.p;
+  init_tables_kernel<<<ctx->sm_count * 4, 256, 0, ctx->s_comp>>>(dc.cl, ncl, dc.sb, nsb, dc.pr, npr);
+  CK(cudaGetLastError());
+
+  // shared memory plan: keep the packed reference on chip when it fits next to the per-warp scratch
+  ctx->ref_smem = (size_t)nwords * 4 <= 64 * 1024;
+  ctx->smem_bytes = walk_smem_bytes(dc, ctx->ref_smem);
+  if (ctx->smem_bytes > ctx->smem_optin) {
+    ctx->ref_smem = false;
+    ctx->smem_bytes = walk_smem_bytes(dc, false);
+    if (ctx->smem_bytes > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->smem_bytes);
+  }
+  CK(cudaFuncSetAttribute(walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  CK(cudaFuncSetAttribute(walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  return NPT_OK;
+}
+
+int npt_submit(npt_ctx* ctx, const npt_batch* b) {
+  if (!ctx || !b) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_submit outside npt_begin_chrom..npt_end_chrom");
+  if (b->n < 0 || b->n > (1LL << 31) - 1) return fail(ctx, NPT_EINVAL, "batch size out of range");
+  if (b->n == 0) return NPT_OK;
+  if (ctx->idx_base + b->n >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "more than 2^40 reads");
+  CK(cudaSetDevice(ctx->device));
+  const int64_t n = b->n;
+  Batch B;
+  B.n = n;
+  BatchDev& d = B.d;
+  d.n = n; d.idx_base = ctx->idx_base;
+
+  if (b->location == NPT_MEM_HOST) {
+    const uint32_t ncig = b->cigar_off[n];
+    const uint64_t nseq = b->seq_off[n];
+    // staging layout (256-byte aligned sections)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_pos = 0, o_flag = al(o_pos + (size_t)n * 4), o_src = al(o_flag + (size_t)n * 2), o_coff = al(o_src + (size_t)n * 2);
+    const size_t o_cig = al(o_coff + (size_t)(n + 1) * 4), o_soff = al(o_cig + (size_t)ncig * 4), o_seq = al(o_soff + (size_t)(n + 1) * 8);
+    const size_t total = al(o_seq + nseq + 16);
+    int si = -1;
+    for (int k = 0; k < 2; k++) if (!ctx->stg[k].busy) { si = k; break; }
+    if (si < 0) {  // both in flight: retire the older one
+      int older = ctx->stg[0].batch_index < ctx->stg[1].batch_index ? 0 : 1;
+      int rc = retire_batch(ctx, (size_t)ctx->stg[older].batch_index);
+      if (rc) return rc;
+      si = older;
+    }
+    Staging& S = ctx->stg[si];
+    CK(S.buf.ensure(total));
+    unsigned char* base = S.buf.p;
+    CK(cudaMemcpyAsync(base + o_pos, b->pos, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_flag, b->flag, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_src, b->src, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_coff, b->cigar_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+    if (ncig) CK(cudaMemcpyAsync(base + o_cig, b->cigar, (size_t)ncig * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_soff, b->seq_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+    if (nseq) CK(cudaMemcpyAsync(base + o_seq, b->seq4, (size_t)nseq, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaEventRecord(S.done, ctx->s_copy));
+    CK(cudaStreamWaitEvent(ctx->s_comp, S.done, 0));
+    d.pos = (const int*)(base + o_pos); d.flag = (const uint16_t*)(base + o_flag); d.src = (const uint16_t*)(base + o_src);
+    d.cigar_off = (const uint32_t*)(base + o_coff); d.cigar = (const uint32_t*)(base + o_cig);
+    d.seq_off = (const unsigned long long*)(base + o_soff); d.seq4 = base + o_seq; d.seq_bytes = (long long)nseq;
+    S.busy = true; S.batch_index = (int)ctx->batches.size();
+    B.staging = si;
+  } else if (b->location == NPT_MEM_DEVICE) {
+    if (((uintptr_t)b->seq4 & 3) != 0) return fail(ctx, NPT_EINVAL, "device seq4 must be 4-byte aligned");
+    uint64_t nseq = 0;
+    CK(cudaMemcpy(&nseq, b->seq_off + n, 8, cudaMemcpyDeviceToHost));
+    d.pos = b->pos; d.flag = b->flag; d.src = b->src; d.cigar_off = b->cigar_off; d.cigar = b->cigar;
+    d.seq_off = (const unsigned long long*)b->seq_off; d.seq4 = b->seq4; d.seq_bytes = (long long)nseq;
+    B.staging = -1;
+  } else {
+    return fail(ctx, NPT_EINVAL, "unknown batch location");
+  }
+
+  // per-read outputs: 11 int arrays in one block + break arena
+  CK(cudaMalloc(&B.out_block, (size_t)n * 11 * 4));
+  int* ob = (int*)B.out_block;
+  d.cluster = ob; d.sub = ob + n; d.start_pos = ob + 2 * n; d.end_pos = ob + 3 * n; d.read_st = ob + 4 * n; d.read_en = ob + 5 * n;
+  d.rflags = (unsigned*)(ob + 6 * n); d.maps_sum = ob + 7 * n; d.err_sum = ob + 8 * n; d.nbreaks = ob + 9 * n; d.break_loc = (unsigned*)(ob + 10 * n);
+  d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n / 4, 4096), 1LL << 30);
+  CK(cudaMalloc(&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int)));
+  CK(cudaMalloc(&B.bctr, 2 * sizeof(unsigned)));
+  CK(cudaMemsetAsync(B.bctr, 0, 2 * sizeof(unsigned), ctx->s_comp));
+  d.bctr = B.bctr;
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, ctx->s_comp));
+  int rc = launch_walk(ctx, d, 0);
+  if (rc) return rc;
+  ctx->walk_launches++;
+  CK(cudaEventRecord(e1, ctx->s_comp));
+  ctx->walk_events.emplace_back(e0, e1);
+  CK(cudaEventCreateWithFlags(&B.done, cudaEventDisableTiming));
+  CK(cudaEventRecord(B.done, ctx->s_comp));
+  ctx->idx_base += n;
+  ctx->batches.push_back(B);
+  return NPT_OK;
+}
+
+int npt_wait(npt_ctx* ctx) {
+  if (!ctx) return NPT_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  for (size_t i = 0; i < ctx->batches.size(); i++) { int rc = retire_batch(ctx, i); if (rc) return rc; }
+  CK(cudaStreamSynchronize(ctx->s_copy));
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  return NPT_OK;
+}
+
+static int sort_pairs(npt_ctx* ctx, unsigned long long* kin, unsigned long long* kout, int* vin, int* vout, int n) {
+  size_t tmp = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, 64, ctx->s_comp));
+  CK(ctx->d_cub.ensure(tmp));
+  CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, tmp, kin, kout, vin, vout, n, 0, 64, ctx->s_comp));
+  ctx->total_launches += 8;
+  return NPT_OK;
+}
+
+static int coverage_rows(npt_ctx* ctx, const int* d_row_of_prov, int n_rows) {
+  const DevCfg& dc = ctx->dc;
+  const int n_prov = std::min(ctx->n_clusters, dc.cov_cap);
+  const size_t elems = 4ull * std::max(n_rows, 1) * dc.S * dc.stride;
+  CK(ctx->d_cov_out.ensure(elems));
+  CK(cudaMemsetAsync(ctx->d_cov_out.p, 0, elems * 4, ctx->s_comp));
+  if (n_prov > 0) {
+    coverage_rows_kernel<<<4 * n_prov * dc.S, SCAN_THREADS, 0, ctx->s_comp>>>(dc.cov, dc.cov_cap, n_prov, dc.S, dc.stride, d_row_of_prov, n_rows,
+                                                                            ctx->d_cov_out.p);
+    ctx->total_launches++;
+    CK(cudaGetLastError());
+  }
+  ctx->cov_rows = n_rows;
+  return NPT_OK;
+}
+
+int npt_end_chrom(npt_ctx* ctx) {
+  if (!ctx) return NPT_EINVAL;
+  if (!ctx->in_chrom) return fail(ctx, NPT_ESTATE, "npt_end_chrom without npt_begin_chrom");
+  if (ctx->finalized) return NPT_OK;
+  int rc = npt_wait(ctx);
+  if (rc) return rc;
+  // walk time = sum over batches of the kernel's event span
+  ctx->walk_ms = 0;
+  for (auto& e : ctx->walk_events) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); ctx->walk_ms += ms; }
+  CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof ctx->h_counters, cudaMemcpyDeviceToHost));
+  const unsigned er = ctx->h_counters[CN_ERROR];
+  if (er) {
+    std::string m = "device table capacity exceeded:";
+    if (er & ERR_CL_FULL) m += " clusters(max_clusters)";
+    if (er & ERR_SUB_FULL) m += " sub-clusters(max_subclusters)";
+    if (er & ERR_PAIR_FULL) m += " break-point pairs(max_break_pairs)";
+    if (er & ERR_COV_FULL) m += " coverage rows(max_coverage_clusters)";
+    if (er & ERR_ARENA_FULL) m += " key arena";
+    if (er & ERR_TOO_MANY_BREAKS) m += " a read has more than 256 breaks";
+    ctx->in_chrom = false;
+    return fail(ctx, NPT_ECAPACITY, "%s", m.c_str());
+  }
+  const DevCfg& dc = ctx->dc;
+  const int nc = (int)ctx->h_counters[CN_CLUSTERS], ns = (int)ctx->h_counters[CN_SUBS];
+  if (ns < nc) return fail(ctx, NPT_ECUDA, "internal: %d sub-clusters for %d clusters", ns, nc);
+  ctx->n_clusters = nc; ctx->n_subs = ns;
+  CK(cudaEventRecord(ctx->ev_a, ctx->s_comp));
+  const int nmax = std::max(std::max(nc, ns), 1);
+  CK(ctx->d_keys.ensure(nmax)); CK(ctx->d_keys2.ensure(nmax)); CK(ctx->d_vals.ensure(nmax)); CK(ctx->d_vals2.ensure(nmax));
+  CK(ctx->d_cl_slot.ensure(std::max(nc, 1))); CK(ctx->d_sb_slot.ensure(std::max(ns, 1)));
+  CK(ctx->d_cl_rank.ensure(std::max(nc, 1))); CK(ctx->d_sb_grank.ensure(std::max(ns, 1))); CK(ctx->d_cl_sub_off.ensure(nc + 1));
+  if (nc > 0) {
+    // sort-and-rank: cluster id = rank of its first read index (CigarClusters.java:83)
+    collect_clusters_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.cl, dc.cl_mask + 1, nc, ctx->d_keys.p, ctx->d_vals.p, ctx->d_cl_slot.p);
+    if ((rc = sort_pairs(ctx, ctx->d_keys.p, ctx->d_keys2.p, ctx->d_vals.p, ctx->d_vals2.p, nc))) return rc;
+    ranks_kernel<<<(nc + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_vals2.p, nc, ctx->d_cl_rank.p);
+    // sub-cluster id = rank of its first read index among the subs of its cluster (CigarCluster.java:660)
+    CK(cudaMemsetAsync(ctx->d_cl_sub_off.p, 0, (size_t)(nc + 1) * 4, ctx->s_comp));
+    if (ns > 0) {
+      collect_subs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.sb, dc.sb_mask + 1, ns, ctx->d_cl_rank.p, ctx->d_keys.p, ctx->d_vals.p,
+                                                                       ctx->d_sb_slot.p, dc.sub_flags);
+      if ((rc = sort_pairs(ctx, ctx->d_keys.p, ctx->d_keys2.p, ctx->d_vals.p, ctx->d_vals2.p, ns))) return rc;
+      ranks_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_vals2.p, ns, ctx->d_sb_grank.p);
+      sub_offsets_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_keys2.p, ns, nc, ctx->d_cl_sub_off.p);
+    }
+    ctx->total_launches += 6;
+    CK(cudaGetLastError());
+  }
+  // per-read: provisional ids -> ranks; break lists -> one compact array in submit order
+  int64_t n_total = 0;
+  for (auto& B : ctx->batches) n_total += B.n;
+  CK(ctx->d_break_off.ensure(n_total + 1));
+  int64_t off_r = 0;
+  std::vector<long long> batch_break_base(ctx->batches.size() + 1, 0);
+  for (size_t bi = 0; bi < ctx->batches.size(); bi++) {
+    Batch& B = ctx->batches[bi];
+    const int grid = (int)std::min<int64_t>((B.n + 255) / 256, ctx->sm_count * 16);
+    if (nc > 0) remap_reads_kernel<<<grid, 256, 0, ctx->s_comp>>>(B.n, B.d.cluster, B.d.sub, ctx->d_cl_rank.p, ctx->d_sb_grank.p, ctx->d_cl_sub_off.p);
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, B.d.nbreaks, ctx->d_break_off.p + off_r, (int)B.n, ctx->s_comp));
+    CK(ctx->d_cub.ensure(tmp));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, tmp, B.d.nbreaks, ctx->d_break_off.p + off_r, (int)B.n, ctx->s_comp));
+    long long last_off = 0; int last_n = 0;
+    CK(cudaMemcpyAsync(&last_off, ctx->d_break_off.p + off_r + B.n - 1, 8, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(cudaMemcpyAsync(&last_n, B.d.nbreaks + B.n - 1, 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    batch_break_base[bi + 1] = batch_break_base[bi] + last_off + last_n;
+    off_r += B.n;
+    ctx->total_launches += 3;
+  }
+  const long long total_breaks = batch_break_base[ctx->batches.size()];
+  CK(ctx->d_breaks_out.ensure(std::max<long long>(total_breaks, 1)));
+  off_r = 0;
+  for (size_t bi = 0; bi < ctx->batches.size(); bi++) {
+    Batch& B = ctx->batches[bi];
+    const int grid = (int)std::min<int64_t>((B.n + 255) / 256, ctx->sm_count * 16);
+    gather_breaks_kernel<<<grid, 256, 0, ctx->s_comp>>>(B.n, B.d.nbreaks, B.d.break_loc, B.d.break_arena, ctx->d_break_off.p + off_r,
+                                                         batch_break_base[bi], ctx->d_breaks_out.p);
+    off_r += B.n;
+    ctx->total_launches++;
+  }
+  CK(cudaMemcpyAsync(ctx->d_break_off.p + n_total, &total_breaks, 8, cudaMemcpyHostToDevice, ctx->s_comp));
+  CK(cudaGetLastError());
+  // break-point pairs -> dense list
+  ctx->n_pairs = 0;
+  if (dc.calc_breaks1) {
+    const int np = (int)ctx->h_counters[CN_PAIRS];
+    CK(ctx->d_pairs_out.ensure((size_t)std::max(np, 1) * 5));
+    unsigned* ctr = ctx->d_counters.p + CN_PAIRS;
+    CK(cudaMemsetAsync(ctr, 0, 4, ctx->s_comp));
+    compact_pairs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.pr, dc.pr_mask + 1, ctx->d_pairs_out.p, ctr, np);
+    ctx->total_launches++;
+    ctx->n_pairs = np;
+  }
+  // coverage: difference rows -> depth, rows in cluster-id order
+  if (dc.record_depth) {
+    if ((rc = coverage_rows(ctx, ctx->d_cl_rank.p, nc))) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev_b, ctx->s_comp));
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  CK(cudaEventElapsedTime(&ctx->fin_ms, ctx->ev_a, ctx->ev_b));
+  ctx->total_breaks = total_breaks;
+  ctx->n_total = n_total;
+  ctx->finalized = true;
+  ctx->in_chrom = false;
+  return NPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ results
+
+int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
+  if (!ctx || !out) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_fetch_results before npt_end_chrom");
+  CK(cudaSetDevice(ctx->device));
+  const DevCfg& dc = ctx->dc;
+  const int S = dc.S, nc = ctx->n_clusters, ns = ctx->n_subs;
+  npt_results& R = ctx->res;
+  memset(&R, 0, sizeof R);
+  cudaStream_t st = ctx->s_comp;
+  const int64_t n = ctx->n_total;
+  R.n_reads = n;
+  R.n_clusters = nc; R.n_subs = ns; R.n_orf = dc.n_orf; R.cov_stride = dc.stride;
+  R.n_slow_reads = ctx->h_counters[CN_SLOW];
+  if (what & NPT_FETCH_READS) {
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    if (!ctx->r_cluster.ensure(nn) || !ctx->r_sub.ensure(nn) || !ctx->r_start.ensure(nn) || !ctx->r_end.ensure(nn) || !ctx->r_rst.ensure(nn) ||
+        !ctx->r_ren.ensure(nn) || !ctx->r_flags.ensure(nn) || !ctx->r_maps.ensure(nn) || !ctx->r_err.ensure(nn) || !ctx->r_boff.ensure(nn + 1) ||
+        !ctx->r_breaks.ensure((size_t)std::max<long long>(ctx->total_breaks, 1)))
+      return fail(ctx, NPT_ENOMEM, "pinned result buffers");
+    int64_t o = 0;
+    for (auto& B : ctx->batches) {
+      const size_t bytes = (size_t)B.n * 4;
+      CK(cudaMemcpyAsync(ctx->r_cluster.p + o, B.d.cluster, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_sub.p + o, B.d.sub, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_start.p + o, B.d.start_pos, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_end.p + o, B.d.end_pos, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_rst.p + o, B.d.read_st, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_ren.p + o, B.d.read_en, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_flags.p + o, B.d.rflags, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_maps.p + o, B.d.maps_sum, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->r_err.p + o, B.d.err_sum, bytes, cudaMemcpyDeviceToHost, st));
+      o += B.n;
+    }
+    CK(cudaMemcpyAsync(ctx->r_boff.p, ctx->d_break_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (ctx->total_breaks) CK(cudaMemcpyAsync(ctx->r_breaks.p, ctx->d_breaks_out.p, (size_t)ctx->total_breaks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    R.cluster_id = ctx->r_cluster.p; R.sub_id = ctx->r_sub.p; R.start_pos = ctx->r_start.p; R.end_pos = ctx->r_end.p;
+    R.read_st = ctx->r_rst.p; R.read_en = ctx->r_ren.p; R.read_flags = ctx->r_flags.p; R.maps_sum = ctx->r_maps.p; R.err_sum = ctx->r_err.p;
+    R.break_off = (const uint64_t*)ctx->r_boff.p; R.breaks = ctx->r_breaks.p;
+  }
+  if (what & NPT_FETCH_TABLES) {
+    const int nc1 = std::max(nc, 1), ns1 = std::max(ns, 1);
+    CK(ctx->d_ex_first.ensure(std::max(nc1, ns1)));
+    for (auto& b : ctx->d_ex_u) CK(b.ensure(std::max(nc1, ns1)));
+    CK(ctx->d_ex_i[0].ensure((size_t)ns1 * S)); CK(ctx->d_ex_i[1].ensure(ns1));
+    CK(ctx->d_ex_flags.ensure(ns1));
+    // clusters
+    std::vector<long long> first(nc1);
+    std::vector<unsigned> toff(nc1), ntok(nc1);
+    if (nc > 0) {
+      export_clusters_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dc.cl, ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_ex_first.p, ctx->d_ex_u[0].p,
+                                                              ctx->d_ex_u[1].p);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(first.data(), ctx->d_ex_first.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(toff.data(), ctx->d_ex_u[0].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ntok.data(), ctx->d_ex_u[1].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int> tok_arena(std::max<unsigned>(ctx->h_counters[CN_TOK_USED], 1));
+    CK(cudaMemcpyAsync(tok_arena.data(), dc.cl_tok, (size_t)ctx->h_counters[CN_TOK_USED] * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int> cl_sub_off(nc + 1, 0);
+    CK(cudaMemcpyAsync(cl_sub_off.data(), ctx->d_cl_sub_off.p, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->t_cl_first.assign(first.begin(), first.begin() + nc);
+    ctx->t_cl_key_off.assign(nc + 1, 0);
+    ctx->t_cl_key_tok.clear();
+    for (int r = 0; r < nc; r++) {
+      ctx->t_cl_key_off[r] = (uint32_t)ctx->t_cl_key_tok.size();
+      ctx->t_cl_key_tok.insert(ctx->t_cl_key_tok.end(), tok_arena.begin() + toff[r], tok_arena.begin() + toff[r] + ntok[r]);
+    }
+    ctx->t_cl_key_off[nc] = (uint32_t)ctx->t_cl_key_tok.size();
+    ctx->t_cl_sub_off.assign(cl_sub_off.begin(), cl_sub_off.end());
+    // sub-clusters
+    std::vector<long long> sfirst(ns1);
+    std::vector<unsigned> koff(ns1), nkey(ns1), soff(ns1), nsum(ns1);
+    std::vector<int> cnt((size_t)ns1 * S), bsum(ns1);
+    std::vector<unsigned char> sflags(ns1);
+    if (ns > 0) {
+      export_subs_kernel<<<(ns + 255) / 256, 256, 0, st>>>(dc.sb, ctx->d_sb_slot.p, ctx->d_sb_grank.p, ns, S, dc.sub_count, dc.sub_break_sum,
+                                                          dc.sub_sum_off, dc.sub_nsum, dc.sub_flags, ctx->d_ex_first.p, ctx->d_ex_u[0].p,
+                                                          ctx->d_ex_u[1].p, ctx->d_ex_i[0].p, ctx->d_ex_i[1].p, ctx->d_ex_u[2].p, ctx->d_ex_u[3].p,
+                                                          ctx->d_ex_flags.p);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(sfirst.data(), ctx->d_ex_first.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(koff.data(), ctx->d_ex_u[0].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(nkey.data(), ctx->d_ex_u[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(cnt.data(), ctx->d_ex_i[0].p, (size_t)ns * S * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(bsum.data(), ctx->d_ex_i[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(soff.data(), ctx->d_ex_u[2].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(nsum.data(), ctx->d_ex_u[3].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(sflags.data(), ctx->d_ex_flags.p, (size_t)ns, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int> key_arena(std::max<unsigned>(ctx->h_counters[CN_SUBKEY_USED], 1));
+    CK(cudaMemcpyAsync(key_arena.data(), dc.sb_key, (size_t)ctx->h_counters[CN_SUBKEY_USED] * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<long long> sums_arena(std::max<unsigned>(ctx->h_counters[CN_SUMS_USED], 1));
+    if (dc.track_sums)
+      CK(cudaMemcpyAsync(sums_arena.data(), dc.sub_sums, (size_t)ctx->h_counters[CN_SUMS_USED] * 8, cudaMemcpyDeviceToHost, st));
+    const int nsmall = S * (1 + 2 * dc.n_orf);
+    ctx->t_small.assign(nsmall, 0);
+    CK(cudaMemcpyAsync(ctx->t_small.data(), dc.small, (size_t)nsmall * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<int> pr((size_t)std::max<int64_t>(ctx->n_pairs, 1) * 5);
+    if (ctx->n_pairs) CK(cudaMemcpyAsync(pr.data(), ctx->d_pairs_out.p, (size_t)ctx->n_pairs * 5 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->t_sub_first.assign(sfirst.begin(), sfirst.begin() + ns);
+    ctx->t_sub_key_off.assign(ns + 1, 0); ctx->t_sub_sum_off.assign(ns + 1, 0);
+    ctx->t_sub_key.clear(); ctx->t_sub_sums.clear();
+    ctx->t_sub_count.assign(cnt.begin(), cnt.begin() + (size_t)ns * S);
+    ctx->t_sub_break_sum.assign(bsum.begin(), bsum.begin() + ns);
+    ctx->t_sub_flags.assign(sflags.begin(), sflags.begin() + ns);
+    for (int r = 0; r < ns; r++) {
+      ctx->t_sub_key_off[r] = (uint32_t)ctx->t_sub_key.size();
+      ctx->t_sub_key.insert(ctx->t_sub_key.end(), key_arena.begin() + koff[r], key_arena.begin() + koff[r] + nkey[r]);
+      ctx->t_sub_sum_off[r] = (uint32_t)ctx->t_sub_sums.size();
+      if (dc.track_sums) ctx->t_sub_sums.insert(ctx->t_sub_sums.end(), sums_arena.begin() + soff[r], sums_arena.begin() + soff[r] + nsum[r]);
+    }
+    ctx->t_sub_key_off[ns] = (uint32_t)ctx->t_sub_key.size();
+    ctx->t_sub_sum_off[ns] = (uint32_t)ctx->t_sub_sums.size();
+    // cluster readCount[src] = sum over its sub-clusters (CigarCluster.merge :679-682)
+    ctx->t_cl_read_count.assign((size_t)nc * S, 0);
+    for (int c = 0; c < nc; c++)
+      for (int k = cl_sub_off[c]; k < cl_sub_off[c + 1]; k++)
+        for (int s = 0; s < S; s++) ctx->t_cl_read_count[(size_t)c * S + s] += ctx->t_sub_count[(size_t)k * S + s];
+    // break-point pairs sorted by (src, level, start, end)
+    std::vector<int> order((size_t)ctx->n_pairs);
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+      for (int j = 0; j < 4; j++) if (pr[(size_t)a * 5 + j] != pr[(size_t)b * 5 + j]) return pr[(size_t)a * 5 + j] < pr[(size_t)b * 5 + j];
+      return false;
+    });
+    for (int j = 0; j < 5; j++) { ctx->t_pair[j].resize(order.size()); for (size_t i = 0; i < order.size(); i++) ctx->t_pair[j][i] = pr[(size_t)order[i] * 5 + j]; }
+    R.cl_first_read = ctx->t_cl_first.data(); R.cl_key_off = ctx->t_cl_key_off.data(); R.cl_key_tok = ctx->t_cl_key_tok.data();
+    R.cl_read_count = ctx->t_cl_read_count.data(); R.cl_sub_off = ctx->t_cl_sub_off.data();
+    R.sub_first_read = ctx->t_sub_first.data(); R.sub_key_off = ctx->t_sub_key_off.data(); R.sub_key = ctx->t_sub_key.data();
+    R.sub_count = ctx->t_sub_count.data(); R.sub_break_sum = ctx->t_sub_break_sum.data(); R.sub_sum_off = ctx->t_sub_sum_off.data();
+    R.sub_sums = ctx->t_sub_sums.data(); R.sub_flags = ctx->t_sub_flags.data();
+    R.total_counts = ctx->t_small.data(); R.spliced = ctx->t_small.data() + S; R.unspliced = ctx->t_small.data() + S + S * dc.n_orf;
+    R.n_pairs = ctx->n_pairs;
+    R.pair_src = ctx->t_pair[0].data(); R.pair_level = ctx->t_pair[1].data(); R.pair_start = ctx->t_pair[2].data();
+    R.pair_end = ctx->t_pair[3].data(); R.pair_count = ctx->t_pair[4].data();
+  }
+  if ((what & NPT_FETCH_COVERAGE) && dc.record_depth) {
+    const size_t per = (size_t)std::max(ctx->cov_rows, 1) * S * dc.stride;
+    if (!ctx->r_cov.ensure(4 * per)) return fail(ctx, NPT_ENOMEM, "pinned coverage buffer (%zu bytes)", 4 * per * 4);
+    if (ctx->cov_rows) CK(cudaMemcpyAsync(ctx->r_cov.p, ctx->d_cov_out.p, 4 * per * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    R.depth = ctx->r_cov.p; R.errors = ctx->r_cov.p + per; R.map_start = ctx->r_cov.p + 2 * per; R.map_end = ctx->r_cov.p + 3 * per;
+  }
+  *out = R;
+  return NPT_OK;
+}
+
+int npt_release_results(npt_ctx* ctx) {
+  if (!ctx) return NPT_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_batches(ctx);
+  ctx->finalized = false;
+  return NPT_OK;
+}
+
+int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global) {
+  if (!ctx || !global_id) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_remap_clusters before npt_end_chrom");
+  if (!ctx->dc.record_depth) return NPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  // row_of_prov[prov] = global_id[local_rank[prov]]
+  const int nc = ctx->n_clusters;
+  std::vector<int> rank(std::max(nc, 1)), row(std::max(nc, 1));
+  if (nc) CK(cudaMemcpy(rank.data(), ctx->d_cl_rank.p, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+  for (int p = 0; p < nc; p++) {
+    const int g = global_id[rank[p]];
+    if (g < 0 || g >= n_global) return fail(ctx, NPT_EINVAL, "global id %d out of range", g);
+    row[p] = g;
+  }
+  CK(ctx->d_vals.ensure(std::max(nc, 1)));
+  if (nc) CK(cudaMemcpyAsync(ctx->d_vals.p, row.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->s_comp));
+  int rc = coverage_rows(ctx, ctx->d_vals.p, n_global);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  return NPT_OK;
+}
+
+int npt_device_view_get(npt_ctx* ctx, npt_device_view* out) {
+  if (!ctx || !out) return NPT_EINVAL;
+  if (!ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_device_view_get before npt_end_chrom");
+  out->n_clusters = ctx->n_clusters;
+  out->cov_stride = ctx->dc.stride;
+  out->coverage = ctx->dc.record_depth ? ctx->d_cov_out.p : nullptr;
+  out->coverage_elems = ctx->dc.record_depth ? 4ll * ctx->cov_rows * ctx->dc.S * ctx->dc.stride : 0;
+  out->small_counts = ctx->d_small.p;
+  out->small_elems = (int64_t)ctx->dc.S * (1 + 2 * ctx->dc.n_orf);
+  return NPT_OK;
+}
+
+void* npt_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void npt_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches) {
+  if (!ctx) return NPT_EINVAL;
+  if (walk_ms) *walk_ms = ctx->walk_ms;
+  if (finalize_ms) *finalize_ms = ctx->fin_ms;
+  if (walk_launches) *walk_launches = ctx->walk_launches;
+  if (total_launches) *total_launches = ctx->total_launches;
+  return NPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""Thin ctypes wrapper over libnpt.so (include/npt.h).  Product path: fails loudly when the CUDA library is missing,
+cannot be loaded, or finds no sm_100 device — there is no CPU fallback and nothing here touches oracle/."""
+import ctypes as C
+
+import numpy as np
+
+from . import _build, abi
+
+_lib = None
+
+
+class NptError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"npt error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build_libnpt()
+        _lib = abi.declare(C.CDLL(path))
+        if _lib.npt_abi_version() != abi.NPT_ABI_VERSION:
+            raise RuntimeError("libnpt.so ABI version mismatch")
+    return _lib
+
+
+def make_config(**kw):
+    """npt_config with the reference's defaults (ViralTranscriptAnalysisCmd2.java:118-190, 336-372)."""
+    c = abi.npt_config()
+    c.abi_version = abi.NPT_ABI_VERSION
+    d = dict(bin=1, break_thresh=1000, include_start=1, coronavirus=1, start_thresh=100, end_thresh=100, enforce_strand=0,
+             record_depth=0, calc_breaks=1, first_is_transcriptome=0, track_break_sums=1, num_sources=1, device=0,
+             max_clusters=0, max_subclusters=0, max_break_pairs=0, max_coverage_clusters=0)
+    d.update({k: v for k, v in kw.items() if k != "rna"})
+    for k, v in d.items():
+        setattr(c, k, int(v))
+    rna = kw.get("rna", [1] * abi.NPT_MAX_SOURCES)
+    for i in range(abi.NPT_MAX_SOURCES):
+        c.rna[i] = int(rna[i]) if i < len(rna) else 0
+    return c
+
+
+def _np(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).copy()
+
+
+class Results(dict):
+    """npt_results copied into numpy arrays (same field names)."""
+
+    @classmethod
+    def from_struct(cls, r, S, what):
+        o = cls()
+        n = r.n_reads
+        o["n_reads"], o["n_clusters"], o["n_subs"], o["n_orf"] = n, r.n_clusters, r.n_subs, r.n_orf
+        o["n_slow_reads"] = r.n_slow_reads
+        if what & abi.NPT_FETCH_READS:
+            for k in ("cluster_id", "sub_id", "start_pos", "end_pos", "read_st", "read_en", "maps_sum", "err_sum"):
+                o[k] = _np(getattr(r, k), n, np.int32)
+            o["read_flags"] = _np(r.read_flags, n, np.uint32)
+            o["break_off"] = _np(r.break_off, n + 1, np.uint64) if n else np.zeros(1, np.uint64)
+            o["breaks"] = _np(r.breaks, int(o["break_off"][-1]), np.int32)
+        if what & abi.NPT_FETCH_TABLES:
+            nc, ns = r.n_clusters, r.n_subs
+            o["cl_first_read"] = _np(r.cl_first_read, nc, np.int64)
+            o["cl_key_off"] = _np(r.cl_key_off, nc + 1, np.uint32)
+            o["cl_key_tok"] = _np(r.cl_key_tok, int(o["cl_key_off"][-1]) if nc else 0, np.int32)
+            o["cl_read_count"] = _np(r.cl_read_count, nc * S, np.int32).reshape(nc, S)
+            o["cl_sub_off"] = _np(r.cl_sub_off, nc + 1, np.uint32)
+            o["sub_first_read"] = _np(r.sub_first_read, ns, np.int64)
+            o["sub_key_off"] = _np(r.sub_key_off, ns + 1, np.uint32)
+            o["sub_key"] = _np(r.sub_key, int(o["sub_key_off"][-1]) if ns else 0, np.int32)
+            o["sub_count"] = _np(r.sub_count, ns * S, np.int32).reshape(ns, S)
+            o["sub_break_sum"] = _np(r.sub_break_sum, ns, np.int32)
+            o["sub_sum_off"] = _np(r.sub_sum_off, ns + 1, np.uint32)
+            o["sub_sums"] = _np(r.sub_sums, int(o["sub_sum_off"][-1]) if ns else 0, np.int64)
+            o["sub_flags"] = _np(r.sub_flags, ns, np.uint8)
+            o["total_counts"] = _np(r.total_counts, S, np.int32)
+            o["spliced"] = _np(r.spliced, S * r.n_orf, np.int32).reshape(S, r.n_orf)
+            o["unspliced"] = _np(r.unspliced, S * r.n_orf, np.int32).reshape(S, r.n_orf)
+            o["n_pairs"] = r.n_pairs
+            for k in ("pair_src", "pair_level", "pair_start", "pair_end", "pair_count"):
+                o[k] = _np(getattr(r, k), r.n_pairs, np.int32)
+        if (what & abi.NPT_FETCH_COVERAGE) and r.depth:
+            nc, st = r.n_clusters, r.cov_stride
+            o["cov_stride"] = st
+            for k in ("depth", "errors", "map_start", "map_end"):
+                o[k] = _np(getattr(r, k), nc * S * st, np.int32).reshape(nc, S, st)
+        return o
+
+
+class Engine:
+    """One npt_ctx.  begin_chrom → submit* → end_chrom → fetch."""
+
+    def __init__(self, cfg):
+        self.L = lib()
+        self.cfg = cfg
+        self.S = cfg.num_sources
+        h = C.c_void_p()
+        rc = self.L.npt_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise NptError(rc, self.L.npt_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def _ck(self, rc):
+        if rc:
+            raise NptError(rc, self.L.npt_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.npt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def begin_chrom(self, chrom_index, ref_codes, annotation):
+        ref = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+        st = np.asarray(annotation.start, dtype=np.int32)
+        en = np.asarray(annotation.end, dtype=np.int32)
+        sd = np.asarray(annotation.strand, dtype=np.uint8)
+        ni = np.asarray(annotation.name_id, dtype=np.int32)
+        a = abi.npt_annotation()
+        a.kind, a.n = annotation.kind, len(st)
+        a.start = st.ctypes.data_as(C.POINTER(C.c_int32)); a.end = en.ctypes.data_as(C.POINTER(C.c_int32))
+        a.strand = sd.ctypes.data_as(C.POINTER(C.c_uint8)); a.name_id = ni.ctypes.data_as(C.POINTER(C.c_int32))
+        self._ck(self.L.npt_begin_chrom(self.h, chrom_index, ref.ctypes.data, len(ref), C.byref(a)))
+        self._keep = []
+
+    def set_read_index_base(self, base):
+        self._ck(self.L.npt_set_read_index_base(self.h, base))
+
+    def submit(self, batch):
+        """batch: synth.Batch-like with host numpy arrays (kept alive until wait/end_chrom)."""
+        s = abi.npt_batch()
+        s.n, s.location = batch.n, abi.NPT_MEM_HOST
+        s.pos, s.flag, s.src = batch.pos.ctypes.data, batch.flag.ctypes.data, batch.src.ctypes.data
+        s.cigar_off, s.cigar = batch.cigar_off.ctypes.data, batch.cigar.ctypes.data
+        s.seq_off, s.seq4 = batch.seq_off.ctypes.data, batch.seq4.ctypes.data
+        self._keep.append(batch)
+        self._ck(self.L.npt_submit(self.h, C.byref(s)))
+
+    def submit_device(self, n, pos, flag, src, cigar_off, cigar, seq_off, seq4):
+        """Device pointers (ints) of a batch already resident in HBM."""
+        s = abi.npt_batch()
+        s.n, s.location = n, abi.NPT_MEM_DEVICE
+        s.pos, s.flag, s.src, s.cigar_off, s.cigar, s.seq_off, s.seq4 = pos, flag, src, cigar_off, cigar, seq_off, seq4
+        self._ck(self.L.npt_submit(self.h, C.byref(s)))
+
+    def wait(self):
+        self._ck(self.L.npt_wait(self.h))
+        self._keep = []
+
+    def end_chrom(self):
+        self._ck(self.L.npt_end_chrom(self.h))
+        self._keep = []
+
+    def fetch(self, what=abi.NPT_FETCH_ALL):
+        r = abi.npt_results()
+        self._ck(self.L.npt_fetch_results(self.h, what, C.byref(r)))
+        return Results.from_struct(r, self.S, what)
+
+    def fetch_raw(self, what=abi.NPT_FETCH_ALL):
+        """No numpy copies: the npt_results struct with pointers into the context's (pinned) buffers."""
+        r = abi.npt_results()
+        self._ck(self.L.npt_fetch_results(self.h, what, C.byref(r)))
+        return r
+
+    def release(self):
+        self._ck(self.L.npt_release_results(self.h))
+
+    def kernel_ms(self):
+        w, f, wl, tl = C.c_float(), C.c_float(), C.c_int64(), C.c_int64()
+        self._ck(self.L.npt_last_kernel_ms(self.h, C.byref(w), C.byref(f), C.byref(wl), C.byref(tl)))
+        return dict(walk_ms=w.value, finalize_ms=f.value, walk_launches=wl.value, total_launches=tl.value)
+
+    def device_view(self):
+        v = abi.npt_device_view()
+        self._ck(self.L.npt_device_view_get(self.h, C.byref(v)))
+        return v
+
+    def remap_clusters(self, global_id, n_global):
+        g = np.ascontiguousarray(global_id, dtype=np.int32)
+        self._ck(self.L.npt_remap_clusters(self.h, g.ctypes.data, n_global))
+
+
+def run(cfg, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL):
+    e = Engine(cfg)
+    try:
+        e.begin_chrom(chrom_index, ref_codes, annotation)
+        for b in batches:
+            e.submit(b)
+        e.end_chrom()
+        r = e.fetch(what)
+        r["_timing"] = e.kernel_ms()
+        return r
+    finally:
+        e.close()
