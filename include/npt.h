@@ -234,6 +234,8 @@ void npt_free_pinned(void* p);
 /* timing of the device work of the last npt_submit..npt_end_chrom span, measured with CUDA events
  * on the library's compute stream (milliseconds); used by bench.py for the roofline numbers. */
 int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches);
+/* CUDA-event span on the compute stream from the first device work of npt_begin_chrom to the last of npt_end_chrom. */
+int npt_last_step_ms(npt_ctx* ctx, float* step_ms);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ class npt_device_view(C.Structure):
 SYMBOLS = [
     "npt_abi_version", "npt_create", "npt_destroy", "npt_last_error", "npt_begin_chrom", "npt_submit", "npt_wait",
     "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_remap_clusters", "npt_device_view_get",
-    "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms",
+    "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms",
 ]
 
 
@@ -90,8 +90,9 @@ def declare(lib):
     lib.npt_free_pinned.argtypes = [vp]
     lib.npt_free_pinned.restype = None
     lib.npt_last_kernel_ms.argtypes = [vp, P(C.c_float), P(C.c_float), P(i64), P(i64)]
+    lib.npt_last_step_ms.argtypes = [vp, P(C.c_float)]
     for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_wait", "npt_end_chrom", "npt_fetch_results",
               "npt_release_results", "npt_remap_clusters", "npt_device_view_get", "npt_set_read_index_base",
-              "npt_last_kernel_ms"):
+              "npt_last_kernel_ms", "npt_last_step_ms"):
         getattr(lib, s).restype = C.c_int
     return lib

@@ -134,7 +134,8 @@ struct npt_ctx {
   std::vector<uint8_t> t_sub_flags;
   std::vector<int32_t> t_pair[5];
   // timing
-  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
+  float step_ms = 0;
   float walk_ms = 0, fin_ms = 0;
   int64_t walk_launches = 0, total_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> walk_events;
@@ -385,6 +386,8 @@ int npt_create(const npt_config* cfg, npt_ctx** out) {
   CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ctx->ev_a));
   CK(cudaEventCreate(&ctx->ev_b));
+  CK(cudaEventCreate(&ctx->ev_c0));
+  CK(cudaEventCreate(&ctx->ev_c1));
   for (auto& s : ctx->stg) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   *out = ctx;
   return NPT_OK;
@@ -410,6 +413,8 @@ void npt_destroy(npt_ctx* ctx) {
   ctx->r_maps.release(); ctx->r_err.release(); ctx->r_breaks.release(); ctx->r_flags.release(); ctx->r_boff.release(); ctx->r_cov.release();
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_c0) cudaEventDestroy(ctx->ev_c0);
+  if (ctx->ev_c1) cudaEventDestroy(ctx->ev_c1);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
   delete ctx;
@@ -441,6 +446,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   ctx->idx_base = ctx->idx_user_base;
   ctx->walk_ms = ctx->fin_ms = 0; ctx->walk_launches = ctx->total_launches = 0;
 
+  CK(cudaEventRecord(ctx->ev_c0, ctx->s_comp));
   DevCfg& dc = ctx->dc;
   memset(&dc, 0, sizeof dc);
   dc.T = cf.break_thresh; dc.bin = cf.bin; dc.include_start = cf.include_start; dc.coronavirus = cf.coronavirus;
@@ -736,8 +742,10 @@ int npt_end_chrom(npt_ctx* ctx) {
     if ((rc = coverage_rows(ctx, ctx->d_cl_rank.p, nc))) return rc;
   }
   CK(cudaEventRecord(ctx->ev_b, ctx->s_comp));
+  CK(cudaEventRecord(ctx->ev_c1, ctx->s_comp));
   CK(cudaStreamSynchronize(ctx->s_comp));
   CK(cudaEventElapsedTime(&ctx->fin_ms, ctx->ev_a, ctx->ev_b));
+  CK(cudaEventElapsedTime(&ctx->step_ms, ctx->ev_c0, ctx->ev_c1));
   ctx->total_breaks = total_breaks;
   ctx->n_total = n_total;
   ctx->finalized = true;
@@ -946,6 +954,12 @@ void* npt_alloc_pinned(size_t bytes) {
   return p;
 }
 void npt_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int npt_last_step_ms(npt_ctx* ctx, float* step_ms) {
+  if (!ctx || !step_ms) return NPT_EINVAL;
+  *step_ms = ctx->step_ms;
+  return NPT_OK;
+}
 
 int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches) {
   if (!ctx) return NPT_EINVAL;

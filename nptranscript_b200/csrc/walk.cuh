@@ -83,6 +83,23 @@ __device__ __forceinline__ int ev_reserve(WarpScratch* ws, int n) {
   return o;
 }
 
+// Where fast_walk sends coverage events.  SINK 0: nowhere (depth off, or first pass of a long read);
+// SINK 1: shared-memory staging (flushed once the cluster is known); SINK 2: straight to the cluster's rows.
+struct CovSink { int* cov; long long arr_stride; };
+template <int SINK>
+__device__ __forceinline__ void emit_mismatches(WarpScratch* ws, const CovSink& sk, uint32_t mis, int pos0) {
+  if (SINK == 1) {
+    int o = ev_reserve(ws, __popc(mis));
+    if (o >= 0) {
+      uint32_t m = mis;
+      while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); ws->ev[o++] = (EV_ERR << 29) | (unsigned)(pos0 + ((28 - bit) >> 2)); }
+    }
+  } else if (SINK == 2) {
+    uint32_t m = mis;
+    while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); atomicAdd(sk.cov + sk.arr_stride + pos0 + ((28 - bit) >> 2), 1); }
+  }
+}
+
 struct ReadCtx {
   int alnStart, alnEnd, src, neg;
   uint32_t c0, c1;
@@ -186,15 +203,17 @@ __device__ int serial_read_pos(const BatchDev& b, const ReadCtx& rc, int pos) {
 
 // ------------------------------------------------------------------------------------------------ fast warp walker
 // Returns false when the read must be re-walked serially.  Breaks land in ws->br, coverage events in ws->ev.
-template <bool REF_SMEM>
-__device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws, unsigned lane) {
+template <bool REF_SMEM, int SINK>
+__device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws, unsigned lane,
+                          const CovSink sk) {
   const int T = c.T, G = c.G;
-  const bool depth = c.record_depth != 0;
+  constexpr bool depth = SINK != 0;
+  constexpr bool store_br = SINK != 2;  // the direct coverage pass must not disturb the (possibly trimmed) break list
   const unsigned lt = lanemask_lt();
   int refBase = rc.alnStart - 1, readBase = 0;
   int prev = rc.alnStart;
   int nb = 1;
-  if (lane == 0) ws->br[0] = rc.alnStart;
+  if (store_br && lane == 0) ws->br[0] = rc.alnStart;
   int maps = 0, errs = 0;
   bool slow = false;
   bool stFound = false; int st_r = 0;
@@ -233,13 +252,7 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
           if (fmI < 0) fmI = f; else if (f - lmI > T) slow = true;
           lmI = j8 + 7 - ((__ffs(mat) - 1) >> 2);
         }
-        if (depth && mis) {
-          int o = ev_reserve(ws, __popc(mis));
-          if (o >= 0) {
-            uint32_t m = mis;
-            while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); ws->ev[o++] = (EV_ERR << 29) | (unsigned)(base + j8 + ((28 - bit) >> 2)); }
-          }
-        }
+        if (depth && mis) emit_mismatches<SINK>(ws, sk, mis, base + j8);
       }
     }
     __syncwarp();
@@ -260,13 +273,7 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
           cmp8(rw, gw, cnt, mis, mat);
         }
         nmisL += __popc(mis);
-        if (depth && mis) {
-          int o = ev_reserve(ws, __popc(mis));
-          if (o >= 0) {
-            uint32_t m = mis;
-            while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); ws->ev[o++] = (EV_ERR << 29) | (unsigned)(startL + 1 + j8 + ((28 - bit) >> 2)); }
-          }
-        }
+        if (depth && mis) emit_mismatches<SINK>(ws, sk, mis, startL + 1 + j8);
         __syncwarp();
         const unsigned mm = __ballot_sync(0xffffffffu, mat != 0);
         if (mm) {
@@ -300,7 +307,7 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
     const unsigned bm = __ballot_sync(0xffffffffu, brk);
     if (bm) {
       const int o = nb + 2 * __popc(bm & lt);
-      if (brk && o + 1 < MAXB) { ws->br[o] = prev_j; ws->br[o + 1] = fm; }
+      if (store_br && brk && o + 1 < MAXB) { ws->br[o] = prev_j; ws->br[o + 1] = fm; }
       nb += 2 * __popc(bm);
     }
     if (hasMask) prev = __shfl_sync(0xffffffffu, lm, 31 - __clz(hasMask));
@@ -326,18 +333,30 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
         if (lo <= hi) { ms_lo = lo; ms_n = hi - lo + 1; }
       }
       const int tot = ne + nerr + 2 * ms_n;
-      if (tot) {
-        int o = ev_reserve(ws, tot);
-        if (o >= 0) {
-          if (emitStart) {
-            if (prevE >= 0) ws->ev[o++] = (EV_DEPTH_DEC << 29) | (unsigned)prevE;
-            ws->ev[o++] = (EV_DEPTH_INC << 29) | (unsigned)S_j;
+      if (SINK == 1) {
+        if (tot) {
+          int o = ev_reserve(ws, tot);
+          if (o >= 0) {
+            if (emitStart) {
+              if (prevE >= 0) ws->ev[o++] = (EV_DEPTH_DEC << 29) | (unsigned)prevE;
+              ws->ev[o++] = (EV_DEPTH_INC << 29) | (unsigned)S_j;
+            }
+            for (int i = 0; i < nerr; i++) ws->ev[o++] = (EV_ERR << 29) | (unsigned)(base + i);
+            for (int i = 0; i < ms_n; i++) {
+              ws->ev[o++] = (EV_MSTART << 29) | (unsigned)(base + ms_lo + i);
+              ws->ev[o++] = (EV_MEND << 29) | (unsigned)prev_j;
+            }
           }
-          for (int i = 0; i < nerr; i++) ws->ev[o++] = (EV_ERR << 29) | (unsigned)(base + i);
-          for (int i = 0; i < ms_n; i++) {
-            ws->ev[o++] = (EV_MSTART << 29) | (unsigned)(base + ms_lo + i);
-            ws->ev[o++] = (EV_MEND << 29) | (unsigned)prev_j;
-          }
+        }
+      } else if (SINK == 2) {
+        if (emitStart) {
+          if (prevE >= 0) atomicAdd(sk.cov + prevE, -1);
+          atomicAdd(sk.cov + S_j, 1);
+        }
+        for (int i = 0; i < nerr; i++) atomicAdd(sk.cov + sk.arr_stride + base + i, 1);
+        for (int i = 0; i < ms_n; i++) {
+          atomicAdd(sk.cov + 2 * sk.arr_stride + base + ms_lo + i, 1);
+          atomicAdd(sk.cov + 3 * sk.arr_stride + prev_j, 1);
         }
       }
       if (emMask) pendingEnd = __shfl_sync(0xffffffffu, E_j, 31 - __clz(emMask));
@@ -370,14 +389,17 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
   if (__any_sync(0xffffffffu, slow)) return false;
   if (nb + 1 > MAXB) return false;  // let the serial path report it
   rc.alnEnd = refBase;
-  if (lane == 0) ws->br[nb] = rc.alnEnd;
+  if (store_br && lane == 0) ws->br[nb] = rc.alnEnd;
   nb++;
   if (depth && pendingEnd >= 0 && lane == 0) {
-    int o = ev_reserve(ws, 1);
-    if (o >= 0) ws->ev[o] = (EV_DEPTH_DEC << 29) | (unsigned)pendingEnd;
+    if (SINK == 1) {
+      int o = ev_reserve(ws, 1);
+      if (o >= 0) ws->ev[o] = (EV_DEPTH_DEC << 29) | (unsigned)pendingEnd;
+    } else if (SINK == 2) {
+      atomicAdd(sk.cov + pendingEnd, -1);
+    }
   }
   __syncwarp();
-  if (depth && *(volatile int*)&ws->ev_ovf) return false;
   rc.nb = nb;
   rc.maps_sum = __reduce_add_sync(0xffffffffu, maps);
   rc.err_sum = __reduce_add_sync(0xffffffffu, errs);
@@ -603,8 +625,20 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) walk_kernel(const DevCfg
     if (lane == 0) { ws->nev = 0; ws->ev_ovf = 0; }
     __syncwarp();
 
+    // coverage plan: short reads stage their events in shared memory during the walk; reads that could overflow the
+    // staging buffer are walked without events first and a second time, straight into the cluster's rows, once the
+    // cluster is known (their CIGAR and bases are L1/L2-resident by then).
+    const CovSink nosink{nullptr, 0};
+    bool direct_cov = c.record_depth && (rc.c1 - rc.c0) * 2u > (unsigned)MAXEV;
     bool serial = c.force_serial || rc.alnStart <= 0;
-    if (!serial) serial = !fast_walk<REF_SMEM>(c, refw, b, rc, ws, lane);
+    if (!serial) {
+      if (c.record_depth && !direct_cov) {
+        serial = !fast_walk<REF_SMEM, 1>(c, refw, b, rc, ws, lane, nosink);
+        if (!serial && *(volatile int*)&ws->ev_ovf) direct_cov = true;
+      } else {
+        serial = !fast_walk<REF_SMEM, 0>(c, refw, b, rc, ws, lane, nosink);
+      }
+    }
     if (serial && !rc.bad) {
       if (lane == 0) {
         ws->nev = 0; ws->ev_ovf = 0;
@@ -768,6 +802,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) walk_kernel(const DevCfg
         if (serial) {
           if (lane == 0) { ReadCtx rc2 = rc; serial_walk(c, refw, b, rc2, ws, cov, arr_stride); }
           __syncwarp();
+        } else if (direct_cov) {
+          ReadCtx rc2 = rc;
+          fast_walk<REF_SMEM, 2>(c, refw, b, rc2, ws, lane, CovSink{cov, arr_stride});
         } else {
           const int nev = *(volatile int*)&ws->nev;
           for (int i = lane; i < nev; i += 32) {

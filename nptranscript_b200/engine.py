@@ -178,7 +178,9 @@ class Engine:
     def kernel_ms(self):
         w, f, wl, tl = C.c_float(), C.c_float(), C.c_int64(), C.c_int64()
         self._ck(self.L.npt_last_kernel_ms(self.h, C.byref(w), C.byref(f), C.byref(wl), C.byref(tl)))
-        return dict(walk_ms=w.value, finalize_ms=f.value, walk_launches=wl.value, total_launches=tl.value)
+        st = C.c_float()
+        self._ck(self.L.npt_last_step_ms(self.h, C.byref(st)))
+        return dict(walk_ms=w.value, finalize_ms=f.value, walk_launches=wl.value, total_launches=tl.value, step_ms=st.value)
 
     def device_view(self):
         v = abi.npt_device_view()

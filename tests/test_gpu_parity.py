@@ -23,7 +23,7 @@ def test_sars2_20k(depth):
     b = synth.generate(w, 20200301, 20000)
     dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=depth), w, [b])
     assert_same(dev, ora)
-    assert dev["n_slow_reads"] < 20000 // 50
+    assert dev["n_slow_reads"] < 20000 // 200
 
 
 def test_multi_batch_and_sources():
