@@ -23,23 +23,26 @@ namespace npt {
 
 constexpr int WARPS_PER_BLOCK = 8;
 constexpr int MAXB = 256;       // breaks per read held in shared memory
-constexpr int MAXEV = 832;      // coverage events per read staged in shared memory
-constexpr int LONGOP = 64;      // M ops longer than this are compared by the whole warp
+constexpr int MAXEV = 448;      // staged run/start/end events per read
+constexpr int MAXMM = 256;      // staged error windows per read (position of an 8-base window + its mismatch mask)
 constexpr int BRK_INLINE = 6;   // breaks stored in the per-read inline slot
 
-constexpr unsigned EV_DEPTH_INC = 0, EV_DEPTH_DEC = 1, EV_ERR = 2, EV_MSTART = 3, EV_MEND = 4;
+constexpr unsigned EV_DEPTH_INC = 0, EV_DEPTH_DEC = 1, EV_MSTART = 3, EV_MEND = 4;
 constexpr unsigned EV_POS_MASK = (1u << 29) - 1;
 
 struct WarpScratch {
-  int nev;
-  int ev_ovf;
   int br[MAXB];
   int tok[MAXB + 2];
-  unsigned ev[MAXEV];
+  // descriptors of the M ops of the current 32-op chunk, indexed by their rank among the chunk's M ops
+  int m_start0[32], m_rpos0[32], m_nE[32], m_wstart[32], m_fm[32], m_lm[32];
+  unsigned ev[MAXEV];        // (type << 29) | position
+  unsigned mm_pos[MAXMM];    // 1-based position of the first base of an 8-base window
+  unsigned mm_mask[MAXMM];   // error mask of that window, bit 28-4j <-> base j
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+__device__ __forceinline__ unsigned lanemask_le() { unsigned m; asm("mov.u32 %0, %%lanemask_le;" : "=r"(m)); return m; }
 
 template <typename T>
 __device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
@@ -58,14 +61,15 @@ __device__ __forceinline__ uint32_t ref_win8(const uint32_t* w, uint32_t nib) {
   uint32_t k = nib >> 3, o = (nib & 7) << 2;
   return __funnelshift_l(w[k + 1], w[k], o);
 }
-// 8 read bases from the BAM-packed byte stream (little-endian word loads, byte-swapped to base order)
-__device__ __forceinline__ uint32_t read_win8(const uint32_t* w, uint32_t nib, uint32_t lastw) {
+// 8 read bases from the BAM-packed byte stream (little-endian word loads, byte-swapped to base order).
+// Reads one word past the window: batches carry >= 8 readable bytes after seq4 (npt.h).
+__device__ __forceinline__ uint32_t read_win8(const uint32_t* w, uint32_t nib) {
   uint32_t k = nib >> 3, o = (nib & 7) << 2;
-  uint32_t a = __byte_perm(__ldg(w + min(k, lastw)), 0, 0x0123);
-  uint32_t b = __byte_perm(__ldg(w + min(k + 1, lastw)), 0, 0x0123);
+  uint32_t a = __byte_perm(__ldg(w + k), 0, 0x0123);
+  uint32_t b = __byte_perm(__ldg(w + k + 1), 0, 0x0123);
   return __funnelshift_l(b, a, o);
 }
-__device__ __forceinline__ int read_base(const uint32_t* w, uint32_t nib, uint32_t lastw) { return (int)(read_win8(w, nib, lastw) >> 28); }
+__device__ __forceinline__ int read_base(const uint32_t* w, uint32_t nib) { return (int)(read_win8(w, nib) >> 28); }
 __device__ __forceinline__ int ref_base(const uint32_t* w, uint32_t nib) { return (int)((w[nib >> 3] >> (28 - ((nib & 7) << 2))) & 0xF); }
 
 // mismatch / match masks of an 8-base window (bit 28-4j <-> base j), cnt valid bases
@@ -77,26 +81,16 @@ __device__ __forceinline__ void cmp8(uint32_t rw, uint32_t gw, int cnt, uint32_t
   mat = vm & ~nz;
 }
 
-__device__ __forceinline__ int ev_reserve(WarpScratch* ws, int n) {
-  int o = atomicAdd(&ws->nev, n);
-  if (o + n > MAXEV) { ws->ev_ovf = 1; return -1; }
-  return o;
-}
-
 // Where fast_walk sends coverage events.  SINK 0: nowhere (depth off, or first pass of a long read);
 // SINK 1: shared-memory staging (flushed once the cluster is known); SINK 2: straight to the cluster's rows.
 struct CovSink { int* cov; long long arr_stride; };
-template <int SINK>
-__device__ __forceinline__ void emit_mismatches(WarpScratch* ws, const CovSink& sk, uint32_t mis, int pos0) {
-  if (SINK == 1) {
-    int o = ev_reserve(ws, __popc(mis));
-    if (o >= 0) {
-      uint32_t m = mis;
-      while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); ws->ev[o++] = (EV_ERR << 29) | (unsigned)(pos0 + ((28 - bit) >> 2)); }
-    }
-  } else if (SINK == 2) {
-    uint32_t m = mis;
-    while (m) { int bit = 31 - __clz(m); m &= ~(1u << bit); atomicAdd(sk.cov + sk.arr_stride + pos0 + ((28 - bit) >> 2), 1); }
+
+// error positions of one window -> REDs on the cluster's error row
+__device__ __forceinline__ void red_error_window(int* err_row, unsigned pos0, uint32_t mask) {
+  while (mask) {
+    const int bit = 31 - __clz(mask);
+    mask &= ~(1u << bit);
+    atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
   }
 }
 
@@ -114,7 +108,7 @@ struct ReadCtx {
 // ------------------------------------------------------------------------------------------------ serial exact walker
 // Lane 0 only.  Literal restatement of processCigar + CigarCluster.add.  When cov != nullptr the depth/error/start/end
 // events go straight to the cluster's rows (cov points at [arr=0][prov][src][0]; arr_stride ints between arrays).
-__device__ void serial_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws, int* cov,
+__device__ __noinline__ void serial_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws, int* cov,
                             long long arr_stride) {
   const bool store = cov == nullptr;  // the coverage pass must not disturb the (possibly trimmed) break list
   int nb = 0;
@@ -160,7 +154,7 @@ __device__ void serial_walk(const DevCfg& c, const uint32_t* refw, const BatchDe
       case 1: readPos += len; break;
       case 0:
         for (int i = 0; i < len && refPos + i < G; i++) {
-          bool m = ref_base(refw, (uint32_t)(refPos + i)) == read_base(rc.wread, rc.nib0 + (uint32_t)(readPos + i), rc.lastw);
+          bool m = ref_base(refw, (uint32_t)(refPos + i)) == read_base(rc.wread, rc.nib0 + (uint32_t)(readPos + i));
           add(refPos + i + 1, m);
         }
         readPos += len; refPos += len;
@@ -184,7 +178,7 @@ __device__ void serial_walk(const DevCfg& c, const uint32_t* refw, const BatchDe
 }
 
 // htsjdk getReadPositionAtReferencePosition over alignment blocks (lane 0)
-__device__ int serial_read_pos(const BatchDev& b, const ReadCtx& rc, int pos) {
+__device__ __noinline__ int serial_read_pos(const BatchDev& b, const ReadCtx& rc, int pos) {
   if (pos <= 0) return 0;
   int readBase = 1, refBase = rc.alnStart;
   for (uint32_t k = rc.c0; k < rc.c1; k++) {
@@ -202,30 +196,150 @@ __device__ int serial_read_pos(const BatchDev& b, const ReadCtx& rc, int pos) {
 }
 
 // ------------------------------------------------------------------------------------------------ fast warp walker
-// Returns false when the read must be re-walked serially.  Breaks land in ws->br, coverage events in ws->ev.
-template <bool REF_SMEM, int SINK>
-__device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws, unsigned lane,
-                          const CovSink sk) {
-  const int T = c.T, G = c.G;
-  constexpr bool depth = SINK != 0;
-  constexpr bool store_br = SINK != 2;  // the direct coverage pass must not disturb the (possibly trimmed) break list
-  const unsigned lt = lanemask_lt();
-  int refBase = rc.alnStart - 1, readBase = 0;
-  int prev = rc.alnStart;
-  int nb = 1;
-  if (store_br && lane == 0) ws->br[0] = rc.alnStart;
-  int maps = 0, errs = 0;
+// Per 32-op chunk: (1) lane = op: decode, warp scans give every op its reference/read offset; M ops publish a descriptor
+// to shared memory.  (2) lane = 8-base window: the chunk's M bases are cut into windows dealt round-robin to the lanes, so
+// the compare runs with (almost) all lanes busy whatever the op lengths are.  (3) lane = op again: depth runs as
+// difference events.  All staging offsets are warp-uniform (ballot + popc), no shared atomics.
+//
+// Two tiers per chunk.  Tier 1 (hot): when every window holds at least one match, consecutive matches are at most 15
+// apart inside an op, so with breakThresh >= 16 a break / mapStart / mapEnd event needs an op whose first possible match
+// lies > T past the previous op's last possible match — a purely geometric test (ballot).  Chunks that pass it skip the
+// per-op first/last-match machinery altogether.  Tier 2 (chunk_exact, not inlined): chunks with a candidate junction, a
+// window without a match, an '=' op or a small breakThresh get the exact segmented first/last-match computation.
+struct WalkOut { int nev, nmm, ovf; };
+struct WalkState { int prev, nb, nev, ovf; bool slow; };
+
+// sink 0: no coverage events; 1: shared-memory staging; 2: straight to the cluster's rows (also: do not touch ws->br)
+__device__ __noinline__ void chunk_exact(const DevCfg& c, const uint32_t* refw, const ReadCtx& rc, WarpScratch* ws, const unsigned lane,
+                                         const int sink, const CovSink sk, const int op, const int nE, const int base, const bool isM,
+                                         const int mrank, const int W, const int wStart, WalkState& st) {
+  const int T = c.T;
+  const unsigned lt = lanemask_lt(), le = lanemask_le();
+  if (isM) { ws->m_fm[mrank] = -1; ws->m_lm[mrank] = -1; }
+  __syncwarp();
   bool slow = false;
+  int headsBefore = 0;
+  for (int r0 = 0; r0 < W; r0 += 32) {
+    const int v = r0 + (int)lane;
+    const bool wv = v < W;
+    const unsigned hbit = (isM && wStart >= r0 && wStart < r0 + 32) ? 1u << (wStart - r0) : 0u;
+    const unsigned heads = __reduce_or_sync(0xffffffffu, hbit);
+    const int mr = max(0, headsBefore + __popc(heads & le) - 1);
+    headsBefore += __popc(heads);
+    uint32_t mis = 0, mat = 0;
+    int j8 = 0;
+    if (wv) {
+      const int d_start0 = ws->m_start0[mr], d_rpos0 = ws->m_rpos0[mr], d_nE = ws->m_nE[mr];
+      j8 = (v - ws->m_wstart[mr]) << 3;
+      const int cnt = min(8, d_nE - j8);
+      cmp8(read_win8(rc.wread, rc.nib0 + (uint32_t)(d_rpos0 + j8)), ref_win8(refw, (uint32_t)(d_start0 + j8)), cnt, mis, mat);
+    }
+    // per-op first / last match through segments of equal op
+    const bool hasMat = mat != 0;
+    const int f = j8 + (__clz(mat | 1u) >> 2);
+    const int l = j8 + 7 - ((__ffs(mat | 0x80000000u) - 1) >> 2);
+    const unsigned matMask = __ballot_sync(0xffffffffu, hasMat);
+    const unsigned segHeads = heads | 1u;
+    const int a = 31 - __clz(segHeads & le);
+    const unsigned above = segHeads & ~le;
+    const unsigned upto = above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu;
+    const unsigned segMask = upto & ~((1u << a) - 1u);
+    const unsigned sm = matMask & segMask;
+    const int fmSeg = __shfl_sync(0xffffffffu, f, sm ? __ffs(sm) - 1 : (int)lane);
+    const int lmSeg = __shfl_sync(0xffffffffu, l, sm ? 31 - __clz(sm) : (int)lane);
+    const unsigned pm = sm & lt;
+    const int lprev = __shfl_sync(0xffffffffu, l, pm ? 31 - __clz(pm) : (int)lane);
+    if (hasMat) {
+      const int pl = pm ? lprev : ws->m_lm[mr];  // last match of this op before this window (earlier rounds via shared)
+      if (pl >= 0 && f - pl > T) slow = true;     // a gap > T inside one op: serial walker
+    }
+    __syncwarp();
+    if (wv && (int)lane == a && sm) {
+      if (ws->m_fm[mr] < 0) ws->m_fm[mr] = fmSeg;
+      ws->m_lm[mr] = lmSeg;
+    }
+    __syncwarp();
+  }
+  int fmI = -1, lmI = -1;
+  if (isM) { fmI = ws->m_fm[mrank]; lmI = ws->m_lm[mrank]; }
+  if (op == 7 && nE > 0) { fmI = 0; lmI = nE - 1; }
+  const bool has = fmI >= 0;
+  const int fm = base + fmI, lm = base + lmI;
+  // last matched position before this op (prev_position of CigarCluster.add at the op's first base)
+  const unsigned hasMask = __ballot_sync(0xffffffffu, has);
+  const unsigned lowerH = hasMask & lt;
+  const int lmPrev = __shfl_sync(0xffffffffu, lm, lowerH ? 31 - __clz(lowerH) : (int)lane);
+  const int prev_j = lowerH ? lmPrev : st.prev;
+  // breaks: first match of the op further than T from the previous match
+  const bool brk = has && (fm - prev_j > T);
+  const unsigned bm = __ballot_sync(0xffffffffu, brk);
+  if (bm) {
+    const int o = st.nb + 2 * __popc(bm & lt);
+    if (sink != 2 && brk && o + 1 < MAXB) { ws->br[o] = prev_j; ws->br[o + 1] = fm; }
+    st.nb += 2 * __popc(bm);
+  }
+  if (hasMask) st.prev = __shfl_sync(0xffffffffu, lm, 31 - __clz(hasMask));
+  if (__any_sync(0xffffffffu, slow)) st.slow = true;
+  if (sink != 0) {
+    // mapStart / mapEnd (CigarCluster.add :479-484): every emitted position further than T from the last match before it.
+    // lead: positions up to and including the op's first match, against prev_j; trail: positions after the op's last match.
+    for (int pass = 0; pass < 2; pass++) {
+      int lo = 0, n = 0, pj = 0;
+      if (nE > 0) {
+        if (pass == 0) {
+          const int hi = has ? fmI : nE - 1;
+          lo = max(0, T + prev_j - base + 1);
+          if (lo <= hi) n = hi - lo + 1;
+          pj = prev_j;
+        } else if (has) {
+          lo = lmI + T + 1;
+          if (lo <= nE - 1) n = nE - lo;
+          pj = lm;
+        }
+      }
+      unsigned msMask = __ballot_sync(0xffffffffu, n > 0);
+      while (msMask) {
+        const int Lm = __ffs(msMask) - 1;
+        msMask &= msMask - 1;
+        const int p0 = __shfl_sync(0xffffffffu, base + lo, Lm), nn = __shfl_sync(0xffffffffu, n, Lm);
+        const int pp = __shfl_sync(0xffffffffu, pj, Lm);
+        if (sink == 1) {
+          if (st.nev + 2 * nn > MAXEV) st.ovf = 1;
+          else for (int i = lane; i < nn; i += 32) { ws->ev[st.nev + 2 * i] = (EV_MSTART << 29) | (unsigned)(p0 + i); ws->ev[st.nev + 2 * i + 1] = (EV_MEND << 29) | (unsigned)pp; }
+          st.nev += 2 * nn;
+        } else {
+          for (int i = lane; i < nn; i += 32) { atomicAdd(sk.cov + 2 * sk.arr_stride + p0 + i, 1); atomicAdd(sk.cov + 3 * sk.arr_stride + pp, 1); }
+        }
+      }
+    }
+  }
+}
+
+// Returns false when the read must be re-walked serially.  Breaks land in ws->br, coverage events in ws->ev / ws->mm_*.
+__device__ __noinline__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev& b, ReadCtx& rc, WarpScratch* ws,
+                                       const unsigned lane, const int sink, const CovSink sk, WalkOut& wo) {
+  const int T = c.T, G = c.G;
+  const bool depth = sink != 0;
+  const bool tier1 = T >= 16;
+  const unsigned lt = lanemask_lt(), le = lanemask_le();
+  int refBase = rc.alnStart - 1, readBase = 0;
+  WalkState st{rc.alnStart, 1, 0, 0, false};
+  if (sink != 2 && lane == 0) ws->br[0] = rc.alnStart;
+  int maps = 0, errs = 0;
   bool stFound = false; int st_r = 0;
-  int endMax = INT_MIN, endBs = 0, endRs = 0;
+  int kBs = 0, kRs = 0, kEnd = INT_MIN, lastBlkLane = -1;  // per-lane copy of the last chunk that held an alignment block
   int pendingEnd = -1;  // depth run end (exclusive) of the last emitting op, not yet written as an event
+  int nmm = 0;
 
   for (uint32_t k0 = rc.c0; k0 < rc.c1; k0 += 32) {
     const uint32_t k = k0 + lane;
     const bool valid = k < rc.c1;
     const uint32_t w = valid ? __ldg(b.cigar + k) : 5u;
     const int len = (int)(w >> 4), op = (int)(w & 15);
-    if (__any_sync(0xffffffffu, op > 8)) { rc.bad = true; return true; }
+    const bool isBlk = valid && (op == 0 || op == 7 || op == 8);
+    // bad op -> the reference throws; zero-length M/=/X -> let the serial walker decide the alignment-block corner cases
+    const unsigned odd = __ballot_sync(0xffffffffu, op > 8 || (isBlk && len == 0));
+    if (odd) { if (__any_sync(0xffffffffu, op > 8)) { rc.bad = true; return true; } return false; }
     const int refAdv = ((0x18D >> op) & 1) ? len : 0;   // M D N = X
     const int readAdv = ((0x193 >> op) & 1) ? len : 0;  // M I S = X
     const int ri = warp_incl_scan(refAdv, lane), qi = warp_incl_scan(readAdv, lane);
@@ -236,175 +350,144 @@ __device__ bool fast_walk(const DevCfg& c, const uint32_t* refw, const BatchDev&
     const int start0 = (op == 0) ? refPos0 : refPos0 + len;  // 0-based index of the first emitted reference base
     const int nE = emits ? max(0, min(len, G - start0)) : 0;
     const int base = start0 + 1;
+    const bool em = nE > 0;
 
-    int fmI = -1, lmI = -1, nmis = 0;
-    const bool isM = (op == 0) && nE > 0;
-    if (isM && nE <= LONGOP) {
-      for (int j8 = 0; j8 < nE; j8 += 8) {
-        const int cnt = min(8, nE - j8);
-        const uint32_t rw = read_win8(rc.wread, rc.nib0 + (uint32_t)(readPos0 + j8), rc.lastw);
-        const uint32_t gw = ref_win8(refw, (uint32_t)(start0 + j8));
-        uint32_t mis, mat;
-        cmp8(rw, gw, cnt, mis, mat);
-        nmis += __popc(mis);
-        if (mat) {
-          const int f = j8 + (__clz(mat) >> 2);
-          if (fmI < 0) fmI = f; else if (f - lmI > T) slow = true;
-          lmI = j8 + 7 - ((__ffs(mat) - 1) >> 2);
-        }
-        if (depth && mis) emit_mismatches<SINK>(ws, sk, mis, base + j8);
-      }
-    }
+    // ---- (2) balanced compare of the chunk's M bases
+    const bool isM = (op == 0) && em;
+    const int nW = isM ? (nE + 7) >> 3 : 0;
+    const int wEnd = warp_incl_scan(nW, lane);
+    const int W = __shfl_sync(0xffffffffu, wEnd, 31);
+    const int wStart = wEnd - nW;
+    const unsigned mMask = __ballot_sync(0xffffffffu, isM);
+    const int mrank = __popc(mMask & lt);
+    if (isM) { ws->m_start0[mrank] = start0; ws->m_rpos0[mrank] = readPos0; ws->m_nE[mrank] = nE; ws->m_wstart[mrank] = wStart; }
     __syncwarp();
-    unsigned longMask = __ballot_sync(0xffffffffu, isM && nE > LONGOP);
-    while (longMask) {
-      const int L = __ffs(longMask) - 1;
-      longMask &= longMask - 1;
-      const int startL = __shfl_sync(0xffffffffu, start0, L), rposL = __shfl_sync(0xffffffffu, readPos0, L);
-      const int nEL = __shfl_sync(0xffffffffu, nE, L);
-      int fmL = -1, lmL = -1, nmisL = 0;
-      for (int jb = 0; jb < nEL; jb += 256) {
-        const int j8 = jb + (int)lane * 8;
-        const int cnt = max(0, min(8, nEL - j8));
-        uint32_t mis = 0, mat = 0;
-        if (cnt > 0) {
-          const uint32_t rw = read_win8(rc.wread, rc.nib0 + (uint32_t)(rposL + j8), rc.lastw);
-          const uint32_t gw = ref_win8(refw, (uint32_t)(startL + j8));
-          cmp8(rw, gw, cnt, mis, mat);
-        }
-        nmisL += __popc(mis);
-        if (depth && mis) emit_mismatches<SINK>(ws, sk, mis, startL + 1 + j8);
-        __syncwarp();
-        const unsigned mm = __ballot_sync(0xffffffffu, mat != 0);
-        if (mm) {
-          const int f = j8 + (__clz(mat | 1u) >> 2);          // meaningful only where mat != 0
-          const int l = j8 + 7 - ((__ffs(mat | 0x80000000u) - 1) >> 2);
-          const unsigned lower = mm & lt;
-          const int pl_s = __shfl_sync(0xffffffffu, l, lower ? 31 - __clz(lower) : (int)lane);
-          const int pl = lower ? pl_s : lmL;
-          if (mat && pl >= 0 && f - pl > T) slow = true;
-          const int f0 = __shfl_sync(0xffffffffu, f, __ffs(mm) - 1);
-          if (fmL < 0) fmL = f0;
-          lmL = __shfl_sync(0xffffffffu, l, 31 - __clz(mm));
+    int headsBefore = 0;
+    bool noMatch = false;
+    uint32_t mat = 0; int j8 = 0, d_start0 = 0;  // of this lane's window in the last round (for the exact prev carry)
+    for (int r0 = 0; r0 < W; r0 += 32) {
+      const int v = r0 + (int)lane;
+      const unsigned hbit = (isM && wStart >= r0 && wStart < r0 + 32) ? 1u << (wStart - r0) : 0u;
+      const unsigned heads = __reduce_or_sync(0xffffffffu, hbit);
+      const int mr = max(0, headsBefore + __popc(heads & le) - 1);
+      headsBefore += __popc(heads);
+      uint32_t mis = 0;
+      mat = 0;
+      if (v < W) {
+        d_start0 = ws->m_start0[mr];
+        const int d_rpos0 = ws->m_rpos0[mr], d_nE = ws->m_nE[mr];
+        j8 = (v - ws->m_wstart[mr]) << 3;
+        const int cnt = min(8, d_nE - j8);
+        cmp8(read_win8(rc.wread, rc.nib0 + (uint32_t)(d_rpos0 + j8)), ref_win8(refw, (uint32_t)(d_start0 + j8)), cnt, mis, mat);
+        noMatch |= mat == 0;
+      }
+      errs += __popc(mis);
+      if (depth) {
+        const unsigned hm = __ballot_sync(0xffffffffu, mis != 0);
+        if (hm) {
+          if (sink == 1) {
+            const int o = nmm + __popc(hm & lt);
+            if (mis && o < MAXMM) { ws->mm_pos[o] = (unsigned)(d_start0 + 1 + j8); ws->mm_mask[o] = mis; }
+            nmm += __popc(hm);
+          } else if (mis) {
+            red_error_window(sk.cov + sk.arr_stride, (unsigned)(d_start0 + 1 + j8), mis);
+          }
         }
       }
-      nmisL = __reduce_add_sync(0xffffffffu, nmisL);
-      if ((int)lane == L) { fmI = fmL; lmI = lmL; nmis = nmisL; }
     }
-    if (op == 7 && nE > 0) { fmI = 0; lmI = nE - 1; }
-    if (op == 2 || op == 8) nmis = nE;
-    const bool has = fmI >= 0;
-    const int fm = base + fmI, lm = base + lmI;
 
-    // last matched position before this op (prev_position of CigarCluster.add at the op's first base)
-    const unsigned hasMask = __ballot_sync(0xffffffffu, has);
-    const unsigned lowerH = hasMask & lt;
-    const int lmPrev = __shfl_sync(0xffffffffu, lm, lowerH ? 31 - __clz(lowerH) : (int)lane);
-    const int prev_j = lowerH ? lmPrev : prev;
-
-    // breaks: first match of the op further than T from the previous match
-    const bool brk = has && (fm - prev_j > T);
-    const unsigned bm = __ballot_sync(0xffffffffu, brk);
-    if (bm) {
-      const int o = nb + 2 * __popc(bm & lt);
-      if (store_br && brk && o + 1 < MAXB) { ws->br[o] = prev_j; ws->br[o + 1] = fm; }
-      nb += 2 * __popc(bm);
+    // ---- tier decision: can this chunk hold a break or a mapStart/mapEnd event?
+    const unsigned lowerM = mMask & lt;
+    const int E_j = base + nE;
+    const int eprev = __shfl_sync(0xffffffffu, E_j, lowerM ? 31 - __clz(lowerM) : (int)lane);
+    const int lb = lowerM ? eprev - 8 : st.prev;                       // the previous match is at or after this position
+    const int ub = isM ? base + min(7, nE - 1) : base + nE - 1;        // the next match / far non-match is at or before this one
+    const bool cand = em && (ub - lb > T);
+    if (!tier1 || __any_sync(0xffffffffu, cand || noMatch || (op == 7 && valid))) {
+      chunk_exact(c, refw, rc, ws, lane, sink, sk, op, nE, base, isM, mrank, W, wStart, st);
+    } else if (W > 0) {
+      // every window matched somewhere: the chunk's last match is the last match of its last window
+      const int lpos = d_start0 + 1 + j8 + 7 - ((__ffs(mat | 0x80000000u) - 1) >> 2);
+      st.prev = __shfl_sync(0xffffffffu, lpos, (W - 1) & 31);
     }
-    if (hasMask) prev = __shfl_sync(0xffffffffu, lm, 31 - __clz(hasMask));
-    maps += nE; errs += nmis;
 
+    // ---- (3) per-op stage: depth runs, D/X error windows, alignment-block bookkeeping
+    const bool dx = (op == 2 || op == 8) && em;  // every emitted position of D / X is an error
+    if (dx) errs += nE;
+    maps += nE;
     if (depth) {
       // depth runs as difference events, cancelling "end of previous run == start of this run"
-      const bool em = nE > 0;
-      const int S_j = base, E_j = base + nE;
       const unsigned emMask = __ballot_sync(0xffffffffu, em);
       const unsigned lowerE = emMask & lt;
       const int pe_s = __shfl_sync(0xffffffffu, E_j, lowerE ? 31 - __clz(lowerE) : (int)lane);
       const int prevE = lowerE ? pe_s : pendingEnd;
-      const bool emitStart = em && prevE != S_j;
-      int ne = emitStart ? (prevE >= 0 ? 2 : 1) : 0;
-      // D / X ops: every emitted position is an error
-      const int nerr = (op == 2 || op == 8) ? nE : 0;
-      // mapStart / mapEnd: emitted positions up to and including the first match that are > T past prev_j
-      int ms_lo = 0, ms_n = 0;
-      if (em) {
-        const int hi = has ? fmI : nE - 1;
-        const int lo = max(0, T + prev_j - base + 1);
-        if (lo <= hi) { ms_lo = lo; ms_n = hi - lo + 1; }
-      }
-      const int tot = ne + nerr + 2 * ms_n;
-      if (SINK == 1) {
-        if (tot) {
-          int o = ev_reserve(ws, tot);
-          if (o >= 0) {
-            if (emitStart) {
-              if (prevE >= 0) ws->ev[o++] = (EV_DEPTH_DEC << 29) | (unsigned)prevE;
-              ws->ev[o++] = (EV_DEPTH_INC << 29) | (unsigned)S_j;
-            }
-            for (int i = 0; i < nerr; i++) ws->ev[o++] = (EV_ERR << 29) | (unsigned)(base + i);
-            for (int i = 0; i < ms_n; i++) {
-              ws->ev[o++] = (EV_MSTART << 29) | (unsigned)(base + ms_lo + i);
-              ws->ev[o++] = (EV_MEND << 29) | (unsigned)prev_j;
-            }
-          }
-        }
-      } else if (SINK == 2) {
-        if (emitStart) {
-          if (prevE >= 0) atomicAdd(sk.cov + prevE, -1);
-          atomicAdd(sk.cov + S_j, 1);
-        }
-        for (int i = 0; i < nerr; i++) atomicAdd(sk.cov + sk.arr_stride + base + i, 1);
-        for (int i = 0; i < ms_n; i++) {
-          atomicAdd(sk.cov + 2 * sk.arr_stride + base + ms_lo + i, 1);
-          atomicAdd(sk.cov + 3 * sk.arr_stride + prev_j, 1);
-        }
-      }
+      const bool emitStart = em && prevE != base;
       if (emMask) pendingEnd = __shfl_sync(0xffffffffu, E_j, 31 - __clz(emMask));
+      const unsigned sMask = __ballot_sync(0xffffffffu, emitStart);
+      if (sMask) {
+        if (sink == 1) {
+          // two slots per run start: [-1 at the previous run's end] [+1 at this run's start]; the very first run of a read has
+          // no previous end and writes a +0 no-op (EV_DEPTH_INC at position 0 is never read: rows start at position 1 ... see flush)
+          const int o = st.nev + 2 * __popc(sMask & lt);
+          if (emitStart && o + 1 < MAXEV) {
+            ws->ev[o] = prevE >= 0 ? ((EV_DEPTH_DEC << 29) | (unsigned)prevE) : (7u << 29);
+            ws->ev[o + 1] = (EV_DEPTH_INC << 29) | (unsigned)base;
+          }
+          st.nev += 2 * __popc(sMask);
+        } else if (emitStart) {
+          if (prevE >= 0) atomicAdd(sk.cov + prevE, -1);
+          atomicAdd(sk.cov + base, 1);
+        }
+      }
+      const unsigned dxMask = __ballot_sync(0xffffffffu, dx);
+      if (dxMask) {
+        if (sink == 1) {
+          if (__any_sync(0xffffffffu, dx && nE > 8)) st.ovf = 1;  // long deletions are rare: direct pass
+          const int o = nmm + __popc(dxMask & lt);
+          if (dx && nE <= 8 && o < MAXMM) { ws->mm_pos[o] = (unsigned)base; ws->mm_mask[o] = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); }
+          nmm += __popc(dxMask);
+        } else if (dx) {
+          for (int i = 0; i < nE; i++) atomicAdd(sk.cov + sk.arr_stride + base + i, 1);
+        }
+      }
     }
-
-    // read offsets of alignment start / end (htsjdk alignment blocks = M,=,X elements)
-    const bool isBlk = valid && (op == 0 || op == 7 || op == 8);
-    const int bStart = refPos0 + 1, bEnd = refPos0 + len, rStart = readPos0 + 1;
-    if (!stFound) {
-      const unsigned m = __ballot_sync(0xffffffffu, isBlk && bEnd >= rc.alnStart);
-      if (m) {
-        const int l = __ffs(m) - 1;
-        const int bs = __shfl_sync(0xffffffffu, bStart, l), rs = __shfl_sync(0xffffffffu, rStart, l);
-        st_r = rc.alnStart < bs ? 0 : rc.alnStart - bs + rs;
+    // read offsets of alignment start / end (htsjdk alignment blocks = M,=,X elements; all have len > 0 here)
+    const unsigned blkMask = __ballot_sync(0xffffffffu, isBlk);
+    if (blkMask) {
+      const int bStart = refPos0 + 1, rStart = readPos0 + 1;
+      if (!stFound) {
+        const int l0 = __ffs(blkMask) - 1;
+        const int bs = __shfl_sync(0xffffffffu, bStart, l0), rs = __shfl_sync(0xffffffffu, rStart, l0);
+        st_r = (bs == rc.alnStart) ? rs : 0;  // first block: its end >= alnStart always; 0 if the read starts with D/N
         stFound = true;
       }
-    }
-    {
-      const int v = isBlk ? bEnd : INT_MIN;
-      const int mx = __reduce_max_sync(0xffffffffu, v);
-      if (mx > endMax) {
-        endMax = mx;
-        const int l = __ffs(__ballot_sync(0xffffffffu, isBlk && bEnd == mx)) - 1;
-        endBs = __shfl_sync(0xffffffffu, bStart, l);
-        endRs = __shfl_sync(0xffffffffu, rStart, l);
-      }
+      kBs = bStart; kRs = rStart; kEnd = refPos0 + len; lastBlkLane = 31 - __clz(blkMask);
     }
   }
   __syncwarp();
-  if (__any_sync(0xffffffffu, slow)) return false;
-  if (nb + 1 > MAXB) return false;  // let the serial path report it
+  if (st.slow) return false;
+  if (st.nb + 1 > MAXB) return false;  // let the serial path report it
   rc.alnEnd = refBase;
-  if (store_br && lane == 0) ws->br[nb] = rc.alnEnd;
-  nb++;
-  if (depth && pendingEnd >= 0 && lane == 0) {
-    if (SINK == 1) {
-      int o = ev_reserve(ws, 1);
-      if (o >= 0) ws->ev[o] = (EV_DEPTH_DEC << 29) | (unsigned)pendingEnd;
-    } else if (SINK == 2) {
-      atomicAdd(sk.cov + pendingEnd, -1);
-    }
+  if (sink != 2 && lane == 0) ws->br[st.nb] = rc.alnEnd;
+  st.nb++;
+  if (depth && pendingEnd >= 0) {
+    if (sink == 1) { if (lane == 0 && st.nev < MAXEV) ws->ev[st.nev] = (EV_DEPTH_DEC << 29) | (unsigned)pendingEnd; st.nev++; }
+    else if (lane == 0) atomicAdd(sk.cov + pendingEnd, -1);
   }
+  if (sink == 1 && (st.nev > MAXEV - 2 || nmm > MAXMM)) st.ovf = 1;
   __syncwarp();
-  rc.nb = nb;
+  wo.nev = st.nev; wo.nmm = nmm; wo.ovf = st.ovf;
+  rc.nb = st.nb;
   rc.maps_sum = __reduce_add_sync(0xffffffffu, maps);
   rc.err_sum = __reduce_add_sync(0xffffffffu, errs);
-  rc.st_r = (rc.alnStart <= 0) ? 0 : st_r;
-  rc.end_r = (rc.alnEnd > 0 && endMax == rc.alnEnd) ? (rc.alnEnd < endBs ? 0 : rc.alnEnd - endBs + endRs) : 0;
+  rc.st_r = st_r;
+  int end_r = 0;
+  if (lastBlkLane >= 0) {
+    const int bs = __shfl_sync(0xffffffffu, kBs, lastBlkLane), rs = __shfl_sync(0xffffffffu, kRs, lastBlkLane);
+    const int be = __shfl_sync(0xffffffffu, kEnd, lastBlkLane);
+    if (rc.alnEnd > 0 && be == rc.alnEnd) end_r = rc.alnEnd - bs + rs;  // the last block reaches alnEnd unless the read ends with D/N
+  }
+  rc.end_r = end_r;
   return true;
 }
 
@@ -586,7 +669,7 @@ __device__ void pair_add(const DevCfg& c, int src, int level, int st, int en) {
 // ------------------------------------------------------------------------------------------------ the kernel
 // mode 0: full pass.  mode 1: re-emit breaks only at exact offsets (b.break_loc holds the exclusive scan; no side effects).
 template <bool REF_SMEM>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) walk_kernel(const DevCfg c, const BatchDev b, const int mode) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3) walk_kernel(const DevCfg c, const BatchDev b, const int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_ref = (uint32_t*)smem_raw;
   const int refw_n = REF_SMEM ? c.ref_nwords : 0;
@@ -622,26 +705,26 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) walk_kernel(const DevCfg
     const long long lw = total_words - 1 - (long long)(so >> 2);
     rc.lastw = (uint32_t)max(0LL, min(lw, 0xFFFFFFFFLL));
     rc.bad = false; rc.nb = 0; rc.maps_sum = 0; rc.err_sum = 0; rc.st_r = 0; rc.end_r = 0; rc.alnEnd = 0;
-    if (lane == 0) { ws->nev = 0; ws->ev_ovf = 0; }
     __syncwarp();
 
     // coverage plan: short reads stage their events in shared memory during the walk; reads that could overflow the
     // staging buffer are walked without events first and a second time, straight into the cluster's rows, once the
     // cluster is known (their CIGAR and bases are L1/L2-resident by then).
     const CovSink nosink{nullptr, 0};
-    bool direct_cov = c.record_depth && (rc.c1 - rc.c0) * 2u > (unsigned)MAXEV;
-    bool serial = c.force_serial || rc.alnStart <= 0;
-    if (!serial) {
+    WalkOut wo{0, 0, 0};
+    bool direct_cov = c.record_depth && (rc.c1 - rc.c0) > 520u;
+    if (rc.alnStart <= 0) rc.bad = true;  // not a mapped record
+    bool serial = c.force_serial;
+    if (!serial && !rc.bad) {
       if (c.record_depth && !direct_cov) {
-        serial = !fast_walk<REF_SMEM, 1>(c, refw, b, rc, ws, lane, nosink);
-        if (!serial && *(volatile int*)&ws->ev_ovf) direct_cov = true;
+        serial = !fast_walk(c, refw, b, rc, ws, lane, 1, nosink, wo);
+        if (!serial && wo.ovf) direct_cov = true;
       } else {
-        serial = !fast_walk<REF_SMEM, 0>(c, refw, b, rc, ws, lane, nosink);
+        serial = !fast_walk(c, refw, b, rc, ws, lane, 0, nosink, wo);
       }
     }
     if (serial && !rc.bad) {
       if (lane == 0) {
-        ws->nev = 0; ws->ev_ovf = 0;
         serial_walk(c, refw, b, rc, ws, nullptr, 0);
         if (!rc.bad) { rc.st_r = serial_read_pos(b, rc, rc.alnStart); rc.end_r = serial_read_pos(b, rc, rc.alnEnd); }
       }
@@ -804,19 +887,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) walk_kernel(const DevCfg
           __syncwarp();
         } else if (direct_cov) {
           ReadCtx rc2 = rc;
-          fast_walk<REF_SMEM, 2>(c, refw, b, rc2, ws, lane, CovSink{cov, arr_stride});
+          WalkOut wo2{0, 0, 0};
+          fast_walk(c, refw, b, rc2, ws, lane, 2, CovSink{cov, arr_stride}, wo2);
         } else {
-          const int nev = *(volatile int*)&ws->nev;
-          for (int i = lane; i < nev; i += 32) {
+          for (int i = lane; i < wo.nev; i += 32) {
             const unsigned ev = ws->ev[i];
             const unsigned t = ev >> 29, p = ev & EV_POS_MASK;
+            if (t == 7u) continue;  // filler slot of a read's first depth run
             const int arr = t <= EV_DEPTH_DEC ? 0 : (int)t - 1;
             atomicAdd(cov + arr * arr_stride + p, t == EV_DEPTH_DEC ? -1 : 1);
           }
+          for (int i = lane; i < wo.nmm; i += 32) red_error_window(cov + arr_stride, ws->mm_pos[i], ws->mm_mask[i]);
         }
         // CigarCluster.setStartEnd :360-365 (uses the trimmed startPos/endPos)
-        if (lane == 0) atomicAdd(cov + 2 * arr_stride + startPos, 1);
-        if (lane == 1) atomicAdd(cov + 3 * arr_stride + endPos, 1);
+        // (positions beyond seqlen+1 only arise from alignments running past the reference end; dense rows drop them)
+        if (lane == 0 && startPos >= 0 && startPos < c.stride) atomicAdd(cov + 2 * arr_stride + startPos, 1);
+        if (lane == 1 && endPos >= 0 && endPos < c.stride) atomicAdd(cov + 3 * arr_stride + endPos, 1);
       }
     }
 

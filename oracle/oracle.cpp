@@ -214,6 +214,7 @@ void per_read(const Cfg& cfg, const Annot& annot, const uint8_t* ref, int64_t re
   s.clear();
   o = ReadOut();
   int alnEnd = 0;
+  if (alnStart <= 0) return;  // unmapped-style record: the caller's filter chain drops these (ViralTranscriptAnalysisCmd2.java:716)
   if (!process_cigar(s, cfg, alnStart, cig, nc, seq4, ref, refLen, &alnEnd)) return;
   o.ok = true;
   // :634-635
@@ -446,8 +447,10 @@ void commit(Run& R, const ReadOut& o, const Scratch& s, int src) {
       for (size_t i = 0; i < s.ev_pos.size(); i++) { d[s.ev_pos[i]] += 1; if (!s.ev_match[i]) e[s.ev_pos[i]] += 1; }
       int* ms = c->mapStart.data() + (size_t)src * R.stride;
       int* me = c->mapEnd.data() + (size_t)src * R.stride;
-      for (int p : s.ms_pos) ms[p] += 1;
-      for (int p : s.me_pos) me[p] += 1;
+      // Dense rows hold positions 0..seqlen+1.  An alignment that runs past the end of the reference (invalid SAM) can put
+      // its start/end beyond that; the reference's sparse TreeMap would keep such a key, the dense rows drop it.
+      for (int p : s.ms_pos) if (p >= 0 && p < R.stride) ms[p] += 1;
+      for (int p : s.me_pos) if (p >= 0 && p < R.stride) me[p] += 1;
     }
   }
   if (R.keep_reads) {

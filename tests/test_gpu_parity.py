@@ -5,12 +5,13 @@ import pytest
 from nptranscript_b200 import abi, engine, synth, workloads
 from oracle import oracle
 from tests.common import assert_same
+from tests.fuzz import random_batch
 
 pytestmark = pytest.mark.gpu
 
 
-def _both(cfg_kw, w, batches, annotation=None, chrom_index=0):
-    g = synth.genome_codes(w)
+def _both(cfg_kw, w, batches, annotation=None, chrom_index=0, genome=None):
+    g = synth.genome_codes(w) if genome is None else genome
     ann = annotation or w.annotation
     dev = engine.run(engine.make_config(**cfg_kw), g, ann, batches, chrom_index)
     ora = oracle.run(oracle.make_config(**cfg_kw), g, ann, batches, chrom_index)
@@ -30,4 +31,77 @@ def test_multi_batch_and_sources():
     w = workloads.HCOV229E
     bs = [synth.generate(w, 20200310 + k, 5000, first_index=0, num_sources=4, src_fixed=k) for k in range(4)]
     dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1, num_sources=4), w, bs)
+    assert_same(dev, ora)
+
+
+def test_eqx_cigars():
+    w = workloads.SARS2
+    b = synth.generate(w, 5, 8000, use_eqx=True)
+    dev, ora = _both(dict(bin=100, break_thresh=500, record_depth=1), w, [b])
+    assert_same(dev, ora)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(bin=10, break_thresh=1000, record_depth=1),
+    dict(bin=1, break_thresh=50, record_depth=1),
+    dict(bin=100, break_thresh=8, record_depth=1),
+    dict(bin=7, break_thresh=3, record_depth=1),            # breakThresh < 8: exact serial device walker
+    dict(bin=10, break_thresh=1000, record_depth=0, include_start=0),
+    dict(bin=10, break_thresh=1000, record_depth=1, enforce_strand=1),
+    dict(bin=10, break_thresh=200, record_depth=1, start_thresh=30, end_thresh=500),
+    dict(bin=10, break_thresh=40000, record_depth=1),       # breakThresh >= seqlen: no break-point matrix
+])
+def test_fuzz_virus(kw):
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(1234 + kw["bin"] + kw["break_thresh"])
+    small_t = kw["break_thresh"] < 8  # keep reads under the 256-breaks-per-read limit
+    bs = [random_batch(rng, 1500, w.genome_len, g, num_sources=3, long_reads=(i == 1 and not small_t), max_ops=12 if small_t else 60)
+          for i in range(3)]
+    dev, ora = _both(dict(kw, num_sources=3, max_coverage_clusters=4096), w, bs)
+    assert_same(dev, ora)
+
+
+def test_fuzz_bad_ops():
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(99)
+    bs = [random_batch(rng, 2000, w.genome_len, g, bad_op=0.01)]
+    dev, ora = _both(dict(bin=10, break_thresh=300, record_depth=1), w, bs)
+    assert (ora["read_flags"] & abi.NPT_RF_BADCIGAR).any()
+    assert_same(dev, ora)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1]),
+    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[0, 1]),
+    dict(bin=10, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, rna=[1, 0]),
+])
+def test_fuzz_host_mode_empty_annotation(kw):
+    """Host mode (opts_host.txt flag set minus firstIsTranscriptome) with EmptyAnnotation: chr.bin keys, exon trimming."""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(7)
+    bs = [random_batch(rng, 2000, w.genome_len, g, num_sources=2, big_n=300)]
+    dev, ora = _both(dict(kw, num_sources=2), w, bs, annotation=workloads.Annotation.empty(), chrom_index=3)
+    assert_same(dev, ora)
+
+
+def test_small_tables_report_capacity():
+    w = workloads.SARS2
+    b = synth.generate(w, 1, 5000)
+    with pytest.raises(engine.NptError) as e:
+        engine.run(engine.make_config(bin=1, break_thresh=1000, max_subclusters=64), synth.genome_codes(w), w.annotation, [b])
+    assert e.value.code == abi.NPT_ECAPACITY
+
+
+def test_many_breaks_overflow_area():
+    """Reads with > BRK_INLINE breaks exercise the overflow area and its exact re-emit pass."""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(5)
+    bs = [random_batch(rng, 6000, w.genome_len, g, big_n=400, max_ops=120)]
+    dev, ora = _both(dict(bin=10, break_thresh=100, record_depth=0), w, bs)
+    nb = np.diff(ora["break_off"].astype(np.int64))
+    assert (nb > 6).sum() > 1500
     assert_same(dev, ora)
