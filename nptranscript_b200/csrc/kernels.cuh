@@ -1,0 +1,476 @@
+// kernels.cuh — the hot path as three small kernels, one THREAD per read with lane-level dynamic scheduling.
+//
+//   walk_kernel<0>   CIGAR walk + 4-bit base compare, 8 bases per 32-bit word -> break list, read offsets, error sums
+//                    (IdentityProfile1.processCigar + CigarCluster.add, J/cluster/IdentityProfile1.java:482-585,
+//                    J/cluster/CigarCluster.java:442-498, incl. the D/=/X "advance, then emit" quirk)
+//   cluster_kernel   break list -> key tokens / break-point pairs / ORF counters / type -> cluster and sub-cluster hash
+//                    tables (IdentityProfile1.processRefPositions :149-356, CigarClusters.matchCluster :75-102,
+//                    CigarCluster.merge :633-698).  Records are written before the CAS that publishes them: no waiting.
+//   walk_kernel<1>   second walk (inputs are L2-resident for long reads, re-streamed otherwise) that sends the read's
+//                    depth runs as difference-array events (+1 at run start, -1 after run end) and its error / mapStart /
+//                    mapEnd points straight to the rows of its cluster with RED.ADD; a segmented scan at end of
+//                    chromosome turns difference rows into depth.
+//
+// Why thread-per-read: the first design of this file was warp-per-read (32 ops per step, warp scans for offsets, ballot
+// compaction, shared-memory event staging).  ncu (profiles/r01a..r01c) showed it instruction- and I-cache-bound at 1 % of
+// the HBM roofline: ~7 000 warp-instructions per read, `no_instruction` the top stall, DRAM 1 % busy.  A read is a strictly
+// sequential state machine with ~8-base granularity; giving each lane its own read removes every scan, shuffle and ballot
+// (~25x fewer warp-instructions per read) and lets each kernel fit the instruction cache.  Lanes fetch the next read from
+// an atomic cursor as soon as they finish one, so a warp stays busy whatever the read lengths are.
+#pragma once
+#include "npt_device.cuh"
+
+namespace npt {
+
+constexpr int BRK_INLINE = 6;     // breaks stored in the per-read inline slot
+constexpr int WALK_THREADS = 128;
+constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
+constexpr int MAX_BREAKS = 1 << 20;
+
+template <typename T>
+__device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
+
+// 8 reference bases starting at 0-based index `nib` (words hold the first base in bits 31..28)
+__device__ __forceinline__ uint32_t ref_win8(const uint32_t* w, uint32_t nib) {
+  const uint32_t k = nib >> 3, o = (nib & 7) << 2;
+  return __funnelshift_l(w[k + 1], w[k], o);
+}
+// 8 read bases from the BAM-packed byte stream (little-endian word loads, byte-swapped to base order).
+// Reads one word past the window: batches carry >= 8 readable bytes after seq4 (npt.h).
+__device__ __forceinline__ uint32_t read_win8(const uint32_t* w, uint32_t nib) {
+  const uint32_t k = nib >> 3, o = (nib & 7) << 2;
+  const uint32_t a = __byte_perm(__ldg(w + k), 0, 0x0123);
+  const uint32_t b = __byte_perm(__ldg(w + k + 1), 0, 0x0123);
+  return __funnelshift_l(b, a, o);
+}
+// mismatch / match masks of an 8-base window (bit 28-4j <-> base j), cnt valid bases
+__device__ __forceinline__ void cmp8(uint32_t rw, uint32_t gw, int cnt, uint32_t& mis, uint32_t& mat) {
+  const uint32_t x = rw ^ gw;
+  const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+  const uint32_t vm = 0x11111111u & (0xFFFFFFFFu << ((8 - cnt) << 2));
+  mis = nz & vm;
+  mat = vm & ~nz;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------ the walk
+// MODE 0: first pass (breaks into the inline slot, counts, read offsets).  MODE 1: coverage pass (REDs into the cluster's
+// rows).  MODE 2: store-all pass for the reads whose break list did not fit the inline slot.
+template <int MODE, bool REF_SMEM>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, const BatchDev b) {
+  extern __shared__ __align__(16) uint32_t s_ref[];
+  if (MODE == 1 && ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  if (REF_SMEM) {
+    for (int i = threadIdx.x; i < c.ref_nwords; i += blockDim.x) s_ref[i] = c.ref_words[i];
+    __syncthreads();
+  }
+  const uint32_t* refw = REF_SMEM ? s_ref : c.ref_words;
+  const int T = c.T, G = c.G;
+  const bool per_base = T < 8;  // a break could hide inside one 8-base window: always take the exact per-base path
+  unsigned* cursor = b.bctr + 2 + MODE;  // one read cursor per pass
+  const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
+
+  long long r = 0, rEnd = 0;
+  bool active = false;
+  // state of the read being walked
+  uint32_t ck = 0, cend = 0, nib0 = 0;
+  const uint32_t* wread = nullptr;
+  int alnStart = 0, refPos = 0, readPos = 0, prev = 0, nb = 0, maps = 0, errs = 0;
+  int mStart0 = 0, mRpos = 0, mN = 0, mOff = 0;  // M op being windowed: windows remain while mOff < mN
+  int st_r = 0, maxEnd = 0, eBs = 0, eRs = 0;
+  bool stFound = false;
+  int pendingEnd = -1;      // MODE 1: exclusive end of the last depth run, not yet written
+  int* cov = nullptr;       // MODE 1: row [arr 0][cluster][src][0]
+  int* bdst = nullptr;      // MODE 0/2: where this read's breaks go
+  int slow_windows = 0;
+
+  // CigarCluster.add for one emitted position (exact, used only near junctions or when T < 8)
+  auto add = [&](int p, bool match) {
+    const bool break_p = prev < 0 || p - prev > T;
+    if (MODE == 1 && break_p && prev > 0) { atomicAdd(cov + 2 * arr_stride + p, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+    if (match) {
+      if (break_p) {
+        if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
+        if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = p;
+        nb++;
+      }
+      prev = p;
+    }
+  };
+  // depth run [base, base+n): difference events, cancelling "end of previous run == start of this run"
+  auto depth_run = [&](int base, int n) {
+    if (MODE != 1 || n <= 0) return;
+    if (pendingEnd != base) {
+      if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
+      atomicAdd(cov + base, 1);
+    }
+    pendingEnd = base + n;
+  };
+
+  // Every outer iteration compares one 8-base window per lane (the convergent part); the inner loop brings a lane to its
+  // next window: it consumes the non-M ops in between, finishes a read and fetches the next one from the cursor.
+  // Lanes that ran out of reads stay in the loop (idle) until the whole warp is done, so that the __syncwarp below can
+  // force the lanes back together after the divergent inner loop; without it the compiler lets every lane run the
+  // window code on its own (ncu: 7 of 32 lanes active).
+  bool done = false;
+  for (;;) {
+    while (!done && mOff >= mN) {
+      if (!active) {
+        if (++r >= rEnd) {
+          r = (long long)atomicAdd(cursor, (unsigned)GRAB);
+          rEnd = min(r + GRAB, b.n);
+          if (r >= b.n) { done = true; break; }
+        }
+        if (MODE == 2 && b.nbreaks[r] <= BRK_INLINE) continue;
+        if (MODE == 1) {
+          const int slot = b.cluster[r];
+          if (slot < 0) continue;  // bad record
+          const int prov = ldcg(c.cl_rec + (unsigned)(ldcg(&c.cl[slot].word) & 0xffffffffu));
+          if (prov >= c.cov_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_COV_FULL); continue; }
+          cov = c.cov + ((long long)prov * c.S + __ldg(b.src + r)) * c.stride;
+          pendingEnd = -1;
+        }
+        alnStart = __ldg(b.pos + r);
+        ck = __ldg(b.cigar_off + r); cend = __ldg(b.cigar_off + r + 1);
+        const unsigned long long so = __ldg(b.seq_off + r);
+        wread = (const uint32_t*)b.seq4 + (so >> 2);
+        nib0 = (uint32_t)(so & 3) * 2;
+        if (MODE == 0) bdst = b.break_arena + r * BRK_INLINE;
+        if (MODE == 2) {
+          const unsigned n_all = (unsigned)b.nbreaks[r];
+          const unsigned loc = atomicAdd(b.bctr, n_all);
+          if (loc + n_all > b.break_cap) { atomicOr(b.bctr + 1, 1u); b.break_loc[r] = 0xFFFFFFFEu; continue; }
+          b.break_loc[r] = loc;
+          bdst = b.break_arena + b.n * BRK_INLINE + loc;
+        }
+        if (alnStart <= 0) {  // not a mapped record
+          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+          continue;
+        }
+        refPos = alnStart - 1; readPos = 0; maps = 0; errs = 0;
+        stFound = false; st_r = 0; maxEnd = INT_MIN; eBs = 0; eRs = 0;
+        if (MODE != 1) bdst[0] = alnStart;  // CigarCluster.addStart :442-446
+        nb = 1;
+        prev = alnStart;
+        active = true;
+      }
+      if (ck == cend) {
+        // ---- end of read: CigarCluster.addEnd :466-469, read offsets of alignment start/end
+        const int alnEnd = refPos;  // alnStart + reference span - 1
+        if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = alnEnd;
+        nb++;
+        if (MODE == 0) {
+          b.nbreaks[r] = nb;
+          b.break_loc[r] = 0xFFFFFFFFu;
+          b.read_st[r] = st_r;
+          b.read_en[r] = (alnEnd > 0 && maxEnd == alnEnd) ? (alnEnd < eBs ? 0 : alnEnd - eBs + eRs) : 0;
+          b.maps_sum[r] = c.record_depth ? maps : 0;
+          b.err_sum[r] = c.record_depth ? errs : 0;
+          b.rflags[r] = 0;
+          if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
+        }
+        if (MODE == 1) {
+          if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
+          // CigarCluster.setStartEnd :360-365 with the (trimmed) start/end of the read; positions past seqlen+1 only come
+          // from alignments that run off the reference and are dropped by the dense rows
+          const int sp = b.start_pos[r], ep = b.end_pos[r];
+          if (sp >= 0 && sp < c.stride) atomicAdd(cov + 2 * arr_stride + sp, 1);
+          if (ep >= 0 && ep < c.stride) atomicAdd(cov + 3 * arr_stride + ep, 1);
+        }
+        active = false;
+        continue;
+      }
+      // ---- one CIGAR element, as straight-line predicated code (lanes handle different op types side by side)
+      const uint32_t w = __ldg(b.cigar + ck);
+      ck++;
+      const int len = (int)(w >> 4), op = (int)(w & 15);
+      if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
+        if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+        active = false;
+        continue;
+      }
+      const bool isM = op == 0, isDX = (op == 2) | (op == 8), isEQ = op == 7;
+      const int ref0 = refPos, read0 = readPos;
+      refPos += ((0x18D >> op) & 1) ? len : 0;    // M D N = X consume reference
+      readPos += ((0x193 >> op) & 1) ? len : 0;   // M I S = X consume read
+      if (isM | isEQ | (op == 8)) {
+        // htsjdk AlignmentBlock(readStart, refStart, len) bookkeeping for getReadPositionAtReferencePosition
+        const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
+        if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
+        if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
+      }
+      // M emits from its own start; D / = / X advance first and emit afterwards (quirk :513-522, :552-576)
+      const int e0 = isM ? ref0 : refPos;
+      const int nE = (isM | isDX | isEQ) ? max(0, min(len, G - e0)) : 0;
+      const int base = e0 + 1;
+      maps += nE;
+      errs += isDX ? nE : 0;
+      if (isM) { mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE; }
+      if (MODE == 1 && nE > 0) {
+        depth_run(base, nE);
+        if (isDX) {
+          for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
+          if (prev > 0 && base + nE - 1 - prev > T)
+            for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+        }
+      }
+      if (isEQ && nE > 0) {
+        if (per_base || base + nE - 1 - prev > T) for (int i = 0; i < nE; i++) add(base + i, true);
+        else prev = base + nE - 1;
+      }
+      // H, P: nothing
+    }
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) break;
+    if (!done) {
+      // ---- one 8-base window of the current M op
+      const int cnt = min(8, mN - mOff);
+      const int pos0 = mStart0 + 1 + mOff;
+      uint32_t mis, mat;
+      cmp8(read_win8(wread, nib0 + (uint32_t)(mRpos + mOff)), ref_win8(refw, (uint32_t)(mStart0 + mOff)), cnt, mis, mat);
+      errs += __popc(mis);
+      if (per_base || pos0 + cnt - 1 - prev > T) {
+        // a break or a mapStart/mapEnd event is possible inside this window: exact per-base CigarCluster.add
+        slow_windows++;
+        for (int i = 0; i < cnt; i++) add(pos0 + i, (mat >> (28 - 4 * i)) & 1u);
+      } else if (mat) {
+        prev = pos0 + 7 - ((__ffs(mat) - 1) >> 2);  // every position of the window is within T of the last match before it
+      }
+      if (MODE == 1) {
+        int* err_row = cov + arr_stride;
+        while (mis) {
+          const int bit = 31 - __clz(mis);
+          mis &= ~(1u << bit);
+          atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
+        }
+      }
+      mOff += 8;
+    }
+  }
+  if (MODE == 0 && slow_windows) atomicAdd(c.counters + CN_SLOW, (unsigned)slow_windows);
+}
+
+// ------------------------------------------------------------------------------------------------ annotation lookups
+// Annotation.nextUpstream :87-97 (highest row i with leftBreak + tol >= start[i]) / EmptyAnnotation :22-24
+__device__ __forceinline__ int tok_up(const DevCfg& c, const int* ostart, const int* oname, const int* ostrand, int p, bool fwd) {
+  if (c.annot_kind == 1) return p / c.bin;
+  for (int i = c.n_orf - 1; i >= 0; i--)
+    if ((!c.enforce_strand || (int)fwd == ostrand[i]) && p + c.bin >= ostart[i]) return oname[i];
+  return -1;  // NPT_TOK_ST
+}
+// Annotation.nextDownstream :62-72 (lowest row i with rightBreak - tol <= start[i])
+__device__ __forceinline__ int tok_down(const DevCfg& c, const int* ostart, const int* oname, const int* ostrand, int p, bool fwd) {
+  if (c.annot_kind == 1) return p / c.bin;
+  for (int i = 0; i < c.n_orf; i++)
+    if ((!c.enforce_strand || (int)fwd == ostrand[i]) && p - c.bin <= ostart[i]) return oname[i];
+  return -2;  // NPT_TOK_END
+}
+
+// break-point matrix cell += 1   (BreakPoints.addBreakPoint, J/cluster/BreakPoints.java:102-108)
+__device__ void pair_add(const DevCfg& c, int src, int level, int st, int en) {
+  const unsigned long long key = (1ULL << 63) | ((unsigned long long)src << 59) | ((unsigned long long)level << 58) |
+                                 ((unsigned long long)(unsigned)st << 29) | (unsigned long long)(unsigned)en;
+  unsigned slot = (unsigned)mix64(key) & c.pr_mask;
+  for (unsigned probe = 0; probe <= c.pr_mask; probe++, slot = (slot + 1) & c.pr_mask) {
+    PairEntry* e = c.pr + slot;
+    unsigned long long k = ldcg(&e->key);
+    if (k == 0) {
+      k = atomicCAS(&e->key, 0ULL, key);
+      if (k == 0) {
+        const unsigned np = atomicAdd(c.counters + CN_PAIRS, 1u);
+        if ((int)np >= c.pr_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
+        k = key;
+      }
+    }
+    if (k == key) { atomicAdd(&e->count, 1); return; }
+  }
+  atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
+}
+
+// ------------------------------------------------------------------------------------------------ clustering
+constexpr int CLUSTER_THREADS = 128;
+
+// One thread per read.  Key tokens are functions of the break list, so they are regenerated on the fly for hashing,
+// comparing and storing instead of being held in registers.
+__global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c, const BatchDev b) {
+  extern __shared__ __align__(16) int s_int[];
+  if (ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  int* s_ostart = s_int;
+  int* s_oname = s_ostart + c.n_orf;
+  int* s_ostrand = s_oname + c.n_orf;
+  int* s_cnt = s_ostrand + c.n_orf;  // total_counts[S], spliced[S][n_orf], unspliced[S][n_orf] (block-privatised)
+  const int ncnt = c.S * (1 + 2 * c.n_orf);
+  for (int i = threadIdx.x; i < c.n_orf; i += blockDim.x) { s_ostart[i] = c.orf_start[i]; s_oname[i] = c.orf_name[i]; s_ostrand[i] = c.orf_strand[i]; }
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
+    if (b.rflags[r] & 0x10u) {  // bad record: not clustered
+      b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0;
+      continue;
+    }
+    int nb = b.nbreaks[r];
+    unsigned loc = b.break_loc[r];
+    int* br = (loc == 0xFFFFFFFFu) ? b.break_arena + r * BRK_INLINE : b.break_arena + b.n * BRK_INLINE + loc;
+    const int src = b.src[r];
+    const bool neg = (b.flag[r] & 0x10) != 0;
+    // ---- small first/last exon removal (IdentityProfile1.java:205-228), host mode only: drops the first and/or last pair
+    if (c.min_fl_exon > 0 && nb > 2) {
+      const int m = c.min_fl_exon;
+      const int diff0 = br[1] - br[0], diff1 = br[nb - 1] - br[nb - 2];
+      int a = 0, e = nb;
+      if (nb == 4 && diff0 < m && diff1 < m) { if (diff1 < diff0) e -= 2; else a += 2; }
+      else { if (diff1 < m) e -= 2; if (diff0 < m) a += 2; }
+      if (a) {
+        if (loc == 0xFFFFFFFFu) { for (int i = a; i < e; i++) br[i - a] = br[i]; }
+        else { loc += (unsigned)a; b.break_loc[r] = loc; br += a; }
+      }
+      nb = e - a;
+      b.nbreaks[r] = nb;
+    }
+    const int startPos = br[0], endPos = br[nb - 1];
+    const bool fwd_known = (c.rna_mask >> src) & 1;
+    const bool fwd = !neg;  // meaningful when fwd_known; in coronavirus mode callers guarantee rna[src]
+    bool leader = false;
+    if (c.coronavirus && nb > 1) leader = (c.annot_kind == 1) ? (br[1] < 100) : (br[1] < s_ostart[1] - c.bin);
+
+    // ---- key tokens (IdentityProfile1.java:266-299, 325-327) as a function of the token index
+    const bool ends = c.include_start || nb == 2;
+    const int nbody = c.coronavirus ? (ends ? nb : nb - 1) : 1;
+    const int ntok = nbody + (c.enforce_strand ? 1 : 0);
+    auto token = [&](int k) -> int {
+      if (k >= nbody) return fwd ? -3 : -4;                                          // '+' / '-'
+      if (!c.coronavirus) return tok_up(c, s_ostart, s_oname, s_ostrand, (fwd_known && !fwd) ? br[0] : br[nb - 1], fwd);
+      if (!ends && k == 0) return -5;                                                // NPT_TOK_NOENDS marker
+      const bool isEnd = ends && (k == 0 || k == nb - 1);
+      const bool up = isEnd || (k & 1);
+      return up ? tok_up(c, s_ostart, s_oname, s_ostrand, br[k], fwd) : tok_down(c, s_ostart, s_oname, s_ostrand, br[k], fwd);
+    };
+
+    // ---- break-point pairs (:271-288): level 0 for the first internal gap > T of the read, 1 for the others
+    if (c.coronavirus) {
+      bool first = true;
+      for (int i = 1; i < nb - 1; i += 2) {
+        if (br[i + 1] - br[i] > c.T) {
+          leader = true;
+          if (c.calc_breaks1) pair_add(c, src, first ? 0 : 1, br[i], br[i + 1]);
+          first = false;
+        }
+      }
+    }
+    // ---- type (Annotation.getTypeInd :233-236)
+    int type_ind = 0;
+    if (c.coronavirus) type_ind = (startPos <= c.start_thresh) ? (endPos >= c.G - c.end_thresh ? 0 : 1) : (endPos >= c.G - c.end_thresh ? 2 : 3);
+    // ---- totalCounts (CigarClusters.java:81) and ORF spliced/unspliced counters (:349-356)
+    atomicAdd(&s_cnt[src], 1);
+    if (c.coronavirus) {
+      const int st1 = br[nb - 2];
+      const bool spliced = startPos <= c.start_thresh;
+      for (int i = c.n_orf - 1; i >= 0; i--) {
+        if (s_ostart[i] < st1 - 10) break;
+        if (endPos > s_ostart[i] + 100) atomicAdd(&s_cnt[c.S + (spliced ? 0 : c.S * c.n_orf) + src * c.n_orf + i], 1);
+      }
+    }
+
+    // ---- cluster table: find or insert the token list
+    const unsigned long long gidx = (unsigned long long)(b.idx_base + r);
+    unsigned long long h = 0x1234ULL ^ ((unsigned long long)ntok << 48);
+    for (int k = 0; k < ntok; k++) h = mix64(h + (unsigned)token(k));
+    const unsigned h32 = (unsigned)(h >> 32) | 1u;
+    int cl_slot = -1;
+    {
+      unsigned slot = (unsigned)h & c.cl_mask;
+      unsigned my_off = 0xFFFFFFFFu;
+      for (unsigned probe = 0; probe <= c.cl_mask; probe++, slot = (slot + 1) & c.cl_mask) {
+        unsigned long long w = ldcg(&c.cl[slot].word);
+        if (w == 0) {
+          if (my_off == 0xFFFFFFFFu) {  // write the record first, publish it with the CAS
+            my_off = atomicAdd(c.counters + CN_TOK_USED, (unsigned)(CL_REC_HDR + ntok));
+            if (my_off + CL_REC_HDR + ntok > c.tok_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); break; }
+            c.cl_rec[my_off] = -1; c.cl_rec[my_off + 1] = ntok;
+            for (int k = 0; k < ntok; k++) c.cl_rec[my_off + CL_REC_HDR + k] = token(k);
+            __threadfence();
+          }
+          w = atomicCAS(&c.cl[slot].word, 0ULL, ((unsigned long long)h32 << 32) | my_off);
+          if (w == 0) {
+            const unsigned prov = atomicAdd(c.counters + CN_CLUSTERS, 1u);
+            if ((int)prov >= c.cl_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
+            c.cl_rec[my_off] = (int)prov;  // read by the coverage pass (a later kernel) and at end of chromosome
+            cl_slot = (int)slot;
+            break;
+          }
+        }
+        if ((unsigned)(w >> 32) == h32) {  // verify the full key
+          const unsigned off = (unsigned)(w & 0xffffffffu);
+          bool eq = ldcg(c.cl_rec + off + 1) == ntok;
+          for (int k = 0; eq && k < ntok; k++) eq = ldcg(c.cl_rec + off + CL_REC_HDR + k) == token(k);
+          if (eq) { cl_slot = (int)slot; break; }
+        }
+      }
+      if (cl_slot < 0) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
+    }
+    // ---- sub-cluster table: key = (cluster slot, binned breaks) — CigarCluster.cloneBreaks :620-631
+    int sb_slot = -1;
+    if (cl_slot >= 0) {
+      if (gidx < ldcg(&c.cl[cl_slot].min_idx)) atomicMin(&c.cl[cl_slot].min_idx, gidx);
+      int a = 0, e = nb;
+      if (!c.include_start && fwd_known) { if (fwd) a = 1; else e = nb - 1; }
+      const int nkey = e - a;
+      const int nsum = c.track_sums ? nb : 0;
+      unsigned long long hs = 0x77ULL + (unsigned long long)(unsigned)cl_slot * 0x9E3779B97F4A7C15ULL + ((unsigned long long)nkey << 48);
+      for (int i = a; i < e; i++) hs = mix64(hs + (unsigned)(br[i] / c.bin));
+      const unsigned hs32 = (unsigned)(hs >> 32) | 1u;
+      unsigned slot = (unsigned)hs & c.sb_mask;
+      unsigned my_off = 0xFFFFFFFFu;
+      for (unsigned probe = 0; probe <= c.sb_mask; probe++, slot = (slot + 1) & c.sb_mask) {
+        unsigned long long w = ldcg(&c.sb[slot].word);
+        if (w == 0) {
+          if (my_off == 0xFFFFFFFFu) {
+            my_off = atomicAdd(c.counters + CN_SUBKEY_USED, (unsigned)(SB_REC_HDR + nkey));
+            const unsigned soff = nsum ? atomicAdd(c.counters + CN_SUMS_USED, (unsigned)nsum) : 0u;
+            if (my_off + SB_REC_HDR + nkey > c.sbkey_cap || soff + nsum > c.sums_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); break; }
+            c.sb_rec[my_off] = cl_slot; c.sb_rec[my_off + 1] = nkey; c.sb_rec[my_off + 2] = (int)soff; c.sb_rec[my_off + 3] = nsum;
+            for (int i = a; i < e; i++) c.sb_rec[my_off + SB_REC_HDR + i - a] = br[i] / c.bin;
+            __threadfence();
+          }
+          w = atomicCAS(&c.sb[slot].word, 0ULL, ((unsigned long long)hs32 << 32) | my_off);
+          if (w == 0) {
+            const unsigned ns = atomicAdd(c.counters + CN_SUBS, 1u);
+            if ((int)ns >= c.sb_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL);
+            sb_slot = (int)slot;
+            break;
+          }
+        }
+        if ((unsigned)(w >> 32) == hs32) {
+          const unsigned off = (unsigned)(w & 0xffffffffu);
+          bool eq = ldcg(c.sb_rec + off) == cl_slot && ldcg(c.sb_rec + off + 1) == nkey;
+          for (int i = a; eq && i < e; i++) eq = ldcg(c.sb_rec + off + SB_REC_HDR + i - a) == br[i] / c.bin;
+          if (eq) { sb_slot = (int)slot; break; }
+        }
+      }
+      if (sb_slot < 0) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL);
+      else {
+        const unsigned long long idxf = (gidx << 2) | (unsigned long long)(((fwd_known && fwd) ? 1 : 0) | (neg ? 2 : 0));
+        if (idxf < ldcg(&c.sb[sb_slot].min_idx)) atomicMin(&c.sb[sb_slot].min_idx, idxf);
+        atomicAdd(c.sub_count + (size_t)sb_slot * c.S + src, 1);  // Count.increment / new Count
+        if (c.track_sums) {                                         // Count.addBreaks :84-96 (exact integer sums)
+          atomicAdd(c.sub_break_sum + sb_slot, 1);
+          const unsigned off = (unsigned)(ldcg(&c.sb[sb_slot].word) & 0xffffffffu);
+          const unsigned soff = (unsigned)ldcg(c.sb_rec + off + 2);
+          if (ldcg(c.sb_rec + off + 3) == nb)
+            for (int i = 0; i < nb; i++) atomicAdd(c.sub_sums + soff + i, (unsigned long long)(long long)br[i]);
+        }
+      }
+    }
+    b.cluster[r] = cl_slot; b.sub[r] = sb_slot; b.start_pos[r] = startPos; b.end_pos[r] = endPos;
+    b.rflags[r] = (unsigned)type_ind | (leader ? 4u : 0u) | (neg ? 8u : 0u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ncnt; i += blockDim.x) if (s_cnt[i]) atomicAdd(c.small + i, s_cnt[i]);
+}
+
+}  // namespace npt

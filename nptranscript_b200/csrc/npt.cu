@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
@@ -13,7 +14,7 @@
 
 #include "../../include/npt.h"
 #include "npt_device.cuh"
-#include "walk.cuh"
+#include "kernels.cuh"
 
 using namespace npt;
 
@@ -84,24 +85,23 @@ struct npt_ctx {
   int n_orf = 0;
   DevCfg dc{};
   bool ref_smem = false;
-  size_t smem_bytes = 0;
   DBuf<uint32_t> d_ref;
   DBuf<int> d_ostart, d_oname;
   DBuf<uint8_t> d_ostrand;
-  DBuf<ClEntry> d_cl;
-  DBuf<int> d_cl_tok;
-  DBuf<SubEntry> d_sb;
-  DBuf<int> d_sb_key, d_sub_count, d_sub_break_sum;
-  DBuf<unsigned> d_sub_sum_off, d_sub_nsum;
-  DBuf<unsigned char> d_sub_flags;
+  DBuf<Slot> d_cl;
+  DBuf<int> d_cl_rec;
+  DBuf<Slot> d_sb;
+  DBuf<int> d_sb_rec, d_sub_count, d_sub_break_sum;
   DBuf<unsigned long long> d_sub_sums;
+  int walk_blocks[3] = {0, 0, 0};   // grid sizes of walk_kernel<0/1/2>
+  size_t walk_smem = 0, cluster_smem = 0;
   DBuf<PairEntry> d_pr;
   DBuf<int> d_cov, d_cov_out;
   DBuf<int> d_small;
   DBuf<unsigned> d_counters;
   // finalize scratch
   DBuf<unsigned long long> d_keys, d_keys2;
-  DBuf<int> d_vals, d_vals2, d_cl_slot, d_sb_slot, d_cl_rank, d_sb_grank, d_cl_sub_off;
+  DBuf<int> d_vals, d_vals2, d_cl_slot, d_sb_slot, d_cl_rank, d_cl_slot_rank, d_sb_grank, d_cl_sub_off;
   DBuf<unsigned char> d_cub;
   DBuf<long long> d_break_off;
   DBuf<int> d_breaks_out;
@@ -160,30 +160,40 @@ int fail(npt_ctx* c, int code, const char* fmt, ...) {
 unsigned pow2_at_least(unsigned long long v) { unsigned p = 1; while (p < v && p < (1u << 31)) p <<= 1; return p; }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-__global__ void init_tables_kernel(ClEntry* cl, unsigned ncl, SubEntry* sb, unsigned nsb, PairEntry* pr, unsigned npr) {
+__global__ void init_tables_kernel(Slot* cl, unsigned ncl, Slot* sb, unsigned nsb, PairEntry* pr, unsigned npr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = i; k < ncl; k += stride) { cl[k].tag = 0; cl[k].min_idx = ~0ULL; cl[k].prov = -1; cl[k].tok_off = 0; cl[k].ntok = 0; cl[k].pad = 0; }
-  for (size_t k = i; k < nsb; k += stride) { sb[k].tag = 0; sb[k].min_idx = ~0ULL; sb[k].prov = -1; sb[k].key_off = 0; sb[k].nkey = 0; sb[k].cl_prov = -1; }
+  for (size_t k = i; k < ncl; k += stride) { cl[k].word = 0; cl[k].min_idx = ~0ULL; }
+  for (size_t k = i; k < nsb; k += stride) { sb[k].word = 0; sb[k].min_idx = ~0ULL; }
   for (size_t k = i; k < npr; k += stride) { pr[k].key = 0; pr[k].count = 0; pr[k].pad = 0; }
 }
 
-// table slots -> dense arrays indexed by provisional id
-__global__ void collect_clusters_kernel(const ClEntry* cl, unsigned nslots, int n, unsigned long long* keys, int* vals, int* slot_of) {
+// cluster table slots -> dense arrays indexed by the cluster's dense id
+__global__ void collect_clusters_kernel(const Slot* cl, unsigned nslots, const int* cl_rec, int n, unsigned long long* keys, int* vals,
+                                        int* slot_of) {
   for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
-    const int p = cl[s].prov;
-    if (p >= 0 && p < n) { keys[p] = cl[s].min_idx; vals[p] = p; slot_of[p] = (int)s; }
-  }
-}
-__global__ void collect_subs_kernel(const SubEntry* sb, unsigned nslots, int n, const int* cl_rank, unsigned long long* keys, int* vals,
-                                    int* slot_of, unsigned char* flags) {
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
-    const int p = sb[s].prov;
-    if (p >= 0 && p < n) {
-      const unsigned long long m = sb[s].min_idx;
-      keys[p] = ((unsigned long long)(unsigned)cl_rank[sb[s].cl_prov] << 40) | ((m >> 2) & ((1ULL << 40) - 1));
-      vals[p] = p; slot_of[p] = (int)s; flags[p] = (unsigned char)(m & 3);
+    const unsigned long long w = cl[s].word;
+    if (w) {
+      const int p = cl_rec[(unsigned)(w & 0xffffffffu)];
+      if (p >= 0 && p < n) { keys[p] = cl[s].min_idx; vals[p] = p; slot_of[p] = (int)s; }
     }
   }
+}
+// sub-cluster slots -> (sort key, slot) pairs in arbitrary dense order; key = (cluster rank << 40) | first read index
+__global__ void collect_subs_kernel(const Slot* sb, unsigned nslots, const int* sb_rec, const Slot* cl, const int* cl_rec, const int* cl_rank,
+                                    int n, unsigned long long* keys, int* vals, unsigned* counter) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long w = sb[s].word;
+    if (w) {
+      const int cslot = sb_rec[(unsigned)(w & 0xffffffffu)];
+      const int cprov = cl_rec[(unsigned)(cl[cslot].word & 0xffffffffu)];
+      const unsigned o = atomicAdd(counter, 1u);
+      if ((int)o < n) { keys[o] = ((unsigned long long)(unsigned)cl_rank[cprov] << 40) | ((sb[s].min_idx >> 2) & ((1ULL << 40) - 1)); vals[o] = (int)s; }
+    }
+  }
+}
+// rank_of_slot[slot] = rank for clusters (via dense id) / global sub rank for sub-clusters
+__global__ void cluster_slot_ranks_kernel(const int* slot_of_prov, const int* rank_of_prov, int n, int* rank_of_slot) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) rank_of_slot[slot_of_prov[p]] = rank_of_prov[p];
 }
 __global__ void ranks_kernel(const int* sorted_vals, int n, int* rank_of) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) rank_of[sorted_vals[r]] = r;
@@ -197,7 +207,7 @@ __global__ void sub_offsets_kernel(const unsigned long long* sorted_keys, int n,
 }
 __global__ void remap_reads_kernel(int64_t n, int* cluster, int* sub, const int* cl_rank, const int* sb_grank, const int* cl_sub_off) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-    const int cp = cluster[r], sp = sub[r];
+    const int cp = cluster[r], sp = sub[r];  // table slots
     int cr = -1, sr = -1;
     if (cp >= 0) { cr = cl_rank[cp]; if (sp >= 0) sr = sb_grank[sp] - cl_sub_off[cr]; }
     cluster[r] = cr; sub[r] = sr;
@@ -216,26 +226,31 @@ __global__ void gather_breaks_kernel(int64_t n, const int* nbreaks, const unsign
   }
 }
 // dense, rank-ordered copies of the table columns the host needs
-__global__ void export_clusters_kernel(const ClEntry* cl, const int* slot_of, const int* rank_of, int n, long long* first, unsigned* tok_off,
-                                       unsigned* ntok) {
+__global__ void export_clusters_kernel(const Slot* cl, const int* cl_rec, const int* slot_of, const int* rank_of, int n, long long* first,
+                                       unsigned* tok_off, unsigned* ntok) {
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const ClEntry& e = cl[slot_of[p]];
+    const Slot& e = cl[slot_of[p]];
+    const unsigned off = (unsigned)(e.word & 0xffffffffu);
     const int r = rank_of[p];
-    first[r] = (long long)e.min_idx; tok_off[r] = e.tok_off; ntok[r] = e.ntok;
+    first[r] = (long long)e.min_idx; tok_off[r] = off + CL_REC_HDR; ntok[r] = (unsigned)cl_rec[off + 1];
   }
 }
-__global__ void export_subs_kernel(const SubEntry* sb, const int* slot_of, const int* grank_of, int n, int S, const int* sub_count,
-                                   const int* sub_break_sum, const unsigned* sub_sum_off, const unsigned* sub_nsum, const unsigned char* sub_flags,
-                                   long long* first, unsigned* key_off, unsigned* nkey, int* count, int* break_sum, unsigned* sum_off,
-                                   unsigned* nsum, unsigned char* flags) {
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    const SubEntry& e = sb[slot_of[p]];
-    const int r = grank_of[p];
-    first[r] = (long long)(e.min_idx >> 2); key_off[r] = e.key_off; nkey[r] = e.nkey;
-    for (int s = 0; s < S; s++) count[(size_t)r * S + s] = sub_count[(size_t)p * S + s];
-    break_sum[r] = sub_break_sum[p]; sum_off[r] = sub_sum_off[p]; nsum[r] = sub_nsum[p]; flags[r] = sub_flags[p];
+// sorted_slots[g] = slot of the sub-cluster with global rank g
+__global__ void export_subs_kernel(const Slot* sb, const int* sb_rec, const int* sorted_slots, int n, int S, const int* sub_count,
+                                   const int* sub_break_sum, long long* first, unsigned* key_off, unsigned* nkey, int* count, int* break_sum,
+                                   unsigned* sum_off, unsigned* nsum, unsigned char* flags) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+    const int s = sorted_slots[g];
+    const Slot& e = sb[s];
+    const unsigned off = (unsigned)(e.word & 0xffffffffu);
+    first[g] = (long long)(e.min_idx >> 2); flags[g] = (unsigned char)(e.min_idx & 3);
+    key_off[g] = off + SB_REC_HDR; nkey[g] = (unsigned)sb_rec[off + 1];
+    sum_off[g] = (unsigned)sb_rec[off + 2]; nsum[g] = (unsigned)sb_rec[off + 3];
+    for (int k = 0; k < S; k++) count[(size_t)g * S + k] = sub_count[(size_t)s * S + k];
+    break_sum[g] = sub_break_sum[s];
   }
 }
+
 __global__ void compact_pairs_kernel(const PairEntry* pr, unsigned nslots, int* out, unsigned* counter, int cap) {
   for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
     const unsigned long long k = pr[s].key;
@@ -292,19 +307,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
   }
 }
 
-size_t walk_smem_bytes(const DevCfg& dc, bool ref_smem) {
-  size_t b = (ref_smem ? (size_t)dc.ref_nwords * 4 : 0) + (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4;
-  b = (b + 15) & ~(size_t)15;
-  return b + sizeof(WarpScratch) * WARPS_PER_BLOCK + 16;
-}
-
-int launch_walk(npt_ctx* ctx, const BatchDev& bd, int mode) {
-  const int blocks_per_sm = std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / std::max<size_t>(ctx->smem_bytes, 1)));
-  long long want = (bd.n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-  int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)ctx->sm_count * blocks_per_sm));
-  if (ctx->ref_smem) walk_kernel<true><<<grid, WARPS_PER_BLOCK * 32, ctx->smem_bytes, ctx->s_comp>>>(ctx->dc, bd, mode);
-  else walk_kernel<false><<<grid, WARPS_PER_BLOCK * 32, ctx->smem_bytes, ctx->s_comp>>>(ctx->dc, bd, mode);
-  ctx->total_launches++;
+// The per-batch kernel sequence on the compute stream.  from_stage: 0 = everything, 1 = from the store-all pass on
+// (used when the overflow area of a batch had to be enlarged).
+int launch_batch(npt_ctx* ctx, const BatchDev& bd, int from_stage) {
+  const DevCfg& dc = ctx->dc;
+  const int T = WALK_THREADS;
+  if (ctx->ref_smem) {
+    if (from_stage == 0) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+  } else {
+    if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, 0, ctx->s_comp>>>(dc, bd);
+    walk_kernel<2, false><<<ctx->walk_blocks[2], T, 0, ctx->s_comp>>>(dc, bd);
+  }
+  const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
+  cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
+  ctx->total_launches += from_stage == 0 ? 3 : 2;
+  if (dc.record_depth) {
+    if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    else walk_kernel<1, false><<<ctx->walk_blocks[1], T, 0, ctx->s_comp>>>(dc, bd);
+    ctx->total_launches++;
+  }
   CK(cudaGetLastError());
   return NPT_OK;
 }
@@ -313,19 +335,21 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
   Batch& B = ctx->batches[bi];
   if (B.retired) return NPT_OK;
   CK(cudaEventSynchronize(B.done));
-  unsigned h[2];
+  unsigned h[8];
   CK(cudaMemcpy(h, B.bctr, sizeof h, cudaMemcpyDeviceToHost));
   if (h[1]) {
-    // the overflow area for reads with more than BRK_INLINE breaks was too small: re-emit exactly (no side effects)
+    // The overflow area for reads with more than BRK_INLINE breaks was too small; cluster_kernel and the coverage pass
+    // skipped this batch.  h[0] is the exact need: enlarge and run the batch from the store-all pass on.  Running it
+    // late is fine: the tables are order-independent (first-appearance = atomicMin of the global read index).
     const unsigned need = h[0];
     int* bigger = nullptr;
     CK(cudaMalloc(&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int)));
     CK(cudaMemcpyAsync(bigger, B.d.break_arena, (size_t)B.n * BRK_INLINE * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
-    CK(cudaMemsetAsync(B.bctr, 0, 2 * sizeof(unsigned), ctx->s_comp));
+    CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
     CK(cudaStreamSynchronize(ctx->s_comp));
     cudaFree(B.d.break_arena);
     B.d.break_arena = bigger; B.d.break_cap = need;
-    int rc = launch_walk(ctx, B.d, 1);
+    int rc = launch_batch(ctx, B.d, 1);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_comp));
   }
@@ -400,11 +424,11 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   DBuf<unsigned char>* dummy = nullptr; (void)dummy;
   ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_cl.release();
-  ctx->d_cl_tok.release(); ctx->d_sb.release(); ctx->d_sb_key.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
-  ctx->d_sub_sum_off.release(); ctx->d_sub_nsum.release(); ctx->d_sub_flags.release(); ctx->d_sub_sums.release(); ctx->d_pr.release();
+  ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
+  ctx->d_sub_sums.release(); ctx->d_pr.release();
   ctx->d_cov.release(); ctx->d_cov_out.release(); ctx->d_small.release(); ctx->d_counters.release(); ctx->d_keys.release();
   ctx->d_keys2.release(); ctx->d_vals.release(); ctx->d_vals2.release(); ctx->d_cl_slot.release(); ctx->d_sb_slot.release();
-  ctx->d_cl_rank.release(); ctx->d_sb_grank.release(); ctx->d_cl_sub_off.release(); ctx->d_cub.release(); ctx->d_break_off.release();
+  ctx->d_cl_rank.release(); ctx->d_cl_slot_rank.release(); ctx->d_sb_grank.release(); ctx->d_cl_sub_off.release(); ctx->d_cub.release(); ctx->d_break_off.release();
   ctx->d_breaks_out.release(); ctx->d_pairs_out.release(); ctx->d_ex_first.release(); ctx->d_ex_flags.release();
   for (auto& b : ctx->d_ex_u) b.release();
   for (auto& b : ctx->d_ex_i) b.release();
@@ -456,7 +480,6 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   dc.rna_mask = 0;
   for (int s = 0; s < cf.num_sources; s++) if (cf.rna[s]) dc.rna_mask |= 1u << s;
   dc.annot_kind = annot->kind; dc.n_orf = annot->n; dc.G = (int)ref_len; dc.stride = (int)ref_len + 2;
-  dc.force_serial = cf.break_thresh < 8;
 
   // reference: 8 bases per word, first base in the top nibble, 4 words of padding
   const int nwords = (int)((ref_len + 7) / 8) + 4;
@@ -483,17 +506,16 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   dc.cl = ctx->d_cl.p; dc.cl_mask = ncl - 1; dc.cl_cap = max_cl;
   dc.sb = ctx->d_sb.p; dc.sb_mask = nsb - 1; dc.sb_cap = max_sb;
   dc.pr = ctx->d_pr.p; dc.pr_mask = npr - 1; dc.pr_cap = max_pr;
-  dc.tok_cap = (unsigned)std::min<unsigned long long>(16ull * max_cl, 1ull << 30);
-  dc.sbkey_cap = (unsigned)std::min<unsigned long long>(8ull * max_sb, 1ull << 30);
+  dc.tok_cap = (unsigned)std::min<unsigned long long>(24ull * max_cl + (1 << 20), 1ull << 30);   // records incl. lost insertion races
+  dc.sbkey_cap = (unsigned)std::min<unsigned long long>(12ull * max_sb + (1 << 20), 1ull << 30);
   dc.sums_cap = cf.track_break_sums ? dc.sbkey_cap : 0;
-  CK(ctx->d_cl_tok.ensure(dc.tok_cap)); CK(ctx->d_sb_key.ensure(dc.sbkey_cap));
-  CK(ctx->d_sub_count.ensure((size_t)max_sb * dc.S)); CK(ctx->d_sub_break_sum.ensure(max_sb));
-  CK(ctx->d_sub_sum_off.ensure(max_sb)); CK(ctx->d_sub_nsum.ensure(max_sb)); CK(ctx->d_sub_flags.ensure(max_sb));
+  CK(ctx->d_cl_rec.ensure(dc.tok_cap)); CK(ctx->d_sb_rec.ensure(dc.sbkey_cap));
+  CK(ctx->d_sub_count.ensure((size_t)nsb * dc.S)); CK(ctx->d_sub_break_sum.ensure(nsb));
   CK(ctx->d_sub_sums.ensure(std::max<unsigned>(dc.sums_cap, 1)));
-  dc.cl_tok = ctx->d_cl_tok.p; dc.sb_key = ctx->d_sb_key.p; dc.sub_count = ctx->d_sub_count.p; dc.sub_break_sum = ctx->d_sub_break_sum.p;
-  dc.sub_sum_off = ctx->d_sub_sum_off.p; dc.sub_nsum = ctx->d_sub_nsum.p; dc.sub_flags = ctx->d_sub_flags.p; dc.sub_sums = ctx->d_sub_sums.p;
-  CK(cudaMemsetAsync(ctx->d_sub_count.p, 0, (size_t)max_sb * dc.S * 4, ctx->s_comp));
-  CK(cudaMemsetAsync(ctx->d_sub_break_sum.p, 0, (size_t)max_sb * 4, ctx->s_comp));
+  dc.cl_rec = ctx->d_cl_rec.p; dc.sb_rec = ctx->d_sb_rec.p; dc.sub_count = ctx->d_sub_count.p; dc.sub_break_sum = ctx->d_sub_break_sum.p;
+  dc.sub_sums = ctx->d_sub_sums.p;
+  CK(cudaMemsetAsync(ctx->d_sub_count.p, 0, (size_t)nsb * dc.S * 4, ctx->s_comp));
+  CK(cudaMemsetAsync(ctx->d_sub_break_sum.p, 0, (size_t)nsb * 4, ctx->s_comp));
   CK(cudaMemsetAsync(ctx->d_sub_sums.p, 0, (size_t)std::max<unsigned>(dc.sums_cap, 1) * 8, ctx->s_comp));
   const size_t cov_elems = 4ull * max_cov * dc.S * dc.stride;
   if (cf.record_depth) {
@@ -512,16 +534,36 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   init_tables_kernel<<<ctx->sm_count * 4, 256, 0, ctx->s_comp>>>(dc.cl, ncl, dc.sb, nsb, dc.pr, npr);
   CK(cudaGetLastError());
 
-  // shared memory plan: keep the packed reference on chip when it fits next to the per-warp scratch
-  ctx->ref_smem = (size_t)nwords * 4 <= 64 * 1024;
-  ctx->smem_bytes = walk_smem_bytes(dc, ctx->ref_smem);
-  if (ctx->smem_bytes > ctx->smem_optin) {
-    ctx->ref_smem = false;
-    ctx->smem_bytes = walk_smem_bytes(dc, false);
-    if (ctx->smem_bytes > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->smem_bytes);
+  // shared memory plan: the packed reference lives on chip when it fits (30 kb genome = 15 KB)
+  ctx->ref_smem = (size_t)nwords * 4 <= 96 * 1024;
+  ctx->walk_smem = ctx->ref_smem ? (size_t)nwords * 4 : 0;
+  ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
+  if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
+  CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  {
+    // persistent grids: resident blocks per SM from the occupancy API (NPT_WALK_BLOCKS_PER_SM overrides, for experiments)
+    const char* env = getenv("NPT_WALK_BLOCKS_PER_SM");
+    const int forced = env ? atoi(env) : 0;
+    int occ[3] = {1, 1, 1};
+    if (ctx->ref_smem) {
+      CK(cudaFuncSetAttribute(walk_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+      CK(cudaFuncSetAttribute(walk_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+      CK(cudaFuncSetAttribute(walk_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], walk_kernel<0, true>, WALK_THREADS, ctx->walk_smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], walk_kernel<1, true>, WALK_THREADS, ctx->walk_smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], walk_kernel<2, true>, WALK_THREADS, ctx->walk_smem));
+    } else {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], walk_kernel<0, false>, WALK_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], walk_kernel<1, false>, WALK_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], walk_kernel<2, false>, WALK_THREADS, 0));
+    }
+    for (int k = 0; k < 3; k++) {
+      int bps = std::max(1, occ[k]);
+      if (forced > 0) bps = std::min(bps, forced);
+      ctx->walk_blocks[k] = ctx->sm_count * bps;
+    }
+    ctx->walk_blocks[2] = ctx->sm_count;  // the store-all pass only touches the rare long-break-list reads
   }
-  CK(cudaFuncSetAttribute(walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-  CK(cudaFuncSetAttribute(walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
   CK(cudaStreamSynchronize(ctx->s_comp));
   return NPT_OK;
 }
@@ -590,16 +632,16 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   d.rflags = (unsigned*)(ob + 6 * n); d.maps_sum = ob + 7 * n; d.err_sum = ob + 8 * n; d.nbreaks = ob + 9 * n; d.break_loc = (unsigned*)(ob + 10 * n);
   d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n / 4, 4096), 1LL << 30);
   CK(cudaMalloc(&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int)));
-  CK(cudaMalloc(&B.bctr, 2 * sizeof(unsigned)));
-  CK(cudaMemsetAsync(B.bctr, 0, 2 * sizeof(unsigned), ctx->s_comp));
+  CK(cudaMalloc(&B.bctr, 8 * sizeof(unsigned)));
+  CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
   d.bctr = B.bctr;
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, ctx->s_comp));
-  int rc = launch_walk(ctx, d, 0);
+  int rc = launch_batch(ctx, d, 0);
   if (rc) return rc;
-  ctx->walk_launches++;
+  ctx->walk_launches += ctx->dc.record_depth ? 4 : 3;
   CK(cudaEventRecord(e1, ctx->s_comp));
   ctx->walk_events.emplace_back(e0, e1);
   CK(cudaEventCreateWithFlags(&B.done, cudaEventDisableTiming));
@@ -661,7 +703,7 @@ int npt_end_chrom(npt_ctx* ctx) {
     if (er & ERR_PAIR_FULL) m += " break-point pairs(max_break_pairs)";
     if (er & ERR_COV_FULL) m += " coverage rows(max_coverage_clusters)";
     if (er & ERR_ARENA_FULL) m += " key arena";
-    if (er & ERR_TOO_MANY_BREAKS) m += " a read has more than 256 breaks";
+    if (er & ERR_TOO_MANY_BREAKS) m += " a read has more than 2^20 breaks";
     ctx->in_chrom = false;
     return fail(ctx, NPT_ECAPACITY, "%s", m.c_str());
   }
@@ -673,22 +715,28 @@ int npt_end_chrom(npt_ctx* ctx) {
   const int nmax = std::max(std::max(nc, ns), 1);
   CK(ctx->d_keys.ensure(nmax)); CK(ctx->d_keys2.ensure(nmax)); CK(ctx->d_vals.ensure(nmax)); CK(ctx->d_vals2.ensure(nmax));
   CK(ctx->d_cl_slot.ensure(std::max(nc, 1))); CK(ctx->d_sb_slot.ensure(std::max(ns, 1)));
-  CK(ctx->d_cl_rank.ensure(std::max(nc, 1))); CK(ctx->d_sb_grank.ensure(std::max(ns, 1))); CK(ctx->d_cl_sub_off.ensure(nc + 1));
+  CK(ctx->d_cl_rank.ensure(std::max(nc, 1))); CK(ctx->d_cl_sub_off.ensure(nc + 1));
+  const unsigned ncl_slots = dc.cl_mask + 1, nsb_slots = dc.sb_mask + 1;
+  CK(ctx->d_cl_slot_rank.ensure(ncl_slots)); CK(ctx->d_sb_grank.ensure(nsb_slots));
   if (nc > 0) {
     // sort-and-rank: cluster id = rank of its first read index (CigarClusters.java:83)
-    collect_clusters_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.cl, dc.cl_mask + 1, nc, ctx->d_keys.p, ctx->d_vals.p, ctx->d_cl_slot.p);
+    collect_clusters_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.cl, ncl_slots, dc.cl_rec, nc, ctx->d_keys.p, ctx->d_vals.p, ctx->d_cl_slot.p);
     if ((rc = sort_pairs(ctx, ctx->d_keys.p, ctx->d_keys2.p, ctx->d_vals.p, ctx->d_vals2.p, nc))) return rc;
     ranks_kernel<<<(nc + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_vals2.p, nc, ctx->d_cl_rank.p);
+    cluster_slot_ranks_kernel<<<(nc + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_cl_slot_rank.p);
     // sub-cluster id = rank of its first read index among the subs of its cluster (CigarCluster.java:660)
     CK(cudaMemsetAsync(ctx->d_cl_sub_off.p, 0, (size_t)(nc + 1) * 4, ctx->s_comp));
     if (ns > 0) {
-      collect_subs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.sb, dc.sb_mask + 1, ns, ctx->d_cl_rank.p, ctx->d_keys.p, ctx->d_vals.p,
-                                                                       ctx->d_sb_slot.p, dc.sub_flags);
+      unsigned* ctr = ctx->d_counters.p + CN_SUBS;
+      CK(cudaMemsetAsync(ctr, 0, 4, ctx->s_comp));
+      collect_subs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.sb, nsb_slots, dc.sb_rec, dc.cl, dc.cl_rec, ctx->d_cl_rank.p, ns, ctx->d_keys.p,
+                                                                       ctx->d_vals.p, ctr);
       if ((rc = sort_pairs(ctx, ctx->d_keys.p, ctx->d_keys2.p, ctx->d_vals.p, ctx->d_vals2.p, ns))) return rc;
-      ranks_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_vals2.p, ns, ctx->d_sb_grank.p);
+      CK(cudaMemcpyAsync(ctx->d_sb_slot.p, ctx->d_vals2.p, (size_t)ns * 4, cudaMemcpyDeviceToDevice, ctx->s_comp));  // sorted slots
+      ranks_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_vals2.p, ns, ctx->d_sb_grank.p);  // slot -> global sub rank
       sub_offsets_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ctx->d_keys2.p, ns, nc, ctx->d_cl_sub_off.p);
     }
-    ctx->total_launches += 6;
+    ctx->total_launches += 8;
     CK(cudaGetLastError());
   }
   // per-read: provisional ids -> ranks; break lists -> one compact array in submit order
@@ -700,7 +748,7 @@ int npt_end_chrom(npt_ctx* ctx) {
   for (size_t bi = 0; bi < ctx->batches.size(); bi++) {
     Batch& B = ctx->batches[bi];
     const int grid = (int)std::min<int64_t>((B.n + 255) / 256, ctx->sm_count * 16);
-    if (nc > 0) remap_reads_kernel<<<grid, 256, 0, ctx->s_comp>>>(B.n, B.d.cluster, B.d.sub, ctx->d_cl_rank.p, ctx->d_sb_grank.p, ctx->d_cl_sub_off.p);
+    if (nc > 0) remap_reads_kernel<<<grid, 256, 0, ctx->s_comp>>>(B.n, B.d.cluster, B.d.sub, ctx->d_cl_slot_rank.p, ctx->d_sb_grank.p, ctx->d_cl_sub_off.p);
     size_t tmp = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, B.d.nbreaks, ctx->d_break_off.p + off_r, (int)B.n, ctx->s_comp));
     CK(ctx->d_cub.ensure(tmp));
@@ -805,15 +853,15 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
     std::vector<long long> first(nc1);
     std::vector<unsigned> toff(nc1), ntok(nc1);
     if (nc > 0) {
-      export_clusters_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dc.cl, ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_ex_first.p, ctx->d_ex_u[0].p,
-                                                              ctx->d_ex_u[1].p);
+      export_clusters_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dc.cl, dc.cl_rec, ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_ex_first.p,
+                                                              ctx->d_ex_u[0].p, ctx->d_ex_u[1].p);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(first.data(), ctx->d_ex_first.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(toff.data(), ctx->d_ex_u[0].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(ntok.data(), ctx->d_ex_u[1].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int> tok_arena(std::max<unsigned>(ctx->h_counters[CN_TOK_USED], 1));
-    CK(cudaMemcpyAsync(tok_arena.data(), dc.cl_tok, (size_t)ctx->h_counters[CN_TOK_USED] * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(tok_arena.data(), dc.cl_rec, (size_t)ctx->h_counters[CN_TOK_USED] * 4, cudaMemcpyDeviceToHost, st));
     std::vector<int> cl_sub_off(nc + 1, 0);
     CK(cudaMemcpyAsync(cl_sub_off.data(), ctx->d_cl_sub_off.p, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -832,10 +880,9 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
     std::vector<int> cnt((size_t)ns1 * S), bsum(ns1);
     std::vector<unsigned char> sflags(ns1);
     if (ns > 0) {
-      export_subs_kernel<<<(ns + 255) / 256, 256, 0, st>>>(dc.sb, ctx->d_sb_slot.p, ctx->d_sb_grank.p, ns, S, dc.sub_count, dc.sub_break_sum,
-                                                          dc.sub_sum_off, dc.sub_nsum, dc.sub_flags, ctx->d_ex_first.p, ctx->d_ex_u[0].p,
-                                                          ctx->d_ex_u[1].p, ctx->d_ex_i[0].p, ctx->d_ex_i[1].p, ctx->d_ex_u[2].p, ctx->d_ex_u[3].p,
-                                                          ctx->d_ex_flags.p);
+      export_subs_kernel<<<(ns + 255) / 256, 256, 0, st>>>(dc.sb, dc.sb_rec, ctx->d_sb_slot.p, ns, S, dc.sub_count, dc.sub_break_sum,
+                                                          ctx->d_ex_first.p, ctx->d_ex_u[0].p, ctx->d_ex_u[1].p, ctx->d_ex_i[0].p, ctx->d_ex_i[1].p,
+                                                          ctx->d_ex_u[2].p, ctx->d_ex_u[3].p, ctx->d_ex_flags.p);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(sfirst.data(), ctx->d_ex_first.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(koff.data(), ctx->d_ex_u[0].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
@@ -847,7 +894,7 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
       CK(cudaMemcpyAsync(sflags.data(), ctx->d_ex_flags.p, (size_t)ns, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int> key_arena(std::max<unsigned>(ctx->h_counters[CN_SUBKEY_USED], 1));
-    CK(cudaMemcpyAsync(key_arena.data(), dc.sb_key, (size_t)ctx->h_counters[CN_SUBKEY_USED] * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(key_arena.data(), dc.sb_rec, (size_t)ctx->h_counters[CN_SUBKEY_USED] * 4, cudaMemcpyDeviceToHost, st));
     std::vector<long long> sums_arena(std::max<unsigned>(ctx->h_counters[CN_SUMS_USED], 1));
     if (dc.track_sums)
       CK(cudaMemcpyAsync(sums_arena.data(), dc.sub_sums, (size_t)ctx->h_counters[CN_SUMS_USED] * 8, cudaMemcpyDeviceToHost, st));

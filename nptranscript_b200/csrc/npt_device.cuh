@@ -4,36 +4,31 @@
 
 namespace npt {
 
-// counters[] slots (device uint32 unless noted)
+// counters[] slots (device uint32)
 enum {
-  CN_CLUSTERS = 0,   // provisional cluster ids handed out
-  CN_TOK_USED,       // cluster key token arena
-  CN_SUBS,           // provisional sub-cluster ids handed out
-  CN_SUBKEY_USED,    // sub-cluster key arena
+  CN_CLUSTERS = 0,   // dense cluster ids handed out (coverage row index)
+  CN_TOK_USED,       // cluster record arena (ints)
+  CN_SUBS,           // sub-cluster records created
+  CN_SUBKEY_USED,    // sub-cluster record arena (ints)
   CN_SUMS_USED,      // int64 break-sum arena
   CN_PAIRS,          // distinct break-point pairs
   CN_ERROR,          // sticky error bits (ERR_*)
-  CN_SLOW,           // reads that took the serial path
+  CN_SLOW,           // windows that took the exact per-base path (diagnostic)
   CN_COUNT
 };
 
 enum { ERR_CL_FULL = 1, ERR_SUB_FULL = 2, ERR_PAIR_FULL = 4, ERR_COV_FULL = 8, ERR_ARENA_FULL = 16, ERR_TOO_MANY_BREAKS = 32 };
 
-struct ClEntry {   // cluster hash-table slot (key = token list)
-  unsigned long long tag;      // 0 = empty, else 64-bit key hash (never 0)
-  unsigned long long min_idx;  // first-appearance global read index (atomicMin)
-  int prov;                    // provisional dense id, -1 until published
-  unsigned tok_off, ntok;
-  unsigned pad;
+// Hash-table slot (clusters and sub-clusters): `word` = 0 while empty, else (hash32 << 32) | record offset in the arena.
+// The record is fully written before the CAS that publishes it, so readers never wait.  The slot index is the identity
+// of the (sub-)cluster until end of chromosome.
+struct Slot {
+  unsigned long long word;
+  unsigned long long min_idx;  // first-appearance global read index (atomicMin); sub-clusters: (index << 2) | first-read flags
 };
-
-struct SubEntry {  // sub-cluster hash-table slot (key = cluster prov + binned break list)
-  unsigned long long tag;
-  unsigned long long min_idx;
-  int prov;
-  unsigned key_off, nkey;
-  int cl_prov;
-};
+// cluster record in cl_rec:  [0] dense id (coverage row; written by the creator right after the CAS)  [1] ntok  [2..] tokens
+// sub record in sb_rec:      [0] cluster slot  [1] nkey  [2] offset into sub_sums  [3] nsum  [4..] binned breaks
+constexpr int CL_REC_HDR = 2, SB_REC_HDR = 4;
 
 struct PairEntry {  // break-point matrix cell  (src, level, start, end) -> count
   unsigned long long key;  // 0 = empty
@@ -48,7 +43,6 @@ struct DevCfg {
   unsigned rna_mask;
   int annot_kind, n_orf;
   int G, stride;
-  int force_serial;  // T too small for the windowed fast path
   // ---- reference + annotation
   const uint32_t* ref_words;  // 8 bases per word, first base in bits 31..28; padded by 4 words
   int ref_nwords;             // words incl. padding
@@ -56,15 +50,12 @@ struct DevCfg {
   const int* orf_name;
   const uint8_t* orf_strand;
   // ---- tables
-  ClEntry* cl; unsigned cl_mask; int cl_cap;
-  int* cl_tok; unsigned tok_cap;
-  SubEntry* sb; unsigned sb_mask; int sb_cap;
-  int* sb_key; unsigned sbkey_cap;
-  int* sub_count;            // [sb_cap][S]
-  int* sub_break_sum;        // [sb_cap]
-  unsigned* sub_sum_off;     // [sb_cap]
-  unsigned* sub_nsum;        // [sb_cap]
-  unsigned char* sub_flags;  // [sb_cap]
+  Slot* cl; unsigned cl_mask; int cl_cap;
+  int* cl_rec; unsigned tok_cap;
+  Slot* sb; unsigned sb_mask; int sb_cap;
+  int* sb_rec; unsigned sbkey_cap;
+  int* sub_count;            // [sb slots][S]
+  int* sub_break_sum;        // [sb slots]
   unsigned long long* sub_sums; unsigned sums_cap;
   PairEntry* pr; unsigned pr_mask; int pr_cap;
   int* cov; int cov_cap;     // [4][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd
@@ -88,7 +79,7 @@ struct BatchDev {
   int* maps_sum; int* err_sum; int* nbreaks; unsigned* break_loc;
   int* break_arena;     // [n][BRK_INLINE] inline slots, then break_cap ints of overflow area
   unsigned break_cap;
-  unsigned* bctr;       // per batch: [0] overflow-area cursor, [1] overflow-area full flag
+  unsigned* bctr;       // per batch: [0] overflow-area cursor, [1] overflow-area full flag, [2..4] read cursors of walk_kernel<0/1/2>
 };
 
 }  // namespace npt
