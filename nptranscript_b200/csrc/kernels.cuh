@@ -23,9 +23,11 @@
 namespace npt {
 
 constexpr int BRK_INLINE = 6;     // breaks stored in the per-read inline slot
-constexpr int WALK_THREADS = 128;
+constexpr int WALK_THREADS = 256;
 constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
 constexpr int MAX_BREAKS = 1 << 20;
+constexpr int TILE_W = 16;        // words per lane tile (CIGAR: 16 ops; bases: 128 + one overlap word)
+constexpr int TILE_STRIDE = 17;   // odd stride: lane tiles start in different banks
 
 template <typename T>
 __device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
@@ -62,23 +64,33 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 // rows).  MODE 2: store-all pass for the reads whose break list did not fit the inline slot.
 template <int MODE, bool REF_SMEM>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, const BatchDev b) {
-  extern __shared__ __align__(16) uint32_t s_ref[];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
   if (MODE == 1 && ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  // shared memory: [packed reference (if it fits)] [per-warp CIGAR tiles 32 x 17] [per-warp base tiles 32 x 17]
+  uint32_t* s_ref = s_dyn;
+  const int ref_words = REF_SMEM ? c.ref_nwords : 0;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* cigTile = s_dyn + ref_words + warp * (2 * 32 * TILE_STRIDE);
+  uint32_t* seqTile = cigTile + 32 * TILE_STRIDE;
+  uint32_t* myCig = cigTile + lane * TILE_STRIDE;
+  uint32_t* mySeq = seqTile + lane * TILE_STRIDE;
   if (REF_SMEM) {
     for (int i = threadIdx.x; i < c.ref_nwords; i += blockDim.x) s_ref[i] = c.ref_words[i];
     __syncthreads();
   }
   const uint32_t* refw = REF_SMEM ? s_ref : c.ref_words;
+  const uint32_t* seqw = (const uint32_t*)b.seq4;
+  const long long seq_last = max(0LL, ((b.seq_bytes + 3) >> 2) - 1);   // clamp indices: no padding requirement on the batch
+  const long long cig_last = max(0LL, (long long)b.cigar_words - 1);
   const int T = c.T, G = c.G;
   const bool per_base = T < 8;  // a break could hide inside one 8-base window: always take the exact per-base path
   unsigned* cursor = b.bctr + 2 + MODE;  // one read cursor per pass
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
 
-  long long r = 0, rEnd = 0;
+  long long r = 0;
   bool active = false;
   // state of the read being walked
-  uint32_t ck = 0, cend = 0, nib0 = 0;
-  const uint32_t* wread = nullptr;
+  uint32_t nib0 = 0;
   int alnStart = 0, refPos = 0, readPos = 0, prev = 0, nb = 0, maps = 0, errs = 0;
   int mStart0 = 0, mRpos = 0, mN = 0, mOff = 0;  // M op being windowed: windows remain while mOff < mN
   int st_r = 0, maxEnd = 0, eBs = 0, eRs = 0;
@@ -111,54 +123,86 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
     pendingEnd = base + n;
   };
 
-  // Every outer iteration compares one 8-base window per lane (the convergent part); the inner loop brings a lane to its
-  // next window: it consumes the non-M ops in between, finishes a read and fetches the next one from the cursor.
-  // Lanes that ran out of reads stay in the loop (idle) until the whole warp is done, so that the __syncwarp below can
-  // force the lanes back together after the divergent inner loop; without it the compiler lets every lane run the
-  // window code on its own (ncu: 7 of 32 lanes active).
+  // Fixed loop body, re-converged with __syncwarp at two points per iteration:
+  //   (R1) warp-cooperative, coalesced refill of the CIGAR tiles of the lanes that ran out of staged ops;
+  //   (A)  a lane whose M op has no windows left takes ONE step: set up the next read, finish the current one, or consume
+  //        one CIGAR element from its tile (straight-line predicated code);
+  //   (R2) coalesced refill of the base tiles of the lanes whose next window is not staged;
+  //   (B)  every lane that is inside an M op compares one 8-base window from its tile.
+  // Lanes never touch global memory for the streams themselves: a lane-private 4-byte global load drags a 32-byte sector
+  // through L1 that is evicted before its neighbours are used (ncu r01h: 13 KB of L2->L1 traffic per 1.7 KB read, 40 warps
+  // slower than 24).  Lanes that ran out of reads stay in the loop (idle) until the whole warp is done so that the
+  // full-mask __syncwarp is legal; without it the compiler lets every lane run on its own (ncu r01e: 7 of 32 lanes active).
   bool done = false;
+  uint32_t cs = 0;           // index of the first CIGAR word in my tile (valid for [cs, cs+16)); offsets are uint32 in the ABI
+  uint32_t ckg = 0, cendg = 0;  // CIGAR cursor / end of this read
+  uint32_t ss = 0x80000000u; // first base word in my tile, relative to this read's first word (valid for [ss, ss+17))
+  const uint32_t* rp = seqw; // this read's first (4-byte aligned) base word
+  uint32_t dmask = 0; int dpos = 0;  // MODE 1: error positions of a D/X op, flushed in phase (B)
+  const unsigned half = lane >> 4, hl = lane & 15;
   for (;;) {
-    while (!done && mOff >= mN) {
-      if (!active) {
-        if (++r >= rEnd) {
-          r = (long long)atomicAdd(cursor, (unsigned)GRAB);
-          rEnd = min(r + GRAB, b.n);
-          if (r >= b.n) { done = true; break; }
-        }
-        if (MODE == 2 && b.nbreaks[r] <= BRK_INLINE) continue;
-        if (MODE == 1) {
-          const int slot = b.cluster[r];
-          if (slot < 0) continue;  // bad record
-          const int prov = ldcg(c.cl_rec + (unsigned)(ldcg(&c.cl[slot].word) & 0xffffffffu));
-          if (prov >= c.cov_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_COV_FULL); continue; }
-          cov = c.cov + ((long long)prov * c.S + __ldg(b.src + r)) * c.stride;
-          pendingEnd = -1;
-        }
-        alnStart = __ldg(b.pos + r);
-        ck = __ldg(b.cigar_off + r); cend = __ldg(b.cigar_off + r + 1);
-        const unsigned long long so = __ldg(b.seq_off + r);
-        wread = (const uint32_t*)b.seq4 + (so >> 2);
-        nib0 = (uint32_t)(so & 3) * 2;
-        if (MODE == 0) bdst = b.break_arena + r * BRK_INLINE;
-        if (MODE == 2) {
-          const unsigned n_all = (unsigned)b.nbreaks[r];
-          const unsigned loc = atomicAdd(b.bctr, n_all);
-          if (loc + n_all > b.break_cap) { atomicOr(b.bctr + 1, 1u); b.break_loc[r] = 0xFFFFFFFEu; continue; }
-          b.break_loc[r] = loc;
-          bdst = b.break_arena + b.n * BRK_INLINE + loc;
-        }
-        if (alnStart <= 0) {  // not a mapped record
-          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
-          continue;
-        }
-        refPos = alnStart - 1; readPos = 0; maps = 0; errs = 0;
-        stFound = false; st_r = 0; maxEnd = INT_MIN; eBs = 0; eRs = 0;
-        if (MODE != 1) bdst[0] = alnStart;  // CigarCluster.addStart :442-446
-        nb = 1;
-        prev = alnStart;
-        active = true;
+    __syncwarp();
+    // ---- (R1) CIGAR tiles: two lanes are served per step, one by each half-warp (16 words = 64 bytes, coalesced)
+    {
+      unsigned need = __ballot_sync(0xffffffffu, active && mOff >= mN && ckg < cendg && ckg - cs >= (uint32_t)TILE_W);
+      while (need) {
+        const int La = __ffs(need) - 1; need &= need - 1;
+        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
+        const int L = half ? Lb : La;
+        const uint32_t start = __shfl_sync(0xffffffffu, ckg, L);
+        const uint32_t v = __ldg(b.cigar + min((long long)start + hl, cig_last));
+        cigTile[L * TILE_STRIDE + hl] = v;
+        if ((int)lane == La || (int)lane == Lb) cs = ckg;
       }
-      if (ck == cend) {
+    }
+    __syncwarp();
+    // ---- (A) up to two steps per iteration: the usual pattern is one I/D element between two M elements
+#pragma unroll 1
+    for (int step = 0; step < 2; step++)
+    if (!done && mOff >= mN) {
+      if (!active) {
+        bool ok = true;
+        r = (long long)atomicAdd(cursor, 1u);
+        if (r >= b.n) { done = true; ok = false; }
+        if (ok && MODE == 2 && b.nbreaks[r] <= BRK_INLINE) ok = false;
+        if (ok && MODE == 1) {
+          const int slot = b.cluster[r];
+          if (slot < 0) ok = false;  // bad record
+          else {
+            const int prov = ldcg(c.cl_rec + (unsigned)(ldcg(&c.cl[slot].word) & 0xffffffffu));
+            if (prov >= c.cov_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_COV_FULL); ok = false; }
+            else { cov = c.cov + ((long long)prov * c.S + __ldg(b.src + r)) * c.stride; pendingEnd = -1; }
+          }
+        }
+        if (ok) {
+          alnStart = __ldg(b.pos + r);
+          ckg = __ldg(b.cigar_off + r); cendg = __ldg(b.cigar_off + r + 1);
+          cs = ckg - (uint32_t)TILE_W;  // nothing staged yet
+          const unsigned long long so = __ldg(b.seq_off + r);
+          rp = seqw + (so >> 2);
+          ss = 0x80000000u;             // base tile belongs to another read
+          nib0 = (uint32_t)(so & 3) * 2;
+          if (MODE == 0) bdst = b.break_arena + r * BRK_INLINE;
+          if (MODE == 2) {
+            const unsigned n_all = (unsigned)b.nbreaks[r];
+            const unsigned loc = atomicAdd(b.bctr, n_all);
+            if (loc + n_all > b.break_cap) { atomicOr(b.bctr + 1, 1u); b.break_loc[r] = 0xFFFFFFFEu; ok = false; }
+            else { b.break_loc[r] = loc; bdst = b.break_arena + b.n * BRK_INLINE + loc; }
+          }
+        }
+        if (ok && alnStart <= 0) {  // not a mapped record
+          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+          ok = false;
+        }
+        if (ok) {
+          refPos = alnStart - 1; readPos = 0; maps = 0; errs = 0;
+          stFound = false; st_r = 0; maxEnd = INT_MIN; eBs = 0; eRs = 0;
+          if (MODE != 1) bdst[0] = alnStart;  // CigarCluster.addStart :442-446
+          nb = 1;
+          prev = alnStart;
+          active = true;
+        }
+      } else if (ckg == cendg) {
         // ---- end of read: CigarCluster.addEnd :466-469, read offsets of alignment start/end
         const int alnEnd = refPos;  // alnStart + reference span - 1
         if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = alnEnd;
@@ -182,56 +226,78 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (ep >= 0 && ep < c.stride) atomicAdd(cov + 3 * arr_stride + ep, 1);
         }
         active = false;
-        continue;
-      }
-      // ---- one CIGAR element, as straight-line predicated code (lanes handle different op types side by side)
-      const uint32_t w = __ldg(b.cigar + ck);
-      ck++;
-      const int len = (int)(w >> 4), op = (int)(w & 15);
-      if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
-        if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
-        active = false;
-        continue;
-      }
-      const bool isM = op == 0, isDX = (op == 2) | (op == 8), isEQ = op == 7;
-      const int ref0 = refPos, read0 = readPos;
-      refPos += ((0x18D >> op) & 1) ? len : 0;    // M D N = X consume reference
-      readPos += ((0x193 >> op) & 1) ? len : 0;   // M I S = X consume read
-      if (isM | isEQ | (op == 8)) {
-        // htsjdk AlignmentBlock(readStart, refStart, len) bookkeeping for getReadPositionAtReferencePosition
-        const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
-        if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
-        if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
-      }
-      // M emits from its own start; D / = / X advance first and emit afterwards (quirk :513-522, :552-576)
-      const int e0 = isM ? ref0 : refPos;
-      const int nE = (isM | isDX | isEQ) ? max(0, min(len, G - e0)) : 0;
-      const int base = e0 + 1;
-      maps += nE;
-      errs += isDX ? nE : 0;
-      if (isM) { mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE; }
-      if (MODE == 1 && nE > 0) {
-        depth_run(base, nE);
-        if (isDX) {
-          for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
-          if (prev > 0 && base + nE - 1 - prev > T)
-            for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+      } else if (ckg - cs < (uint32_t)TILE_W) {
+        // ---- one CIGAR element, as straight-line predicated code (lanes handle different op types side by side)
+        const uint32_t w = myCig[(int)(ckg - cs)];
+        ckg++;
+        const int len = (int)(w >> 4), op = (int)(w & 15);
+        if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
+          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+          active = false;
+        } else {
+          const bool isM = op == 0, isDX = (op == 2) | (op == 8), isEQ = op == 7;
+          const int ref0 = refPos, read0 = readPos;
+          refPos += ((0x18D >> op) & 1) ? len : 0;    // M D N = X consume reference
+          readPos += ((0x193 >> op) & 1) ? len : 0;   // M I S = X consume read
+          if (isM | isEQ | (op == 8)) {
+            // htsjdk AlignmentBlock(readStart, refStart, len) bookkeeping for getReadPositionAtReferencePosition
+            const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
+            if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
+            if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
+          }
+          // M emits from its own start; D / = / X advance first and emit afterwards (quirk :513-522, :552-576)
+          const int e0 = isM ? ref0 : refPos;
+          const int nE = (isM | isDX | isEQ) ? max(0, min(len, G - e0)) : 0;
+          const int base = e0 + 1;
+          maps += nE;
+          errs += isDX ? nE : 0;
+          if (isM) { mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE; }
+          if (MODE == 1 && nE > 0) {
+            depth_run(base, nE);
+            if (isDX) {
+              if (nE <= 8 && dmask == 0) { dmask = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); dpos = base; }  // flushed in (B)
+              else for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
+              if (prev > 0 && base + nE - 1 - prev > T)
+                for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+            }
+          }
+          if (isEQ && nE > 0) {
+            if (per_base || base + nE - 1 - prev > T) for (int i = 0; i < nE; i++) add(base + i, true);
+            else prev = base + nE - 1;
+          }
         }
       }
-      if (isEQ && nE > 0) {
-        if (per_base || base + nE - 1 - prev > T) for (int i = 0; i < nE; i++) add(base + i, true);
-        else prev = base + nE - 1;
-      }
-      // H, P: nothing
     }
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
-    if (!done) {
-      // ---- one 8-base window of the current M op
+    // ---- (R2) base tiles: the window at read offset mRpos+mOff needs words k, k+1 of this read's packed bases
+    const bool hasWin = !done && mOff < mN;
+    const uint32_t nibw = nib0 + (uint32_t)(mRpos + mOff);
+    const uint32_t kg = nibw >> 3;  // word index relative to rp
+    {
+      unsigned need = __ballot_sync(0xffffffffu, hasWin && kg - ss >= (uint32_t)TILE_W);
+      while (need) {
+        const int La = __ffs(need) - 1; need &= need - 1;
+        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
+        const int L = half ? Lb : La;
+        const long long start = (long long)(((const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)rp, L)) - seqw) + __shfl_sync(0xffffffffu, kg, L);
+        seqTile[L * TILE_STRIDE + hl] = __ldg(seqw + min(start + hl, seq_last));
+        if (hl == 0) seqTile[L * TILE_STRIDE + TILE_W] = __ldg(seqw + min(start + TILE_W, seq_last));
+        if ((int)lane == La || (int)lane == Lb) ss = kg;
+      }
+    }
+    __syncwarp();
+    uint32_t mis = 0;
+    int pos0 = 0;
+    if (hasWin) {
+      // ---- (B) one 8-base window of the current M op
       const int cnt = min(8, mN - mOff);
-      const int pos0 = mStart0 + 1 + mOff;
-      uint32_t mis, mat;
-      cmp8(read_win8(wread, nib0 + (uint32_t)(mRpos + mOff)), ref_win8(refw, (uint32_t)(mStart0 + mOff)), cnt, mis, mat);
+      pos0 = mStart0 + 1 + mOff;
+      const int ki = (int)(kg - ss);
+      const uint32_t rw = __funnelshift_l(__byte_perm(mySeq[ki + 1], 0, 0x0123), __byte_perm(mySeq[ki], 0, 0x0123), (nibw & 7) << 2);
+      uint32_t mat;
+      cmp8(rw, ref_win8(refw, (uint32_t)(mStart0 + mOff)), cnt, mis, mat);
+      mOff += 8;
       errs += __popc(mis);
       if (per_base || pos0 + cnt - 1 - prev > T) {
         // a break or a mapStart/mapEnd event is possible inside this window: exact per-base CigarCluster.add
@@ -240,15 +306,20 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       } else if (mat) {
         prev = pos0 + 7 - ((__ffs(mat) - 1) >> 2);  // every position of the window is within T of the last match before it
       }
-      if (MODE == 1) {
-        int* err_row = cov + arr_stride;
-        while (mis) {
-          const int bit = 31 - __clz(mis);
-          mis &= ~(1u << bit);
-          atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
-        }
+    }
+    if (MODE == 1) {
+      // error positions: mismatches of this window and/or the D/X op consumed in phase (A)
+      int* err_row = cov + arr_stride;
+      while (mis) {
+        const int bit = 31 - __clz(mis);
+        mis &= ~(1u << bit);
+        atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
       }
-      mOff += 8;
+      while (dmask) {
+        const int bit = 31 - __clz(dmask);
+        dmask &= ~(1u << bit);
+        atomicAdd(err_row + dpos + ((28 - bit) >> 2), 1);
+      }
     }
   }
   if (MODE == 0 && slow_windows) atomicAdd(c.counters + CN_SLOW, (unsigned)slow_windows);

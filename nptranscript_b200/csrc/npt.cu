@@ -316,15 +316,15 @@ int launch_batch(npt_ctx* ctx, const BatchDev& bd, int from_stage) {
     if (from_stage == 0) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   } else {
-    if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, 0, ctx->s_comp>>>(dc, bd);
-    walk_kernel<2, false><<<ctx->walk_blocks[2], T, 0, ctx->s_comp>>>(dc, bd);
+    if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   }
   const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
   cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
   ctx->total_launches += from_stage == 0 ? 3 : 2;
   if (dc.record_depth) {
     if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    else walk_kernel<1, false><<<ctx->walk_blocks[1], T, 0, ctx->s_comp>>>(dc, bd);
+    else walk_kernel<1, false><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     ctx->total_launches++;
   }
   CK(cudaGetLastError());
@@ -536,7 +536,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
 
   // shared memory plan: the packed reference lives on chip when it fits (30 kb genome = 15 KB)
   ctx->ref_smem = (size_t)nwords * 4 <= 96 * 1024;
-  ctx->walk_smem = ctx->ref_smem ? (size_t)nwords * 4 : 0;
+  ctx->walk_smem = (ctx->ref_smem ? (size_t)nwords * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4;
   ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
   if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
   CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -553,9 +553,9 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], walk_kernel<1, true>, WALK_THREADS, ctx->walk_smem));
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], walk_kernel<2, true>, WALK_THREADS, ctx->walk_smem));
     } else {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], walk_kernel<0, false>, WALK_THREADS, 0));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], walk_kernel<1, false>, WALK_THREADS, 0));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], walk_kernel<2, false>, WALK_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], walk_kernel<0, false>, WALK_THREADS, ctx->walk_smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], walk_kernel<1, false>, WALK_THREADS, ctx->walk_smem));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], walk_kernel<2, false>, WALK_THREADS, ctx->walk_smem));
     }
     for (int k = 0; k < 3; k++) {
       int bps = std::max(1, occ[k]);
@@ -611,15 +611,17 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     CK(cudaStreamWaitEvent(ctx->s_comp, S.done, 0));
     d.pos = (const int*)(base + o_pos); d.flag = (const uint16_t*)(base + o_flag); d.src = (const uint16_t*)(base + o_src);
     d.cigar_off = (const uint32_t*)(base + o_coff); d.cigar = (const uint32_t*)(base + o_cig);
-    d.seq_off = (const unsigned long long*)(base + o_soff); d.seq4 = base + o_seq; d.seq_bytes = (long long)nseq;
+    d.seq_off = (const unsigned long long*)(base + o_soff); d.seq4 = base + o_seq; d.seq_bytes = (long long)nseq; d.cigar_words = (long long)ncig;
     S.busy = true; S.batch_index = (int)ctx->batches.size();
     B.staging = si;
   } else if (b->location == NPT_MEM_DEVICE) {
     if (((uintptr_t)b->seq4 & 3) != 0) return fail(ctx, NPT_EINVAL, "device seq4 must be 4-byte aligned");
     uint64_t nseq = 0;
+    uint32_t ncig = 0;
     CK(cudaMemcpy(&nseq, b->seq_off + n, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ncig, b->cigar_off + n, 4, cudaMemcpyDeviceToHost));
     d.pos = b->pos; d.flag = b->flag; d.src = b->src; d.cigar_off = b->cigar_off; d.cigar = b->cigar;
-    d.seq_off = (const unsigned long long*)b->seq_off; d.seq4 = b->seq4; d.seq_bytes = (long long)nseq;
+    d.seq_off = (const unsigned long long*)b->seq_off; d.seq4 = b->seq4; d.seq_bytes = (long long)nseq; d.cigar_words = (long long)ncig;
     B.staging = -1;
   } else {
     return fail(ctx, NPT_EINVAL, "unknown batch location");

@@ -74,6 +74,7 @@ struct BatchDev {
   const unsigned long long* seq_off;
   const uint8_t* seq4;
   long long seq_bytes;
+  long long cigar_words;
   // outputs
   int* cluster; int* sub; int* start_pos; int* end_pos; int* read_st; int* read_en; unsigned* rflags;
   int* maps_sum; int* err_sum; int* nbreaks; unsigned* break_loc;
