@@ -63,6 +63,7 @@ struct Batch {
   BatchDev d{};
   int64_t n = 0;
   void* out_block = nullptr;  // one allocation for all per-read outputs
+  size_t out_bytes = 0, arena_bytes = 0, bctr_bytes = 0;
   unsigned* bctr = nullptr;
   int staging = -1;           // index into ctx->stg, or -1 for caller-owned device memory
   bool retired = false;
@@ -106,6 +107,9 @@ struct npt_ctx {
   DBuf<long long> d_break_off;
   DBuf<int> d_breaks_out;
   DBuf<int> d_pairs_out;
+  // device block pool: cudaFree of large blocks is synchronous and slow (hundreds of ms per chromosome in the e2e trace),
+  // so per-batch output blocks are recycled across batches and chromosomes and only freed in npt_destroy
+  std::vector<std::pair<void*, size_t>> pool_free;
   // batches
   std::vector<Batch> batches;
   Staging stg[2];
@@ -331,6 +335,9 @@ int launch_batch(npt_ctx* ctx, const BatchDev& bd, int from_stage) {
   return NPT_OK;
 }
 
+cudaError_t pool_get(npt_ctx* ctx, void** out, size_t bytes, size_t* got);
+void pool_put(npt_ctx* ctx, void* p, size_t bytes);
+
 int retire_batch(npt_ctx* ctx, size_t bi) {
   Batch& B = ctx->batches[bi];
   if (B.retired) return NPT_OK;
@@ -343,12 +350,13 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
     // late is fine: the tables are order-independent (first-appearance = atomicMin of the global read index).
     const unsigned need = h[0];
     int* bigger = nullptr;
-    CK(cudaMalloc(&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int)));
+    size_t bigger_bytes = 0;
+    CK(pool_get(ctx, (void**)&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int), &bigger_bytes));
     CK(cudaMemcpyAsync(bigger, B.d.break_arena, (size_t)B.n * BRK_INLINE * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
     CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
     CK(cudaStreamSynchronize(ctx->s_comp));
-    cudaFree(B.d.break_arena);
-    B.d.break_arena = bigger; B.d.break_cap = need;
+    pool_put(ctx, B.d.break_arena, B.arena_bytes);
+    B.d.break_arena = bigger; B.d.break_cap = need; B.arena_bytes = bigger_bytes;
     int rc = launch_batch(ctx, B.d, 1);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_comp));
@@ -358,11 +366,25 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
   return NPT_OK;
 }
 
+cudaError_t pool_get(npt_ctx* ctx, void** out, size_t bytes, size_t* got) {
+  int best = -1;
+  for (size_t i = 0; i < ctx->pool_free.size(); i++)
+    if (ctx->pool_free[i].second >= bytes && (best < 0 || ctx->pool_free[i].second < ctx->pool_free[best].second)) best = (int)i;
+  if (best >= 0 && ctx->pool_free[best].second <= 2 * bytes + (1 << 20)) {
+    *out = ctx->pool_free[best].first; *got = ctx->pool_free[best].second;
+    ctx->pool_free.erase(ctx->pool_free.begin() + best);
+    return cudaSuccess;
+  }
+  *got = bytes;
+  return cudaMalloc(out, std::max<size_t>(bytes, 256));
+}
+void pool_put(npt_ctx* ctx, void* p, size_t bytes) { if (p) ctx->pool_free.emplace_back(p, bytes); }
+
 void free_batches(npt_ctx* ctx) {
   for (auto& B : ctx->batches) {
-    if (B.out_block) cudaFree(B.out_block);
-    if (B.d.break_arena) cudaFree(B.d.break_arena);
-    if (B.bctr) cudaFree(B.bctr);
+    pool_put(ctx, B.out_block, B.out_bytes);
+    pool_put(ctx, B.d.break_arena, B.arena_bytes);
+    pool_put(ctx, B.bctr, B.bctr_bytes);
     if (B.done) cudaEventDestroy(B.done);
   }
   ctx->batches.clear();
@@ -422,7 +444,8 @@ void npt_destroy(npt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   free_batches(ctx);
-  DBuf<unsigned char>* dummy = nullptr; (void)dummy;
+  for (auto& pb : ctx->pool_free) cudaFree(pb.first);
+  ctx->pool_free.clear();
   ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_pr.release();
@@ -628,13 +651,13 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   }
 
   // per-read outputs: 11 int arrays in one block + break arena
-  CK(cudaMalloc(&B.out_block, (size_t)n * 11 * 4));
+  CK(pool_get(ctx, &B.out_block, (size_t)n * 11 * 4, &B.out_bytes));
   int* ob = (int*)B.out_block;
   d.cluster = ob; d.sub = ob + n; d.start_pos = ob + 2 * n; d.end_pos = ob + 3 * n; d.read_st = ob + 4 * n; d.read_en = ob + 5 * n;
   d.rflags = (unsigned*)(ob + 6 * n); d.maps_sum = ob + 7 * n; d.err_sum = ob + 8 * n; d.nbreaks = ob + 9 * n; d.break_loc = (unsigned*)(ob + 10 * n);
   d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n / 4, 4096), 1LL << 30);
-  CK(cudaMalloc(&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int)));
-  CK(cudaMalloc(&B.bctr, 8 * sizeof(unsigned)));
+  CK(pool_get(ctx, (void**)&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int), &B.arena_bytes));
+  CK(pool_get(ctx, (void**)&B.bctr, 8 * sizeof(unsigned), &B.bctr_bytes));
   CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
   d.bctr = B.bctr;
 
@@ -957,7 +980,8 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
 int npt_release_results(npt_ctx* ctx) {
   if (!ctx) return NPT_EINVAL;
   cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
+  cudaStreamSynchronize(ctx->s_comp);
+  cudaStreamSynchronize(ctx->s_copy);
   free_batches(ctx);
   ctx->finalized = false;
   return NPT_OK;
