@@ -9,111 +9,167 @@ while reads are walked.  At end of chromosome the per-shard tables merge by key 
      rows are summed with one all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests); ORF counters likewise
   4. per-read ids never leave their rank: local ids are rewritten through the local→global maps.
 
-The merge logic works on plain result dicts (numpy), so the CPU tests drive it with oracle output under gloo.
+The merge works on plain result dicts with vectorised numpy (tables of 1e4-1e6 sub-clusters merge in milliseconds), so
+the CPU tests drive it with oracle output under gloo.
 """
 import time
 
 import numpy as np
 
+_SENT = np.int64(-(1 << 62))
+
+
+def _padded(flat, off, width):
+    """Ragged rows (flat, offsets) → dense [n, width] int64 matrix padded with a sentinel."""
+    off = off.astype(np.int64)
+    n = len(off) - 1
+    ln = off[1:] - off[:-1]
+    out = np.full((n, width), _SENT, np.int64)
+    if n and width and len(flat):
+        j = np.arange(width)[None, :]
+        m = j < ln[:, None]
+        idx = np.minimum(off[:-1, None] + j, len(flat) - 1)
+        out[m] = flat.astype(np.int64)[idx][m]
+    return out, ln
+
+
+def _unique_rows(K):
+    """np.unique(K, axis=0, return_inverse=True) for int64 matrices, an order of magnitude faster: unique on a 64-bit row
+    hash, then an exact verification that every row equals its group's representative (falls back if a hash collides)."""
+    if len(K) == 0:
+        return K, np.zeros(0, np.int64)
+    h = np.full(len(K), 0x9E3779B97F4A7C15, np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(K.shape[1]):
+            h = (h ^ K[:, j].astype(np.uint64)) * np.uint64(0x100000001B3)
+            h ^= h >> np.uint64(29)
+    _, rep, inv = np.unique(h, return_index=True, return_inverse=True)
+    inv = inv.reshape(-1)
+    if not np.array_equal(K, K[rep[inv]]):
+        uq, inv = np.unique(K, axis=0, return_inverse=True)
+        return uq, inv.reshape(-1)
+    return K[rep], inv
+
 
 def local_tables(res, idx_base=0):
-    """The part of a rank's results that takes part in the merge (small: O(clusters + sub-clusters))."""
-    nc, ns = res["n_clusters"], res["n_subs"]
-    ko, so, sko, sso = res["cl_key_off"], res["cl_sub_off"], res["sub_key_off"], res["sub_sum_off"]
-    clusters = []
-    for c in range(nc):
-        key = tuple(int(t) for t in res["cl_key_tok"][int(ko[c]):int(ko[c + 1])])
-        subs = []
-        for g in range(int(so[c]), int(so[c + 1])):
-            subs.append(dict(key=tuple(int(t) for t in res["sub_key"][int(sko[g]):int(sko[g + 1])]),
-                             first=int(res["sub_first_read"][g]) + idx_base, count=res["sub_count"][g].astype(np.int64),
-                             break_sum=int(res["sub_break_sum"][g]), sums=res["sub_sums"][int(sso[g]):int(sso[g + 1])].astype(np.int64),
-                             flags=int(res["sub_flags"][g])))
-        clusters.append(dict(key=key, first=int(res["cl_first_read"][c]) + idx_base, subs=subs))
-    pairs = {(int(a), int(b), int(c_), int(d)): int(e) for a, b, c_, d, e in
-             zip(res["pair_src"], res["pair_level"], res["pair_start"], res["pair_end"], res["pair_count"])}
-    return dict(clusters=clusters, pairs=pairs, total_counts=res["total_counts"].astype(np.int64),
-                spliced=res["spliced"].astype(np.int64), unspliced=res["unspliced"].astype(np.int64))
+    """The part of a rank's results that takes part in the merge (small: O(clusters + sub-clusters)), as flat arrays."""
+    keys = ("cl_key_off", "cl_key_tok", "cl_first_read", "cl_sub_off", "sub_key_off", "sub_key", "sub_first_read", "sub_count", "sub_break_sum",
+            "sub_sum_off", "sub_sums", "sub_flags", "pair_src", "pair_level", "pair_start", "pair_end", "pair_count", "total_counts", "spliced",
+            "unspliced")
+    t = {k: np.asarray(res[k]) for k in keys}
+    t["cl_first_read"] = t["cl_first_read"].astype(np.int64) + idx_base
+    t["sub_first_read"] = t["sub_first_read"].astype(np.int64) + idx_base
+    return t
 
 
 def merge_tables(tables):
-    """tables: list over ranks of local_tables().  Returns (global results dict, per-rank maps).
-    maps[r] = (cluster_map[int32 local→global], sub_map[list per local cluster of int32 local k→global k])."""
+    """tables: list over ranks of local_tables().  Returns (global tables dict, per-rank maps).
+    maps[r] = (cluster_map: int32[local clusters] → global id, sub_map: int32[local subs, cluster-major] → global k inside its cluster)."""
+    R = len(tables)
     S = len(tables[0]["total_counts"])
-    merged = {}
-    for t in tables:
-        for cl in t["clusters"]:
-            m = merged.setdefault(cl["key"], dict(first=cl["first"], subs={}))
-            m["first"] = min(m["first"], cl["first"])
-            for sb in cl["subs"]:
-                ms = m["subs"].get(sb["key"])
-                if ms is None:
-                    m["subs"][sb["key"]] = dict(first=sb["first"], count=sb["count"].copy(), break_sum=sb["break_sum"], sums=sb["sums"].copy(), flags=sb["flags"])
-                else:
-                    if sb["first"] < ms["first"]:
-                        ms["first"], ms["flags"] = sb["first"], sb["flags"]
-                    ms["count"] = ms["count"] + sb["count"]
-                    ms["break_sum"] += sb["break_sum"]
-                    if len(ms["sums"]) == len(sb["sums"]):
-                        ms["sums"] = ms["sums"] + sb["sums"]
-                    elif len(ms["sums"]) == 0:
-                        ms["sums"] = sb["sums"].copy()
-    order = sorted(merged.items(), key=lambda kv: kv[1]["first"])
-    cid = {k: i for i, (k, _) in enumerate(order)}
-    g = dict(n_clusters=len(order), cl_first_read=[], cl_key_off=[0], cl_key_tok=[], cl_read_count=[], cl_sub_off=[0], sub_first_read=[],
-             sub_key_off=[0], sub_key=[], sub_count=[], sub_break_sum=[], sub_sum_off=[0], sub_sums=[], sub_flags=[])
-    sid = {}
-    for k, m in order:
-        g["cl_first_read"].append(m["first"])
-        g["cl_key_tok"] += list(k)
-        g["cl_key_off"].append(len(g["cl_key_tok"]))
-        subs = sorted(m["subs"].items(), key=lambda kv: kv[1]["first"])
-        rc = np.zeros(S, np.int64)
-        for j, (sk, sb) in enumerate(subs):
-            sid[(k, sk)] = j
-            g["sub_first_read"].append(sb["first"]); g["sub_key"] += list(sk); g["sub_key_off"].append(len(g["sub_key"]))
-            g["sub_count"].append(sb["count"]); g["sub_break_sum"].append(sb["break_sum"]); g["sub_sums"] += list(sb["sums"])
-            g["sub_sum_off"].append(len(g["sub_sums"])); g["sub_flags"].append(sb["flags"])
-            rc += sb["count"]
-        g["cl_read_count"].append(rc)
-        g["cl_sub_off"].append(len(g["sub_first_read"]))
-    g["n_subs"] = len(g["sub_first_read"])
-    out = dict(n_clusters=g["n_clusters"], n_subs=g["n_subs"],
-               cl_first_read=np.array(g["cl_first_read"], np.int64), cl_key_off=np.array(g["cl_key_off"], np.uint32),
-               cl_key_tok=np.array(g["cl_key_tok"], np.int32), cl_read_count=np.array(g["cl_read_count"], np.int32).reshape(-1, S),
-               cl_sub_off=np.array(g["cl_sub_off"], np.uint32), sub_first_read=np.array(g["sub_first_read"], np.int64),
-               sub_key_off=np.array(g["sub_key_off"], np.uint32), sub_key=np.array(g["sub_key"], np.int32),
-               sub_count=np.array(g["sub_count"], np.int32).reshape(-1, S), sub_break_sum=np.array(g["sub_break_sum"], np.int32),
-               sub_sum_off=np.array(g["sub_sum_off"], np.uint32), sub_sums=np.array(g["sub_sums"], np.int64), sub_flags=np.array(g["sub_flags"], np.uint8))
-    pairs = {}
-    for t in tables:
-        for k, v in t["pairs"].items():
-            pairs[k] = pairs.get(k, 0) + v
-    ks = sorted(pairs)
+    # ---------------- clusters: unique token lists; id = rank of the minimum first read index
+    Lc = max([int(np.diff(t["cl_key_off"].astype(np.int64)).max()) if len(t["cl_key_off"]) > 1 else 0 for t in tables] + [0])
+    rows, firsts, owner = [], [], []
+    for r, t in enumerate(tables):
+        M, ln = _padded(t["cl_key_tok"], t["cl_key_off"], Lc)
+        rows.append(np.concatenate([ln[:, None], M], axis=1))
+        firsts.append(t["cl_first_read"])
+        owner.append(np.full(len(ln), r))
+    K = np.concatenate(rows) if rows else np.zeros((0, Lc + 1), np.int64)
+    first = np.concatenate(firsts) if firsts else np.zeros(0, np.int64)
+    uq, inv = _unique_rows(K)
+    nU = len(uq)
+    ufirst = np.full(nU, np.iinfo(np.int64).max)
+    np.minimum.at(ufirst, inv, first)
+    order = np.argsort(ufirst, kind="stable")
+    gid_of_u = np.empty(nU, np.int64)
+    gid_of_u[order] = np.arange(nU)
+    cl_gid = gid_of_u[inv]                       # per (rank, local cluster) → global id
+    splits = np.cumsum([len(x) for x in firsts])[:-1]
+    cl_gid_by_rank = np.split(cl_gid, splits) if R else []
+    uq_sorted = uq[order]
+    cl_len = uq_sorted[:, 0] if nU else np.zeros(0, np.int64)
+    toks = uq_sorted[:, 1:]
+    mask = np.arange(Lc)[None, :] < cl_len[:, None] if nU else np.zeros((0, Lc), bool)
+    out = dict(n_clusters=nU, cl_first_read=ufirst[order].astype(np.int64), cl_key_tok=toks[mask].astype(np.int32),
+               cl_key_off=np.concatenate([[0], np.cumsum(cl_len)]).astype(np.uint32))
+    # ---------------- sub-clusters: unique (global cluster id, binned break list)
+    Ls = max([int(np.diff(t["sub_key_off"].astype(np.int64)).max()) if len(t["sub_key_off"]) > 1 else 0 for t in tables] + [0])
+    Lm = max([int(np.diff(t["sub_sum_off"].astype(np.int64)).max()) if len(t["sub_sum_off"]) > 1 else 0 for t in tables] + [0])
+    srows, sfirst, scount, sbs, ssum, sflag, sn = [], [], [], [], [], [], []
+    for r, t in enumerate(tables):
+        ns = len(t["sub_first_read"])
+        M, ln = _padded(t["sub_key"], t["sub_key_off"], Ls)
+        per_cl = np.diff(t["cl_sub_off"].astype(np.int64))
+        gcl = np.repeat(cl_gid_by_rank[r], per_cl) if ns else np.zeros(0, np.int64)
+        srows.append(np.concatenate([gcl[:, None], ln[:, None], M], axis=1))
+        sfirst.append(t["sub_first_read"]); scount.append(t["sub_count"].reshape(ns, S).astype(np.int64)); sbs.append(t["sub_break_sum"].astype(np.int64))
+        Ms, lns = _padded(t["sub_sums"], t["sub_sum_off"], Lm)
+        Ms[Ms == _SENT] = 0
+        ssum.append(Ms); sn.append(lns); sflag.append(t["sub_flags"].astype(np.int64))
+    SK = np.concatenate(srows) if srows else np.zeros((0, Ls + 2), np.int64)
+    sf = np.concatenate(sfirst); sc = np.concatenate(scount); sb = np.concatenate(sbs); sm = np.concatenate(ssum); sl = np.concatenate(sn); sg = np.concatenate(sflag)
+    suq, sinv = _unique_rows(SK)
+    nS = len(suq)
+    usf = np.full(nS, np.iinfo(np.int64).max)
+    np.minimum.at(usf, sinv, sf)
+    # flags of the read that came first: the gathered row whose first index equals the minimum
+    is_min = sf == usf[sinv]
+    uflag = np.zeros(nS, np.int64)
+    uflag[sinv[is_min]] = sg[is_min]
+    ucount = np.zeros((nS, S), np.int64); np.add.at(ucount, sinv, sc)
+    ubs = np.zeros(nS, np.int64); np.add.at(ubs, sinv, sb)
+    usum = np.zeros((nS, Lm), np.int64); np.add.at(usum, sinv, sm)
+    ulen = np.zeros(nS, np.int64); np.maximum.at(ulen, sinv, sl)
+    sorder = np.lexsort((usf, suq[:, 0])) if nS else np.zeros(0, np.int64)   # by cluster, then first index
+    s_cl = suq[sorder, 0] if nS else np.zeros(0, np.int64)
+    cl_sub_off = np.concatenate([[0], np.cumsum(np.bincount(s_cl, minlength=nU))]) if nU else np.zeros(1, np.int64)
+    k_in_cl = np.arange(nS) - cl_sub_off[s_cl] if nS else np.zeros(0, np.int64)
+    k_of_u = np.empty(nS, np.int64)
+    k_of_u[sorder] = k_in_cl
+    sub_k = k_of_u[sinv]                          # per (rank, local sub) → global k inside its cluster
+    ssplits = np.cumsum([len(x) for x in sfirst])[:-1]
+    sub_k_by_rank = np.split(sub_k, ssplits) if R else []
+    klen = suq[sorder, 1] if nS else np.zeros(0, np.int64)
+    kmask = np.arange(Ls)[None, :] < klen[:, None] if nS else np.zeros((0, Ls), bool)
+    smask = np.arange(Lm)[None, :] < ulen[sorder][:, None] if nS else np.zeros((0, Lm), bool)
+    counts = ucount[sorder]
+    out.update(n_subs=nS, cl_sub_off=cl_sub_off.astype(np.uint32), sub_first_read=usf[sorder], sub_key=suq[sorder, 2:][kmask].astype(np.int32),
+               sub_key_off=np.concatenate([[0], np.cumsum(klen)]).astype(np.uint32), sub_count=counts.astype(np.int32),
+               sub_break_sum=ubs[sorder].astype(np.int32), sub_sums=usum[sorder][smask].astype(np.int64),
+               sub_sum_off=np.concatenate([[0], np.cumsum(ulen[sorder])]).astype(np.uint32), sub_flags=uflag[sorder].astype(np.uint8))
+    rc = np.zeros((nU, S), np.int64)
+    if nS:
+        np.add.at(rc, s_cl, counts)
+    out["cl_read_count"] = rc.astype(np.int32)
+    # ---------------- break-point pairs, counters
+    P = np.concatenate([np.stack([t["pair_src"], t["pair_level"], t["pair_start"], t["pair_end"]], axis=1).astype(np.int64) for t in tables])
+    pc = np.concatenate([t["pair_count"].astype(np.int64) for t in tables])
+    if len(P):
+        pu, pinv = _unique_rows(P)
+        srt = np.lexsort((pu[:, 3], pu[:, 2], pu[:, 1], pu[:, 0]))
+        rank_of = np.empty(len(pu), np.int64); rank_of[srt] = np.arange(len(pu))
+        pu, pinv = pu[srt], rank_of[pinv]
+        cnt = np.zeros(len(pu), np.int64); np.add.at(cnt, pinv, pc)
+    else:
+        pu, cnt = np.zeros((0, 4), np.int64), np.zeros(0, np.int64)
     for i, name in enumerate(("pair_src", "pair_level", "pair_start", "pair_end")):
-        out[name] = np.array([k[i] for k in ks], np.int32)
-    out["pair_count"] = np.array([pairs[k] for k in ks], np.int32)
-    out["n_pairs"] = len(ks)
-    out["total_counts"] = sum(t["total_counts"] for t in tables).astype(np.int32)
-    out["spliced"] = sum(t["spliced"] for t in tables).astype(np.int32)
-    out["unspliced"] = sum(t["unspliced"] for t in tables).astype(np.int32)
-    maps = []
-    for t in tables:
-        cmap = np.array([cid[cl["key"]] for cl in t["clusters"]], np.int32)
-        smap = [np.array([sid[(cl["key"], sb["key"])] for sb in cl["subs"]], np.int32) for cl in t["clusters"]]
-        maps.append((cmap, smap))
+        out[name] = pu[:, i].astype(np.int32)
+    out["pair_count"] = cnt.astype(np.int32)
+    out["n_pairs"] = len(pu)
+    for k in ("total_counts", "spliced", "unspliced"):
+        out[k] = sum(t[k].astype(np.int64) for t in tables).astype(np.int32)
+    maps = [(cl_gid_by_rank[r].astype(np.int32), sub_k_by_rank[r].astype(np.int32)) for r in range(R)]
     return out, maps
 
 
-def remap_reads(res, cmap, smap):
-    """Rewrite a rank's per-read local ids to global ids (in place on copies)."""
+def remap_reads(res, cmap, smap, cl_sub_off=None):
+    """Rewrite a rank's per-read local ids to global ids.  smap is cluster-major over the rank's local sub-clusters."""
     cl, sb = res["cluster_id"].copy(), res["sub_id"].copy()
     ok = cl >= 0
     if len(cmap):
-        off = np.zeros(len(smap) + 1, np.int64)
-        off[1:] = np.cumsum([len(x) for x in smap])
-        flat = np.concatenate(smap) if smap else np.zeros(0, np.int32)
-        sb[ok] = flat[off[cl[ok]] + sb[ok]]
+        off = (res["cl_sub_off"] if cl_sub_off is None else cl_sub_off).astype(np.int64)
+        sb[ok] = smap[off[cl[ok]] + sb[ok]]
         cl[ok] = cmap[cl[ok]]
     return cl, sb
 
@@ -133,9 +189,9 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
 
 
-def merge_across_ranks(eng, rank, world, timing=False, idx_base=0):
+def merge_across_ranks(eng, rank, world, timing=False):
     """GPU path: merge the tables, permute + all-reduce the coverage rows and small counters in place on the device.
-    Returns the merge time in ms (timing=True) or (global tables, (cluster_map, sub_map)) for this rank."""
+    Returns the merge time in ms (timing=True) or (global tables, (cluster_map, sub_map), local cl_sub_off)."""
     import torch
     import torch.distributed as dist
     from . import abi
@@ -156,4 +212,4 @@ def merge_across_ranks(eng, rank, world, timing=False, idx_base=0):
     dist.all_reduce(small)
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0)
-    return ms if timing else (glob, (cmap, smap))
+    return ms if timing else (glob, (cmap, smap), res["cl_sub_off"])

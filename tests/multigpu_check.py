@@ -27,9 +27,9 @@ eng.begin_chrom(0, g, w.annotation)
 eng.set_read_index_base(rank * per)
 eng.submit(b)
 eng.end_chrom()
-glob, (cmap, smap) = multigpu.merge_across_ranks(eng, rank, world)
+glob, (cmap, smap), cl_sub_off = multigpu.merge_across_ranks(eng, rank, world)
 res = eng.fetch(abi.NPT_FETCH_READS)
-cl, sb = multigpu.remap_reads(res, cmap, smap)
+cl, sb = multigpu.remap_reads(res, cmap, smap, cl_sub_off)
 v = eng.device_view()
 cov = torch.as_tensor(multigpu._DevPtr(v.coverage, v.coverage_elems), device="cuda").cpu().numpy().reshape(4, glob["n_clusters"], 2, v.cov_stride)
 small = torch.as_tensor(multigpu._DevPtr(v.small_counts, v.small_elems), device="cuda").cpu().numpy()
