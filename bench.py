@@ -197,8 +197,8 @@ def run_ours(args, rank, world, local_rank):
     eng = engine.Engine(cfg)
 
     def device_step():
-        eng.begin_chrom(0, g, w.annotation)
         eng.set_read_index_base(first)
+        eng.begin_chrom(0, g, w.annotation)
         eng.submit_device(n_reads, d["pos"].data_ptr(), d["flag"].data_ptr(), d["src"].data_ptr(), d["cigar_off"].data_ptr(),
                           d["cigar"].data_ptr(), d["seq_off"].data_ptr(), d["seq4"].data_ptr())
         eng.end_chrom()
@@ -249,8 +249,8 @@ def run_ours(args, rank, world, local_rank):
     h2d = sum(b.nbytes() for b in host_chunks)
 
     def e2e_step():
-        eng.begin_chrom(0, g, w.annotation)
         eng.set_read_index_base(first)
+        eng.begin_chrom(0, g, w.annotation)
         for b in host_chunks:
             eng.submit(b)
         eng.end_chrom()
@@ -315,6 +315,7 @@ def run_ours(args, rank, world, local_rank):
                        "mean_cigar_ops": float(d["cigar"].numel() / n_reads), "input_bytes_per_read": in_bytes / n_reads,
                        "l2_policy": "inputs (%.1f GB) larger than L2; no flush needed" % (in_bytes / 1e9),
                        "clusters": n_clusters, "sub_clusters": n_subs, "serial_path_reads": n_slow, "gen_seconds": gen_s,
+                       "merge_breakdown_ms": getattr(__import__("nptranscript_b200.multigpu", fromlist=["x"]).merge_across_ranks, "last", None) if world > 1 else None,
                        "timing": "CUDA events inside libnpt on its compute stream (npt_last_step_ms / npt_last_kernel_ms); wall ms/step %.2f" % wall_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "walk_kernel", "kernel_ms": wk, "finalize_ms": float(np.mean(fin_ms)), "algorithmic_bytes": alg,

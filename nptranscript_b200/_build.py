@@ -29,9 +29,9 @@ def _nvcc():
 
 
 def build_libnpt(force=False, verbose=False):
-    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp")))
     srcs.append(os.path.join(ROOT, "include", "npt.h"))
-    cus = [s for s in srcs if s.endswith(".cu")]
+    cus = [s for s in srcs if s.endswith((".cu", ".cpp"))]
     if not force and not _stale(LIBNPT, srcs):
         return LIBNPT
     nvcc = _nvcc()

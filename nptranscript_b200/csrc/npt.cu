@@ -470,7 +470,9 @@ void npt_destroy(npt_ctx* ctx) {
 int npt_set_read_index_base(npt_ctx* ctx, int64_t base) {
   if (!ctx) return NPT_EINVAL;
   if (base < 0 || base >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "read index base out of range");
+  if (ctx->in_chrom && !ctx->batches.empty()) return fail(ctx, NPT_ESTATE, "npt_set_read_index_base after the first npt_submit of a chromosome");
   ctx->idx_user_base = base;
+  ctx->idx_base = base;  // also valid when called between npt_begin_chrom and the first npt_submit
   return NPT_OK;
 }
 

@@ -23,8 +23,8 @@ w = workloads.SARS2
 g = synth.genome_codes(w)
 b = synth.generate(w, 78, per, first_index=rank * per, num_sources=2)
 eng = engine.Engine(engine.make_config(device=local, **KW))
-eng.begin_chrom(0, g, w.annotation)
 eng.set_read_index_base(rank * per)
+eng.begin_chrom(0, g, w.annotation)
 eng.submit(b)
 eng.end_chrom()
 glob, (cmap, smap), cl_sub_off = multigpu.merge_across_ranks(eng, rank, world)
