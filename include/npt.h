@@ -245,6 +245,9 @@ void npt_free_pinned(void* p);
 int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches);
 /* CUDA-event span on the compute stream from the first device work of npt_begin_chrom to the last of npt_end_chrom. */
 int npt_last_step_ms(npt_ctx* ctx, float* step_ms);
+/* Per-kernel CUDA-event durations summed over the batches of the last chromosome, in launch order:
+ * out4 = { walk_kernel<0> (breaks), walk_kernel<2> (long break lists), cluster_kernel, walk_kernel<1> (coverage) }. */
+int npt_last_stage_ms(npt_ctx* ctx, float* out4);
 
 #ifdef __cplusplus
 }

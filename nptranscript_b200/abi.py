@@ -63,7 +63,7 @@ class npt_device_view(C.Structure):
 SYMBOLS = [
     "npt_abi_version", "npt_create", "npt_destroy", "npt_last_error", "npt_begin_chrom", "npt_submit", "npt_wait",
     "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_remap_clusters", "npt_device_view_get",
-    "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms",
+    "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
     "npt_merge_tables", "npt_merged_results", "npt_merged_cluster_map", "npt_merged_sub_map", "npt_merge_free",
 ]
 
@@ -92,6 +92,8 @@ def declare(lib):
     lib.npt_free_pinned.restype = None
     lib.npt_last_kernel_ms.argtypes = [vp, P(C.c_float), P(C.c_float), P(i64), P(i64)]
     lib.npt_last_step_ms.argtypes = [vp, P(C.c_float)]
+    lib.npt_last_stage_ms.argtypes = [vp, P(C.c_float)]
+    lib.npt_last_stage_ms.restype = C.c_int
     lib.npt_merge_tables.argtypes = [C.c_int, P(P(npt_results)), C.c_int]
     lib.npt_merge_tables.restype = vp
     lib.npt_merged_results.argtypes = [vp]

@@ -143,6 +143,8 @@ struct npt_ctx {
   float walk_ms = 0, fin_ms = 0;
   int64_t walk_launches = 0, total_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> walk_events;
+  std::vector<cudaEvent_t> stage_events;  // 5 per batch: before walk<0>, after walk<0>, after walk<2>, after cluster, after walk<1>
+  float stage_ms[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -316,21 +318,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
 int launch_batch(npt_ctx* ctx, const BatchDev& bd, int from_stage) {
   const DevCfg& dc = ctx->dc;
   const int T = WALK_THREADS;
+  cudaEvent_t ev[5];
+  for (auto& e : ev) { CK(cudaEventCreate(&e)); ctx->stage_events.push_back(e); }
+  CK(cudaEventRecord(ev[0], ctx->s_comp));
   if (ctx->ref_smem) {
     if (from_stage == 0) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    CK(cudaEventRecord(ev[1], ctx->s_comp));
     walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   } else {
     if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    CK(cudaEventRecord(ev[1], ctx->s_comp));
     walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   }
+  CK(cudaEventRecord(ev[2], ctx->s_comp));
   const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
   cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
+  CK(cudaEventRecord(ev[3], ctx->s_comp));
   ctx->total_launches += from_stage == 0 ? 3 : 2;
   if (dc.record_depth) {
     if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     else walk_kernel<1, false><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     ctx->total_launches++;
   }
+  CK(cudaEventRecord(ev[4], ctx->s_comp));
   CK(cudaGetLastError());
   return NPT_OK;
 }
@@ -391,6 +401,8 @@ void free_batches(npt_ctx* ctx) {
   for (auto& s : ctx->stg) { s.busy = false; s.batch_index = -1; }
   for (auto& e : ctx->walk_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   ctx->walk_events.clear();
+  for (auto& e : ctx->stage_events) cudaEventDestroy(e);
+  ctx->stage_events.clear();
 }
 
 }  // namespace
@@ -721,6 +733,9 @@ int npt_end_chrom(npt_ctx* ctx) {
   // walk time = sum over batches of the kernel's event span
   ctx->walk_ms = 0;
   for (auto& e : ctx->walk_events) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); ctx->walk_ms += ms; }
+  for (int k = 0; k < 4; k++) ctx->stage_ms[k] = 0;
+  for (size_t i = 0; i + 5 <= ctx->stage_events.size(); i += 5)
+    for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->stage_events[i + k], ctx->stage_events[i + k + 1])); ctx->stage_ms[k] += ms; }
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof ctx->h_counters, cudaMemcpyDeviceToHost));
   const unsigned er = ctx->h_counters[CN_ERROR];
   if (er) {
@@ -1029,6 +1044,12 @@ void* npt_alloc_pinned(size_t bytes) {
   return p;
 }
 void npt_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int npt_last_stage_ms(npt_ctx* ctx, float* out4) {
+  if (!ctx || !out4) return NPT_EINVAL;
+  for (int k = 0; k < 4; k++) out4[k] = ctx->stage_ms[k];
+  return NPT_OK;
+}
 
 int npt_last_step_ms(npt_ctx* ctx, float* step_ms) {
   if (!ctx || !step_ms) return NPT_EINVAL;
