@@ -325,6 +325,26 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   if (MODE == 0 && slow_windows) atomicAdd(c.counters + CN_SLOW, (unsigned)slow_windows);
 }
 
+// ------------------------------------------------------------------------------------------------ firstIsTranscriptome
+// Reads of sources != 0 contribute to Count.true_breaks / break_sum only while their sub-cluster has seen no source-0 read
+// (CigarCluster.java:85).  Runs at end of chromosome, before slots are rewritten to ids.
+__global__ void fit_fixup_kernel(const DevCfg c, const BatchDev b) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
+    const int sb_slot = b.sub[r];
+    if (sb_slot < 0 || b.src[r] == 0) continue;
+    const unsigned long long gidx = (unsigned long long)(b.idx_base + r);
+    if (gidx >= ldcg(c.sub_min0 + sb_slot)) continue;
+    const int nb = b.nbreaks[r];
+    const unsigned loc = b.break_loc[r];
+    const int* br = (loc == 0xFFFFFFFFu) ? b.break_arena + r * BRK_INLINE : b.break_arena + b.n * BRK_INLINE + loc;
+    atomicAdd(c.sub_break_sum + sb_slot, 1);
+    const unsigned off = (unsigned)(ldcg(&c.sb[sb_slot].word) & 0xffffffffu);
+    const unsigned soff = (unsigned)ldcg(c.sb_rec + off + 2);
+    if (ldcg(c.sb_rec + off + 3) == nb)
+      for (int i = 0; i < nb; i++) atomicAdd(c.sub_sums + soff + i, (unsigned long long)(long long)br[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ annotation lookups
 // Annotation.nextUpstream :87-97 (highest row i with leftBreak + tol >= start[i]) / EmptyAnnotation :22-24
 __device__ __forceinline__ int tok_up(const DevCfg& c, const int* ostart, const int* oname, const int* ostrand, int p, bool fwd) {
@@ -528,7 +548,11 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
         const unsigned long long idxf = (gidx << 2) | (unsigned long long)(((fwd_known && fwd) ? 1 : 0) | (neg ? 2 : 0));
         if (idxf < ldcg(&c.sb[sb_slot].min_idx)) atomicMin(&c.sb[sb_slot].min_idx, idxf);
         atomicAdd(c.sub_count + (size_t)sb_slot * c.S + src, 1);  // Count.increment / new Count
-        if (c.track_sums) {                                         // Count.addBreaks :84-96 (exact integer sums)
+        // Count.addBreaks :84-96 (exact integer sums).  With firstIsTranscriptome only source-0 reads add here; a read of
+        // another source adds iff no source-0 read of its sub-cluster came before it (count[0]==0 at that time), which is
+        // decided once the first source-0 index is final (fit_fixup_kernel at end of chromosome).
+        if (c.fit && src == 0 && gidx < ldcg(c.sub_min0 + sb_slot)) atomicMin(c.sub_min0 + sb_slot, gidx);
+        if (c.track_sums && (!c.fit || src == 0)) {
           atomicAdd(c.sub_break_sum + sb_slot, 1);
           const unsigned off = (unsigned)(ldcg(&c.sb[sb_slot].word) & 0xffffffffu);
           const unsigned soff = (unsigned)ldcg(c.sb_rec + off + 2);

@@ -93,7 +93,7 @@ struct npt_ctx {
   DBuf<int> d_cl_rec;
   DBuf<Slot> d_sb;
   DBuf<int> d_sb_rec, d_sub_count, d_sub_break_sum;
-  DBuf<unsigned long long> d_sub_sums;
+  DBuf<unsigned long long> d_sub_sums, d_sub_min0;
   int walk_blocks[3] = {0, 0, 0};   // grid sizes of walk_kernel<0/1/2>
   size_t walk_smem = 0, cluster_smem = 0;
   DBuf<PairEntry> d_pr;
@@ -422,8 +422,6 @@ int npt_create(const npt_config* cfg, npt_ctx** out) {
   if (cfg->num_sources < 1 || cfg->num_sources > NPT_MAX_SOURCES) return fail(nullptr, NPT_EINVAL, "num_sources out of range");
   if (cfg->bin < 1) return fail(nullptr, NPT_EINVAL, "bin must be >= 1");
   if (cfg->break_thresh < 0) return fail(nullptr, NPT_EINVAL, "break_thresh must be >= 0");
-  if (cfg->first_is_transcriptome)
-    return fail(nullptr, NPT_EINVAL, "first_is_transcriptome is not supported yet (order-dependent Count.addBreaks, CigarCluster.java:85)");
   if (cfg->coronavirus)
     for (int s = 0; s < cfg->num_sources; s++)
       if (!cfg->rna[s])
@@ -460,7 +458,7 @@ void npt_destroy(npt_ctx* ctx) {
   ctx->pool_free.clear();
   ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
-  ctx->d_sub_sums.release(); ctx->d_pr.release();
+  ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
   ctx->d_cov.release(); ctx->d_cov_out.release(); ctx->d_small.release(); ctx->d_counters.release(); ctx->d_keys.release();
   ctx->d_keys2.release(); ctx->d_vals.release(); ctx->d_vals2.release(); ctx->d_cl_slot.release(); ctx->d_sb_slot.release();
   ctx->d_cl_rank.release(); ctx->d_cl_slot_rank.release(); ctx->d_sb_grank.release(); ctx->d_cl_sub_off.release(); ctx->d_cub.release(); ctx->d_break_off.release();
@@ -512,7 +510,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   memset(&dc, 0, sizeof dc);
   dc.T = cf.break_thresh; dc.bin = cf.bin; dc.include_start = cf.include_start; dc.coronavirus = cf.coronavirus;
   dc.start_thresh = cf.start_thresh; dc.end_thresh = cf.end_thresh; dc.enforce_strand = cf.enforce_strand;
-  dc.record_depth = cf.record_depth; dc.calc_breaks1 = calc_breaks1; dc.fit = 0; dc.track_sums = cf.track_break_sums;
+  dc.record_depth = cf.record_depth; dc.calc_breaks1 = calc_breaks1; dc.fit = cf.first_is_transcriptome ? 1 : 0; dc.track_sums = cf.track_break_sums;
   dc.S = cf.num_sources; dc.min_fl_exon = cf.coronavirus ? 0 : 10;
   dc.rna_mask = 0;
   for (int s = 0; s < cf.num_sources; s++) if (cf.rna[s]) dc.rna_mask |= 1u << s;
@@ -551,6 +549,11 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(ctx->d_sub_sums.ensure(std::max<unsigned>(dc.sums_cap, 1)));
   dc.cl_rec = ctx->d_cl_rec.p; dc.sb_rec = ctx->d_sb_rec.p; dc.sub_count = ctx->d_sub_count.p; dc.sub_break_sum = ctx->d_sub_break_sum.p;
   dc.sub_sums = ctx->d_sub_sums.p;
+  if (dc.fit) {
+    CK(ctx->d_sub_min0.ensure(nsb));
+    CK(cudaMemsetAsync(ctx->d_sub_min0.p, 0xFF, (size_t)nsb * 8, ctx->s_comp));
+  }
+  dc.sub_min0 = ctx->d_sub_min0.p;
   CK(cudaMemsetAsync(ctx->d_sub_count.p, 0, (size_t)nsb * dc.S * 4, ctx->s_comp));
   CK(cudaMemsetAsync(ctx->d_sub_break_sum.p, 0, (size_t)nsb * 4, ctx->s_comp));
   CK(cudaMemsetAsync(ctx->d_sub_sums.p, 0, (size_t)std::max<unsigned>(dc.sums_cap, 1) * 8, ctx->s_comp));
@@ -754,6 +757,14 @@ int npt_end_chrom(npt_ctx* ctx) {
   if (ns < nc) return fail(ctx, NPT_ECUDA, "internal: %d sub-clusters for %d clusters", ns, nc);
   ctx->n_clusters = nc; ctx->n_subs = ns;
   CK(cudaEventRecord(ctx->ev_a, ctx->s_comp));
+  if (dc.fit && dc.track_sums) {
+    for (auto& B : ctx->batches) {
+      const int grid = (int)std::min<int64_t>((B.n + 255) / 256, ctx->sm_count * 16);
+      fit_fixup_kernel<<<grid, 256, 0, ctx->s_comp>>>(dc, B.d);
+      ctx->total_launches++;
+    }
+    CK(cudaGetLastError());
+  }
   const int nmax = std::max(std::max(nc, ns), 1);
   CK(ctx->d_keys.ensure(nmax)); CK(ctx->d_keys2.ensure(nmax)); CK(ctx->d_vals.ensure(nmax)); CK(ctx->d_vals2.ensure(nmax));
   CK(ctx->d_cl_slot.ensure(std::max(nc, 1))); CK(ctx->d_sb_slot.ensure(std::max(ns, 1)));

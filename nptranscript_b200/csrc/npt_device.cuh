@@ -56,6 +56,7 @@ struct DevCfg {
   int* sb_rec; unsigned sbkey_cap;
   int* sub_count;            // [sb slots][S]
   int* sub_break_sum;        // [sb slots]
+  unsigned long long* sub_min0;  // [sb slots] firstIsTranscriptome: first global index of a source-0 read of the sub-cluster
   unsigned long long* sub_sums; unsigned sums_cap;
   PairEntry* pr; unsigned pr_mask; int pr_cap;
   int* cov; int cov_cap;     // [4][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd

@@ -87,6 +87,26 @@ def sub_id(chrom_index, c, k):
     return f"ID{chrom_index}.{c}.t{k}"  # CigarCluster.java:660, CigarClusters.java:85
 
 
+def sub_names(res, src, read_names, chrom_index, first_is_transcriptome=False):
+    """Per-read subID column.  Normally "ID<chr>.<c>.t<k>".  With --firstIsTranscriptome a sub-cluster is named after the
+    most recent source-0 read seen in it so far, this read included (CigarClusters.java:85, CigarCluster.java:657-669)."""
+    n = res["n_reads"]
+    cl, sb = res["cluster_id"].astype(np.int64), res["sub_id"].astype(np.int64)
+    base = [sub_id(chrom_index, int(c), int(k)) if c >= 0 else "" for c, k in zip(cl, sb)]
+    if not first_is_transcriptome:
+        return base
+    g = np.where(cl >= 0, res["cl_sub_off"].astype(np.int64)[np.maximum(cl, 0)] + sb, -1)
+    order = np.argsort(g, kind="stable")
+    gs = g[order]
+    mark = np.where(np.asarray(src)[order] == 0, order, -1)        # read index where source 0, else -1
+    # running maximum inside each group of equal g: offset every group so that earlier groups cannot leak in
+    grp = np.cumsum(np.concatenate([[0], gs[1:] != gs[:-1]]))
+    run = np.maximum.accumulate(mark + grp * (n + 1)) - grp * (n + 1)
+    last0 = np.full(n, -1, np.int64)
+    last0[order] = np.where(run >= 0, run, -1)
+    return [read_names[int(j)] if (j >= 0 and c >= 0) else b for j, b, c in zip(last0, base, cl)]
+
+
 def read_to_cluster_rows(res, read_names, annotation, chrom_name, chrom_index, record_depth, qvals=None, coronavirus=True):
     """Rows of 0.readToCluster.txt.gz exactly as IdentityProfile1.commit builds them (:133-136); header Outputs.java:313-318.
     span columns are "." / 0 for CSV and empty annotations (Annotation.getSpan :252-255)."""
@@ -169,7 +189,7 @@ def annot_rows(res, annotation):
     return rows
 
 
-def consensus_breaks(res, sub_index):
+def consensus_breaks(res, sub_index, src=None, first_is_transcriptome=False):
     """Count.getBreaks (J/cluster/CigarCluster.java:99-108): Math.round(true_breaks[i] * (1e3 / break_sum)) where
     true_breaks[i] is the arrival-order double sum of break/1e3.  The device returns exact int64 sums; the double sum
     differs from the exact value by < n·2^-50 relative, so the rounding can only differ when the exact mean is within
@@ -196,6 +216,11 @@ def consensus_breaks(res, sub_index):
     cl = int(np.searchsorted(res["cl_sub_off"], sub_index, side="right") - 1)
     k = sub_index - int(res["cl_sub_off"][cl])
     idx = np.flatnonzero((res["cluster_id"] == cl) & (res["sub_id"] == k))
+    if first_is_transcriptome:
+        # only source-0 reads and the reads that came before the sub-cluster's first source-0 read count (CigarCluster.java:85)
+        s_ = np.asarray(src)[idx]
+        first0 = idx[s_ == 0].min() if (s_ == 0).any() else np.iinfo(np.int64).max
+        idx = idx[(s_ == 0) | (idx < first0)]
     bo = res["break_off"]
     tb = [0.0] * len(sums)
     for r in idx:

@@ -26,6 +26,7 @@ class Flags:
     record_depth: bool = False
     calc_breaks: bool = True
     write_gff_or_isoforms: bool = True
+    first_is_transcriptome: bool = False
     num_sources: int = 1
     rna: Tuple[bool, ...] = (True,) * 16
 
@@ -118,7 +119,7 @@ class Run:
         self.calc_breaks1 = flags.calc_breaks and flags.coronavirus and flags.break_thresh < len(ref_codes)  # :882
         self.rows = []  # per read: dict
 
-    def process(self, pos, flag, src, cig, bases):
+    def process(self, pos, flag, src, cig, bases, read_name=None):
         f, T, G = self.f, self.f.break_thresh, len(self.ref)
         if pos <= 0 or any(op > 8 for _, op in cig):
             self.rows.append(dict(ok=False))
@@ -261,12 +262,16 @@ class Run:
         if cl is None:
             cl = Cluster(id=f"ID{self.chrom_index}.{len(self.clusters)}", key=key, breaks=list(br), read_count=[0] * f.num_sources)
             self.clusters[key] = cl
+        fit = f.first_is_transcriptome
         sub = cl.subs.get(br)
         if sub is None:
-            sub = dict(id=f"{cl.id}.t{len(cl.subs)}", count=[0] * f.num_sources, true_breaks=None, break_sum=0, forward=forward, neg=neg)
+            sid = read_name if (fit and src == 0) else f"{cl.id}.t{len(cl.subs)}"   # CigarClusters.java:85 / CigarCluster.java:657-661
+            sub = dict(id=sid, count=[0] * f.num_sources, true_breaks=None, break_sum=0, forward=forward, neg=neg)
             cl.subs[br] = sub
+        elif fit and src == 0:
+            sub["id"] = read_name                                                      # CigarCluster.java:667-669
         sub["count"][src] += 1
-        if f.write_gff_or_isoforms:  # Count.addBreaks :84-96
+        if f.write_gff_or_isoforms and (not fit or src == 0 or sub["count"][0] == 0):  # Count.addBreaks :84-96
             sub["break_sum"] += 1
             if sub["true_breaks"] is None:
                 sub["true_breaks"] = [0.0] * nb

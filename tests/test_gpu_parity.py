@@ -73,6 +73,8 @@ def test_fuzz_bad_ops():
 
 
 @pytest.mark.parametrize("kw", [
+    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1], first_is_transcriptome=1),  # opts_host.txt
+    dict(bin=10, break_thresh=1000, coronavirus=1, record_depth=1, rna=[1, 1], first_is_transcriptome=1),
     dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1]),
     dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[0, 1]),
     dict(bin=10, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, rna=[1, 0]),

@@ -16,23 +16,28 @@ def _compare(kw, annotation, batches, chrom_index=0):
     fl = py_oracle.Flags(bin=kw.get("bin", 1), break_thresh=kw.get("break_thresh", 1000), include_start=bool(kw.get("include_start", 1)),
                          coronavirus=bool(kw.get("coronavirus", 1)), start_thresh=kw.get("start_thresh", 100), end_thresh=kw.get("end_thresh", 100),
                          enforce_strand=bool(kw.get("enforce_strand", 0)), record_depth=bool(kw.get("record_depth", 0)),
-                         num_sources=kw.get("num_sources", 1), rna=tuple(bool(x) for x in kw.get("rna", [1] * 16)))
+                         num_sources=kw.get("num_sources", 1), rna=tuple(bool(x) for x in kw.get("rna", [1] * 16)),
+                         first_is_transcriptome=bool(kw.get("first_is_transcriptome", 0)))
     empty = annotation.kind == abi.NPT_ANNOT_EMPTY
     ann = py_oracle.Annot(annotation.genes, annotation.start, annotation.end, annotation.strand, len(g), fl, empty=empty, chrom_index=chrom_index)
     run = py_oracle.Run(fl, g.tolist(), ann, chrom_index)
+    names, srcs = [], []
     for b in batches:
         for rd in py_oracle.unpack_batch(b):
-            run.process(*rd)
+            names.append(f"read{len(names)}")
+            srcs.append(rd[2])
+            run.process(*rd, read_name=names[-1])
     keys = render.cluster_keys(ora, annotation, chrom_index, coronavirus=fl.coronavirus)
     render.check_key_aliasing(keys)
     assert keys == [c.key for c in run.clusters.values()]
     bo = ora["break_off"]
+    subn = render.sub_names(ora, srcs, names, chrom_index, fl.first_is_transcriptome)
     for i, row in enumerate(run.rows):
         if not row["ok"]:
             assert int(ora["read_flags"][i]) & abi.NPT_RF_BADCIGAR
             continue
         c, k = int(ora["cluster_id"][i]), int(ora["sub_id"][i])
-        assert render.cluster_id(chrom_index, c) == row["cluster"] and render.sub_id(chrom_index, c, k) == row["sub"], i
+        assert render.cluster_id(chrom_index, c) == row["cluster"] and subn[i] == row["sub"], i
         assert ora["breaks"][int(bo[i]):int(bo[i + 1])].tolist() == row["breaks"], i
         assert (int(ora["start_pos"][i]), int(ora["end_pos"][i]), int(ora["read_st"][i]), int(ora["read_en"][i])) == \
                (row["start_pos"], row["end_pos"], row["read_st"], row["read_en"]), i
@@ -55,7 +60,7 @@ def _compare(kw, annotation, batches, chrom_index=0):
             assert int(ora["sub_break_sum"][g_]) == sub["break_sum"]
             tb = ora["sub_true_breaks"][int(to[g_]):int(to[g_ + 1])]
             assert np.array_equal(tb, np.array(sub["true_breaks"])), "arrival-order double sums must be bit-identical"
-            cons = render.consensus_breaks(ora, g_)
+            cons = render.consensus_breaks(ora, g_, srcs, fl.first_is_transcriptome)
             ref = [int(np.floor(t * (1e3 / sub["break_sum"]) + 0.5)) for t in sub["true_breaks"]]
             assert cons.tolist() == ref
         if fl.record_depth:
@@ -84,6 +89,7 @@ def test_virus_mode(kw):
 
 
 @pytest.mark.parametrize("kw", [
+    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, num_sources=2, rna=[1, 1], first_is_transcriptome=1),
     dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, num_sources=2, rna=[1, 0]),
     dict(bin=10, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, num_sources=2, rna=[1, 1]),
 ])
