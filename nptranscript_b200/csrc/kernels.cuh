@@ -124,11 +124,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   };
 
   // Fixed loop body, re-converged with __syncwarp at two points per iteration:
-  //   (R1) warp-cooperative, coalesced refill of the CIGAR tiles of the lanes that ran out of staged ops;
-  //   (A)  a lane whose M op has no windows left takes ONE step: set up the next read, finish the current one, or consume
-  //        one CIGAR element from its tile (straight-line predicated code);
-  //   (R2) coalesced refill of the base tiles of the lanes whose next window is not staged;
-  //   (B)  every lane that is inside an M op compares one 8-base window from its tile.
+  //   (A)  a lane whose M op has no windows left takes up to TWO steps: set up the next read, finish the current one, or
+  //        consume one CIGAR element from its tile (straight-line predicated code);
+  //   (R)  warp-cooperative, coalesced refill of the CIGAR / base tiles of the lanes that ran out of staged words;
+  //   (B)  every lane that is inside an M op compares up to 16 bases (two 8-base windows) from its tile.
   // Lanes never touch global memory for the streams themselves: a lane-private 4-byte global load drags a 32-byte sector
   // through L1 that is evicted before its neighbours are used (ncu r01h: 13 KB of L2->L1 traffic per 1.7 KB read, 40 warps
   // slower than 24).  Lanes that ran out of reads stay in the loop (idle) until the whole warp is done so that the
@@ -141,20 +140,6 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   uint32_t dmask = 0; int dpos = 0;  // MODE 1: error positions of a D/X op, flushed in phase (B)
   const unsigned half = lane >> 4, hl = lane & 15;
   for (;;) {
-    __syncwarp();
-    // ---- (R1) CIGAR tiles: two lanes are served per step, one by each half-warp (16 words = 64 bytes, coalesced)
-    {
-      unsigned need = __ballot_sync(0xffffffffu, active && mOff >= mN && ckg < cendg && ckg - cs >= (uint32_t)TILE_W);
-      while (need) {
-        const int La = __ffs(need) - 1; need &= need - 1;
-        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
-        const int L = half ? Lb : La;
-        const uint32_t start = __shfl_sync(0xffffffffu, ckg, L);
-        const uint32_t v = __ldg(b.cigar + min((long long)start + hl, cig_last));
-        cigTile[L * TILE_STRIDE + hl] = v;
-        if ((int)lane == La || (int)lane == Lb) cs = ckg;
-      }
-    }
     __syncwarp();
     // ---- (A) up to two steps per iteration: the usual pattern is one I/D element between two M elements
 #pragma unroll 1
@@ -270,12 +255,26 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
     }
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
-    // ---- (R2) base tiles: the window at read offset mRpos+mOff needs words k, k+1 of this read's packed bases
+    // ---- (R) one refill point per iteration.  CIGAR tiles: lanes whose staged ops ran out (the ops are consumed by the
+    // next iteration's phase A; a tile is valid by index, so filling it early is harmless).  Base tiles: the windows at
+    // read offset mRpos+mOff need words k..k+2 of this read's packed bases.  Two lanes are served per step, one by each
+    // half-warp (16 words = 64 bytes, coalesced).
+    {
+      unsigned need = __ballot_sync(0xffffffffu, active && ckg < cendg && ckg - cs >= (uint32_t)TILE_W);
+      while (need) {
+        const int La = __ffs(need) - 1; need &= need - 1;
+        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
+        const int L = half ? Lb : La;
+        const uint32_t start = __shfl_sync(0xffffffffu, ckg, L);
+        cigTile[L * TILE_STRIDE + hl] = __ldg(b.cigar + min((long long)start + hl, cig_last));
+        if ((int)lane == La || (int)lane == Lb) cs = ckg;
+      }
+    }
     const bool hasWin = !done && mOff < mN;
     const uint32_t nibw = nib0 + (uint32_t)(mRpos + mOff);
     const uint32_t kg = nibw >> 3;  // word index relative to rp
     {
-      unsigned need = __ballot_sync(0xffffffffu, hasWin && kg - ss >= (uint32_t)TILE_W);
+      unsigned need = __ballot_sync(0xffffffffu, hasWin && kg - ss >= (uint32_t)(TILE_W - 1));
       while (need) {
         const int La = __ffs(need) - 1; need &= need - 1;
         const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
@@ -287,33 +286,49 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       }
     }
     __syncwarp();
-    uint32_t mis = 0;
+    uint32_t misA = 0, misB = 0;
     int pos0 = 0;
     if (hasWin) {
-      // ---- (B) one 8-base window of the current M op
-      const int cnt = min(8, mN - mOff);
+      // ---- (B) up to 16 bases (two 8-base windows) of the current M op
+      const int cnt = min(16, mN - mOff);
+      const int cntA = min(8, cnt), cntB = cnt - cntA;
       pos0 = mStart0 + 1 + mOff;
       const int ki = (int)(kg - ss);
-      const uint32_t rw = __funnelshift_l(__byte_perm(mySeq[ki + 1], 0, 0x0123), __byte_perm(mySeq[ki], 0, 0x0123), (nibw & 7) << 2);
-      uint32_t mat;
-      cmp8(rw, ref_win8(refw, (uint32_t)(mStart0 + mOff)), cnt, mis, mat);
-      mOff += 8;
-      errs += __popc(mis);
-      if (per_base || pos0 + cnt - 1 - prev > T) {
-        // a break or a mapStart/mapEnd event is possible inside this window: exact per-base CigarCluster.add
+      const uint32_t sh = (nibw & 7) << 2;
+      const uint32_t w0 = __byte_perm(mySeq[ki], 0, 0x0123), w1 = __byte_perm(mySeq[ki + 1], 0, 0x0123), w2 = __byte_perm(mySeq[ki + 2], 0, 0x0123);
+      const uint32_t rn = (uint32_t)(mStart0 + mOff), rk = rn >> 3, rs = (rn & 7) << 2;
+      const uint32_t g0 = refw[rk], g1 = refw[rk + 1], g2 = refw[rk + 2];
+      uint32_t matA, matB = 0;
+      cmp8(__funnelshift_l(w1, w0, sh), __funnelshift_l(g1, g0, rs), cntA, misA, matA);
+      if (cntB > 0) cmp8(__funnelshift_l(w2, w1, sh), __funnelshift_l(g2, g1, rs), cntB, misB, matB);
+      mOff += 16;
+      errs += __popc(misA) + __popc(misB);
+      // Fast path only when the last match lies BEFORE the windows and every position is within T of it (then no position can
+      // be a break, whatever the matches inside).  After an '=' op prev can lie ahead of the window (advance-then-emit
+      // quirk): matches then pull prev back and a gap of up to 15 can open inside the 16 bases.
+      if (per_base || prev >= pos0 || pos0 + cnt - 1 - prev > T) {
+        // a break or a mapStart/mapEnd event is possible inside these windows: exact per-base CigarCluster.add
         slow_windows++;
-        for (int i = 0; i < cnt; i++) add(pos0 + i, (mat >> (28 - 4 * i)) & 1u);
-      } else if (mat) {
-        prev = pos0 + 7 - ((__ffs(mat) - 1) >> 2);  // every position of the window is within T of the last match before it
+        for (int i = 0; i < cntA; i++) add(pos0 + i, (matA >> (28 - 4 * i)) & 1u);
+        for (int i = 0; i < cntB; i++) add(pos0 + 8 + i, (matB >> (28 - 4 * i)) & 1u);
+      } else if (matB) {
+        prev = pos0 + 15 - ((__ffs(matB) - 1) >> 2);  // every position is within T of the last match before it
+      } else if (matA) {
+        prev = pos0 + 7 - ((__ffs(matA) - 1) >> 2);
       }
     }
     if (MODE == 1) {
       // error positions: mismatches of this window and/or the D/X op consumed in phase (A)
       int* err_row = cov + arr_stride;
-      while (mis) {
-        const int bit = 31 - __clz(mis);
-        mis &= ~(1u << bit);
+      while (misA) {
+        const int bit = 31 - __clz(misA);
+        misA &= ~(1u << bit);
         atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
+      }
+      while (misB) {
+        const int bit = 31 - __clz(misB);
+        misB &= ~(1u << bit);
+        atomicAdd(err_row + pos0 + 8 + ((28 - bit) >> 2), 1);
       }
       while (dmask) {
         const int bit = 31 - __clz(dmask);
