@@ -27,6 +27,8 @@ constexpr int WALK_THREADS = 256;
 constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
 constexpr int MAX_BREAKS = 1 << 20;
 constexpr int TILE_W = 16;        // words per lane tile (CIGAR: 16 ops; bases: 128 + one overlap word)
+constexpr int DEL_HIST = 4;        // deletion lengths recorded in the per-length histogram rows (coverage arrays 4..7)
+constexpr int COV_ARRAYS = 4 + DEL_HIST;
 constexpr int TILE_STRIDE = 17;   // odd stride: lane tiles start in different banks
 
 template <typename T>
@@ -237,6 +239,15 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           maps += nE;
           errs += isDX ? nE : 0;
           if (isM) { mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE; }
+          // Short deletions (the bulk of the coverage events of a noisy read) are recorded as ONE point in a per-length
+          // histogram instead of 4 depth-difference events + len error points: when the previous depth run ends right before
+          // the deletion the run is simply carried across it, and coverage_rows_kernel removes the deleted positions and adds
+          // the "advance, then emit" positions (depth and error) from the histogram at end of chromosome.
+          if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 &&
+              !(prev > 0 && base + nE - 1 - prev > T)) {
+            atomicAdd(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
+            pendingEnd = base;
+          } else
           if (MODE == 1 && nE > 0) {
             depth_run(base, nE);
             if (isDX) {

@@ -279,8 +279,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
   const int src = row % S, prov = (row / S) % n_prov, arr = row / (S * n_prov);
   const int orow = row_of_prov[prov];
   if (orow < 0) return;
-  const int* in = cov + (((size_t)arr * cov_cap + prov) * S + src) * stride;
+  const size_t arr_stride = (size_t)cov_cap * S * stride;
+  const size_t rowoff = ((size_t)prov * S + src) * stride;
+  const int* in = cov + arr * arr_stride + rowoff;
   int* o = out + (((size_t)arr * n_rows + orow) * S + src) * stride;
+  // deletion histogram rows (arrays 4..): dh[l-1][p] = deletions of length l whose first deleted position is p.  The walk
+  // carried the depth run across them, so: remove the deleted positions [p, p+l-1], add the positions the reference emits
+  // after advancing, [p+l, p+2l-1], to depth and to errors (the D quirk, IdentityProfile1.java:513-522).
+  auto dh = [&](int l, int p) -> int { return (p >= 0 && p < stride) ? cov[(size_t)(3 + l) * arr_stride + rowoff + p] : 0; };
+  if (arr == 1) {
+    for (int i = threadIdx.x; i < stride; i += SCAN_THREADS) {
+      int v = in[i];
+      for (int l = 1; l <= DEL_HIST; l++) for (int j = 0; j < l; j++) v += dh(l, i - l - j);
+      o[i] = v;
+    }
+    return;
+  }
   if (arr != 0) {
     for (int i = threadIdx.x; i < stride; i += SCAN_THREADS) o[i] = in[i];
     return;
@@ -295,7 +309,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
     int sum = 0;
     const int i0 = base + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (i0 + j < stride) ? in[i0 + j] : 0; sum += v[j]; v[j] = sum; }
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+      int x = 0;
+      if (i0 + j < stride) {
+        x = in[i0 + j];
+        for (int l = 1; l <= DEL_HIST; l++) x += -dh(l, i0 + j) + 2 * dh(l, i0 + j - l) - dh(l, i0 + j - 2 * l);
+      }
+      v[j] = x; sum += v[j]; v[j] = sum;
+    }
     int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += t; }
@@ -557,7 +578,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(cudaMemsetAsync(ctx->d_sub_count.p, 0, (size_t)nsb * dc.S * 4, ctx->s_comp));
   CK(cudaMemsetAsync(ctx->d_sub_break_sum.p, 0, (size_t)nsb * 4, ctx->s_comp));
   CK(cudaMemsetAsync(ctx->d_sub_sums.p, 0, (size_t)std::max<unsigned>(dc.sums_cap, 1) * 8, ctx->s_comp));
-  const size_t cov_elems = 4ull * max_cov * dc.S * dc.stride;
+  const size_t cov_elems = (size_t)COV_ARRAYS * max_cov * dc.S * dc.stride;
   if (cf.record_depth) {
     cudaError_t e = ctx->d_cov.ensure(cov_elems);
     if (e != cudaSuccess) return fail(ctx, NPT_ENOMEM, "coverage rows: %zu bytes for %d clusters (lower max_coverage_clusters)", cov_elems * 4, max_cov);

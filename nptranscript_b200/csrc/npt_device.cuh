@@ -59,7 +59,7 @@ struct DevCfg {
   unsigned long long* sub_min0;  // [sb slots] firstIsTranscriptome: first global index of a source-0 read of the sub-cluster
   unsigned long long* sub_sums; unsigned sums_cap;
   PairEntry* pr; unsigned pr_mask; int pr_cap;
-  int* cov; int cov_cap;     // [4][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd
+  int* cov; int cov_cap;     // [8][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd, deletions of length 1..4 by first deleted position
   int* small;                // total_counts[S], spliced[S][n_orf], unspliced[S][n_orf]
   unsigned* counters;
 };
