@@ -403,7 +403,12 @@ __device__ void pair_add(const DevCfg& c, int src, int level, int st, int en) {
         k = key;
       }
     }
-    if (k == key) { atomicAdd(&e->count, 1); return; }
+    if (k == key) {
+      // opportunistic warp aggregation: the canonical junctions are hit by a large share of the reads
+      const unsigned grp = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)e);
+      if ((__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&e->count, __popc(grp));
+      return;
+    }
   }
   atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
 }
@@ -573,17 +578,29 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
       else {
         const unsigned long long idxf = (gidx << 2) | (unsigned long long)(((fwd_known && fwd) ? 1 : 0) | (neg ? 2 : 0));
         if (idxf < ldcg(&c.sb[sb_slot].min_idx)) atomicMin(&c.sb[sb_slot].min_idx, idxf);
-        atomicAdd(c.sub_count + (size_t)sb_slot * c.S + src, 1);  // Count.increment / new Count
         // Count.addBreaks :84-96 (exact integer sums).  With firstIsTranscriptome only source-0 reads add here; a read of
         // another source adds iff no source-0 read of its sub-cluster came before it (count[0]==0 at that time), which is
         // decided once the first source-0 index is final (fit_fixup_kernel at end of chromosome).
         if (c.fit && src == 0 && gidx < ldcg(c.sub_min0 + sb_slot)) atomicMin(c.sub_min0 + sb_slot, gidx);
-        if (c.track_sums && (!c.fit || src == 0)) {
-          atomicAdd(c.sub_break_sum + sb_slot, 1);
+        const bool addb = c.track_sums && (!c.fit || src == 0);
+        // Warp-aggregated updates: a few sub-clusters own most reads (one owns ~40 % of the dRNA workload), so per-read
+        // atomics on their counters serialise in L2 (ncu r01m: cluster_kernel 6 % issue-active).  Lanes of the warp that
+        // hit the same (sub-cluster, source) elect a leader that adds the group's totals once.
+        const unsigned conv = __activemask();
+        const unsigned grp = __match_any_sync(conv, ((unsigned long long)(unsigned)sb_slot << 8) | ((unsigned long long)src << 1) | (addb ? 1ull : 0ull));
+        const bool leader_lane = (__ffs(grp) - 1) == (int)(threadIdx.x & 31);
+        const int gn = __popc(grp);
+        if (leader_lane) atomicAdd(c.sub_count + (size_t)sb_slot * c.S + src, gn);  // Count.increment / new Count
+        if (addb) {
+          if (leader_lane) atomicAdd(c.sub_break_sum + sb_slot, gn);
           const unsigned off = (unsigned)(ldcg(&c.sb[sb_slot].word) & 0xffffffffu);
           const unsigned soff = (unsigned)ldcg(c.sb_rec + off + 2);
-          if (ldcg(c.sb_rec + off + 3) == nb)
-            for (int i = 0; i < nb; i++) atomicAdd(c.sub_sums + soff + i, (unsigned long long)(long long)br[i]);
+          if (ldcg(c.sb_rec + off + 3) == nb)   // same sub-cluster => same number of breaks for every lane of the group
+            for (int i = 0; i < nb; i++) {
+              const unsigned v = (unsigned)br[i];
+              const unsigned lo = __reduce_add_sync(grp, v & 0xFFFFu), hi = __reduce_add_sync(grp, v >> 16);
+              if (leader_lane) atomicAdd(c.sub_sums + soff + i, ((unsigned long long)hi << 16) + lo);
+            }
         }
       }
     }
