@@ -55,6 +55,7 @@ extern "C" {
 /* annotation kinds: J/cluster/Annotation.java (CSV ORF table), J/cluster/EmptyAnnotation.java */
 #define NPT_ANNOT_CSV 0
 #define NPT_ANNOT_EMPTY 1
+#define NPT_ANNOT_GFF 2   /* exon table of one chromosome, J/cluster/GFFAnnotation.java:368-459 (host mode, coronavirus=0) */
 
 /* where the arrays of an npt_batch live */
 #define NPT_MEM_HOST 0
@@ -73,6 +74,10 @@ extern "C" {
 /* first token when the 5'/3' end names are left out of the key (!includeStart and more than two breaks,
  * IdentityProfile1.java:267,289): "a,b_" (4 breaks) must not collide with "a_b" (2 breaks). */
 #define NPT_TOK_NOENDS (-5)
+/* GFF mode: first token of a key made of gene names; the following tokens are name ids in the iteration order of the
+ * reference's HashSet<String> (J/cluster/IdentityProfile1.java:301-318), each rendered as name + '_'.  A key without the
+ * marker is the single coordinate token floor(pos/bin) rendered "<chr>.<bin>" (GFFAnnotation.getCoord :132-135). */
+#define NPT_TOK_GENESET (-6)
 
 /* per-read flag bits in npt_results.read_flags */
 #define NPT_RF_TYPE_MASK 0x3u  /* Annotation.getTypeInd: 0=5_3 1=5_no3 2=no5_3 3=no5_no3 (J/cluster/Annotation.java:233-236) */
@@ -105,7 +110,9 @@ typedef struct npt_config {
 } npt_config;
 
 /* ORF table of one chromosome (J/cluster/Annotation.java:138-179) as parallel arrays, in file row order
- * (rows with Direction=both are already duplicated by the caller when enforce_strand, :160-164). */
+ * (rows with Direction=both are already duplicated by the caller when enforce_strand, :160-164).
+ * NPT_ANNOT_GFF: one row per exon line of the chromosome in file order (start, end, strand, gene = the exon's parent
+ * attribute, J/cluster/GFFAnnotation.java:409-428); up to 2^22 rows. */
 typedef struct npt_annotation {
   int32_t kind;            /* NPT_ANNOT_* */
   int32_t n;               /* rows (0 for EMPTY) */
@@ -113,6 +120,8 @@ typedef struct npt_annotation {
   const int32_t* end;      /* Maximum */
   const uint8_t* strand;   /* 1 = forward */
   const int32_t* name_id;  /* rows with equal gene strings share an id (index of first row with that string) */
+  const uint32_t* name_hash; /* GFF only, per row: h ^ (h >>> 16) of Java's String.hashCode() of the row's gene string
+                              (decides HashSet iteration order = order of the names inside the key); NULL otherwise */
 } npt_annotation;
 
 /* One batch of surviving records (after the filter chain of ViralTranscriptAnalysisCmd2.java:712-959),

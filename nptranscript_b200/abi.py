@@ -6,9 +6,9 @@ NPT_ABI_VERSION = 1
 NPT_MAX_SOURCES = 16
 
 NPT_OK, NPT_EINVAL, NPT_ENODEVICE, NPT_ECUDA, NPT_ENOMEM, NPT_ECAPACITY, NPT_ESTATE = 0, -1, -2, -3, -4, -5, -6
-NPT_ANNOT_CSV, NPT_ANNOT_EMPTY = 0, 1
+NPT_ANNOT_CSV, NPT_ANNOT_EMPTY, NPT_ANNOT_GFF = 0, 1, 2
 NPT_MEM_HOST, NPT_MEM_DEVICE = 0, 1
-NPT_TOK_ST, NPT_TOK_END, NPT_TOK_PLUS, NPT_TOK_MINUS, NPT_TOK_NOENDS = -1, -2, -3, -4, -5
+NPT_TOK_ST, NPT_TOK_END, NPT_TOK_PLUS, NPT_TOK_MINUS, NPT_TOK_NOENDS, NPT_TOK_GENESET = -1, -2, -3, -4, -5, -6
 NPT_RF_TYPE_MASK, NPT_RF_LEADER, NPT_RF_NEG, NPT_RF_BADCIGAR, NPT_RF_SLOWPATH = 0x3, 0x4, 0x8, 0x10, 0x20
 NPT_FETCH_READS, NPT_FETCH_TABLES, NPT_FETCH_COVERAGE, NPT_FETCH_ALL = 1, 2, 4, 7
 
@@ -27,7 +27,8 @@ class npt_config(C.Structure):
 
 
 class npt_annotation(C.Structure):
-    _fields_ = [("kind", i32), ("n", i32), ("start", P(i32)), ("end", P(i32)), ("strand", P(u8)), ("name_id", P(i32))]
+    _fields_ = [("kind", i32), ("n", i32), ("start", P(i32)), ("end", P(i32)), ("strand", P(u8)), ("name_id", P(i32)),
+                ("name_hash", P(u32))]
 
 
 class npt_batch(C.Structure):

@@ -126,10 +126,12 @@ class Engine:
         en = np.asarray(annotation.end, dtype=np.int32)
         sd = np.asarray(annotation.strand, dtype=np.uint8)
         ni = np.asarray(annotation.name_id, dtype=np.int32)
+        nh = np.asarray(annotation.name_hash if annotation.kind == abi.NPT_ANNOT_GFF else [], dtype=np.uint32)
         a = abi.npt_annotation()
         a.kind, a.n = annotation.kind, len(st)
         a.start = st.ctypes.data_as(C.POINTER(C.c_int32)); a.end = en.ctypes.data_as(C.POINTER(C.c_int32))
         a.strand = sd.ctypes.data_as(C.POINTER(C.c_uint8)); a.name_id = ni.ctypes.data_as(C.POINTER(C.c_int32))
+        a.name_hash = nh.ctypes.data_as(C.POINTER(C.c_uint32)) if len(nh) else None
         self._ck(self.L.npt_begin_chrom(self.h, chrom_index, ref.ctypes.data, len(ref), C.byref(a)))
         self._keep = []
 

@@ -49,6 +49,22 @@ class Annotation:
     def empty(cls):
         return cls(kind=1)
 
+    @classmethod
+    def gff(cls, genes, start, end, strand):
+        """Exon rows of one chromosome in file order (GFFAnnotation.java:409-428): gene = the exon's parent attribute."""
+        return cls(kind=2, genes=list(genes), start=list(start), end=list(end), strand=list(strand))
+
+    @property
+    def name_hash(self):
+        """h ^ (h >>> 16) of Java's String.hashCode() per row (HashMap.hash): decides HashSet<String> iteration order."""
+        out = []
+        for g in self.genes:
+            h = 0
+            for ch in g:
+                h = (31 * h + ord(ch)) & 0xFFFFFFFF
+            out.append((h ^ (h >> 16)) & 0xFFFFFFFF)
+        return out
+
 
 def _csv(rows):
     return Annotation(kind=0, genes=[r[0] for r in rows], start=[r[1] for r in rows], end=[r[2] for r in rows],

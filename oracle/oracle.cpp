@@ -37,6 +37,7 @@ struct Annot {
   int kind = NPT_ANNOT_CSV;
   std::vector<int> start, end, name_id;
   std::vector<uint8_t> strand;
+  std::vector<uint32_t> name_hash;  // GFF: HashMap.hash(String.hashCode()) of the row's gene string
   int seqlen = 0;
   int tolerance = 10;  // Annotation.tolerance = --bin (ViralTranscriptAnalysisCmd2.java:497)
   bool enforceStrand = false;
@@ -65,6 +66,24 @@ struct Annot {
       }
     }
     return NPT_TOK_ST;
+  }
+  // GFFAnnotation.contains :72-76
+  bool gffContains(int l2, int r2, int i) const {
+    return r2 - tolerance <= end[i] && r2 + tolerance >= start[i] && l2 - tolerance <= end[i] && l2 + tolerance >= start[i];
+  }
+  // GFFAnnotation.nextUpstream(l1, r1, chrom_index, forward) :80-100.  Returns the exon row or -1 (null).
+  int gffUpstream(int l1, int r1, bool forward_known, bool forward) const {
+    if (l1 < 0) return -1;
+    std::map<int, int> indices;  // TreeMap<score, row>: a later put (lower row) replaces an equal score
+    for (int i = (int)start.size() - 1; i >= 0; i--) {
+      if (!forward_known || forward == (bool)strand[i]) {
+        if (gffContains(l1, r1, i)) indices[std::abs(l1 - start[i]) + std::abs(r1 - end[i])] = i;
+      }
+    }
+    if (!indices.empty()) {
+      if (indices.begin()->first <= 2 * tolerance) return indices.begin()->second;
+    }
+    return -1;
   }
   // Annotation.isLeader :214-216 / EmptyAnnotation :28-30
   bool isLeader(int prev_pos) const {
@@ -121,6 +140,31 @@ inline int seq4_at(const uint8_t* seq4, int64_t i) {
   uint8_t b = seq4[i >> 1];
   return (i & 1) ? (b & 0xF) : (b >> 4);
 }
+
+// java.util.HashSet<String> as far as iteration order goes (OpenJDK HashMap.putVal / resize / treeifyBin): table of 16
+// buckets, doubled when size exceeds 0.75*capacity or when a bucket chain already holds 8 nodes at an append (tables
+// below 64 buckets are resized instead of treeified); a split keeps the relative order inside each half, so a bucket lists
+// its members in insertion order.  Strings are represented by (name id, spread hash).  Tree bins (only possible from 64
+// buckets on) are not restated: ok=false.
+struct JavaStringSet {
+  std::vector<std::vector<std::pair<int, uint32_t>>> tab;
+  size_t size = 0; bool ok = true;
+  JavaStringSet() : tab(16) {}
+  void resize() {
+    std::vector<std::vector<std::pair<int, uint32_t>>> nt(tab.size() * 2);
+    for (auto& bkt : tab) for (auto& e : bkt) nt[e.second & (nt.size() - 1)].push_back(e);
+    tab.swap(nt);
+  }
+  void add(int id, uint32_t h) {
+    auto& bkt = tab[h & (tab.size() - 1)];
+    for (auto& e : bkt) if (e.first == id) return;
+    const size_t before = bkt.size();
+    bkt.emplace_back(id, h);
+    if (before >= 8) { if (tab.size() < 64) resize(); else ok = false; }
+    if (++size > tab.size() * 3 / 4) resize();
+  }
+  template <class F> void for_each(F f) const { for (auto& bkt : tab) for (auto& e : bkt) f(e.first); }
+};
 
 struct ReadOut {
   bool ok = false;            // false: bad cigar (reference throws) → not clustered
@@ -266,7 +310,23 @@ void per_read(const Cfg& cfg, const Annot& annot, const uint8_t* ref, int64_t re
       }
     }
     if (cfg.c.include_start || nB == 2) o.key.push_back(annot.nextUpstream(breaks[nB - 1], fwd));
-  } else {  // :293-299 (EmptyAnnotation); the GFF branch :300-323 is outside this oracle's scope
+  } else if (annot.kind == NPT_ANNOT_GFF) {  // :300-323
+    JavaStringSet genes;
+    std::vector<int> coords;  // GFFAnnotation.getCoord(pos, chrom_index, forward) :132-135 -> the bin; chrom prefix at render
+    const bool fwdOrNull = !o.forward_known || o.forward;
+    for (int i = 0; i + 1 < nB; i += 2) {
+      int upst = annot.gffUpstream(breaks[i], breaks[i + 1], o.forward_known, o.forward);
+      if (upst >= 0) genes.add(annot.name_id[upst], annot.name_hash[upst]);
+      else coords.push_back(Annot::jround(fwdOrNull ? breaks[i + 1] : breaks[i], annot.round));
+    }
+    if (!genes.ok) { o.ok = false; return; }  // tree bins: not restated
+    if (genes.size > 0) {
+      o.key.push_back(NPT_TOK_GENESET);
+      genes.for_each([&](int id) { o.key.push_back(id); });
+    } else {
+      o.key.push_back(fwdOrNull ? coords.back() : coords.front());
+    }
+  } else {  // :293-299 (EmptyAnnotation)
     if (o.forward_known) {
       if (o.forward) o.key.push_back(annot.nextUpstream(breaks[nB - 1], fwd));
       else o.key.push_back(annot.nextUpstream(breaks[0], fwd));
@@ -374,7 +434,10 @@ std::string render_key(const std::vector<int>& tok, const Cfg& cfg, const Annot&
   int n = (int)tok.size();
   bool strandTok = n > 0 && (tok[n - 1] == NPT_TOK_PLUS || tok[n - 1] == NPT_TOK_MINUS);
   int m = strandTok ? n - 1 : n;
-  if (!cfg.c.coronavirus) {
+  if (annot.kind == NPT_ANNOT_GFF) {
+    if (m > 0 && tok[0] == NPT_TOK_GENESET) { for (int i = 1; i < m; i++) { s += name(tok[i]); s += '_'; } }
+    else s += std::to_string(chrom_index) + "." + std::to_string(tok[0]);
+  } else if (!cfg.c.coronavirus) {
     for (int i = 0; i < m; i++) s += name(tok[i]);
   } else if (m > 0 && tok[0] == NPT_TOK_NOENDS) {  // (up,down)* only
     for (int i = 1; i + 1 < m; i += 2) { s += name(tok[i]); s += ','; s += name(tok[i + 1]); s += '_'; }
@@ -489,9 +552,11 @@ void* npto_create(const npt_config* c, int chrom_index, const uint8_t* ref_codes
   for (int i = 0; i < a->n; i++) {
     R->annot.start.push_back(a->start[i]); R->annot.end.push_back(a->end[i]);
     R->annot.strand.push_back(a->strand[i]); R->annot.name_id.push_back(a->name_id[i]);
+    R->annot.name_hash.push_back(a->kind == NPT_ANNOT_GFF && a->name_hash ? a->name_hash[i] : 0u);
   }
-  R->annot.spliced.assign(c->num_sources, std::vector<int>(a->n, 0));
-  R->annot.unspliced.assign(c->num_sources, std::vector<int>(a->n, 0));
+  const int n_orf = a->kind == NPT_ANNOT_GFF ? 0 : a->n;  // ORF counters exist for the CSV table only (Annotation.java:186-187)
+  R->annot.spliced.assign(c->num_sources, std::vector<int>(n_orf, 0));
+  R->annot.unspliced.assign(c->num_sources, std::vector<int>(n_orf, 0));
   R->calcBreaks1 = c->calc_breaks && c->break_thresh < ref_len;  // ViralTranscriptAnalysisCmd2.java:882
   R->totalCounts.assign(c->num_sources, 0);
   R->keep_reads = keep_reads != 0;
@@ -591,7 +656,7 @@ void npto_get_tables(void* h, int64_t* cl_first, uint32_t* cl_key_off, int32_t* 
   }
   cl_key_off[ci] = ko; cl_sub_off[ci] = so; sub_key_off[so] = sko; sub_sum_off[so] = sso;
   for (int s = 0; s < S; s++) total_counts[s] = R.totalCounts[s];
-  const int no = (int)R.annot.start.size();
+  const int no = S ? (int)R.annot.spliced[0].size() : 0;
   for (int s = 0; s < S; s++) for (int i = 0; i < no; i++) { spliced[s * no + i] = R.annot.spliced[s][i]; unspliced[s * no + i] = R.annot.unspliced[s][i]; }
 }
 

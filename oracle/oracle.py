@@ -70,11 +70,13 @@ def _annot_struct(annotation):
     en = np.asarray(annotation.end, dtype=np.int32)
     sd = np.asarray(annotation.strand, dtype=np.uint8)
     ni = np.asarray(annotation.name_id, dtype=np.int32)
+    nh = np.asarray(annotation.name_hash if annotation.kind == abi.NPT_ANNOT_GFF else [], dtype=np.uint32)
     a = abi.npt_annotation()
     a.kind, a.n = annotation.kind, len(st)
     a.start = st.ctypes.data_as(C.POINTER(C.c_int32)); a.end = en.ctypes.data_as(C.POINTER(C.c_int32))
     a.strand = sd.ctypes.data_as(C.POINTER(C.c_uint8)); a.name_id = ni.ctypes.data_as(C.POINTER(C.c_int32))
-    return a, (st, en, sd, ni)
+    a.name_hash = nh.ctypes.data_as(C.POINTER(C.c_uint32)) if len(nh) else None
+    return a, (st, en, sd, ni, nh)
 
 
 def _batch_struct(b):
@@ -92,7 +94,7 @@ class OracleRun:
         self.cfg = cfg
         self.S = cfg.num_sources
         self.ref = np.ascontiguousarray(ref_codes, dtype=np.uint8)
-        self.n_orf = len(annotation.start)
+        self.n_orf = 0 if annotation.kind == abi.NPT_ANNOT_GFF else len(annotation.start)
         a, self._keep = _annot_struct(annotation)
         self.h = lib().npto_create(C.byref(cfg), chrom_index, self.ref.ctypes.data, len(self.ref), C.byref(a), int(keep_reads))
         self.keep_reads = keep_reads
