@@ -26,10 +26,10 @@ constexpr int BRK_INLINE = 6;     // breaks stored in the per-read inline slot
 constexpr int WALK_THREADS = 256;
 constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
 constexpr int MAX_BREAKS = 1 << 20;
-constexpr int TILE_W = 16;        // words per lane tile (CIGAR: 16 ops; bases: 128 + one overlap word)
+constexpr int TILE_W = 20;        // words per lane tile: five 16-byte chunks fetched by the owning lane with cp.async
 constexpr int DEL_HIST = 4;        // deletion lengths recorded in the per-length histogram rows (coverage arrays 4..7)
 constexpr int COV_ARRAYS = 4 + DEL_HIST;
-constexpr int TILE_STRIDE = 17;   // odd stride: lane tiles start in different banks
+constexpr int TILE_STRIDE = 20;   // 80 bytes: keeps every lane tile 16-byte aligned for cp.async
 
 template <typename T>
 __device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
@@ -56,6 +56,15 @@ __device__ __forceinline__ void cmp8(uint32_t rw, uint32_t gw, int cnt, uint32_t
   mat = vm & ~nz;
 }
 
+// 16-byte global -> shared copies of the owning lane (LDGSTS, L2 only); n < 16 zero-fills the rest without reading it
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp16z(uint32_t dst, const void* src, int n) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
   return x;
@@ -68,9 +77,9 @@ template <int MODE, bool REF_SMEM>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, const BatchDev b) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   if (MODE == 1 && ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
-  // shared memory: [packed reference (if it fits)] [per-warp CIGAR tiles 32 x 17] [per-warp base tiles 32 x 17]
+  // shared memory: [packed reference (if it fits), padded to 16 bytes] [per-warp CIGAR tiles 32 x 20] [per-warp base tiles 32 x 20]
   uint32_t* s_ref = s_dyn;
-  const int ref_words = REF_SMEM ? c.ref_nwords : 0;
+  const int ref_words = REF_SMEM ? ((c.ref_nwords + 3) & ~3) : 0;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* cigTile = s_dyn + ref_words + warp * (2 * 32 * TILE_STRIDE);
   uint32_t* seqTile = cigTile + 32 * TILE_STRIDE;
@@ -82,10 +91,11 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   }
   const uint32_t* refw = REF_SMEM ? s_ref : c.ref_words;
   const uint32_t* seqw = (const uint32_t*)b.seq4;
-  const long long seq_last = max(0LL, ((b.seq_bytes + 3) >> 2) - 1);   // clamp indices: no padding requirement on the batch
-  const long long cig_last = max(0LL, (long long)b.cigar_words - 1);
+  const long long seq_words = (b.seq_bytes + 3) >> 2;  // tiles never read past the arrays: the last chunks are clamped
+  const long long cig_words = (long long)b.cigar_words;
+  const uint32_t myCigS = (uint32_t)__cvta_generic_to_shared(myCig), mySeqS = (uint32_t)__cvta_generic_to_shared(mySeq);
   const int T = c.T, G = c.G;
-  const bool per_base = T < 8;  // a break could hide inside one 8-base window: always take the exact per-base path
+  const bool per_base = T < 16;  // a break could hide inside one 16-base step: always take the exact per-base path
   unsigned* cursor = b.bctr + 2 + MODE;  // one read cursor per pass
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
 
@@ -128,19 +138,20 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   // Fixed loop body, re-converged with __syncwarp at two points per iteration:
   //   (A)  a lane whose M op has no windows left takes up to TWO steps: set up the next read, finish the current one, or
   //        consume one CIGAR element from its tile (straight-line predicated code);
-  //   (R)  warp-cooperative, coalesced refill of the CIGAR / base tiles of the lanes that ran out of staged words;
+  //   (R)  lanes that ran out of staged CIGAR / base words refill their own 80-byte tile with five 16-byte cp.async copies;
   //   (B)  every lane that is inside an M op compares up to 16 bases (two 8-base windows) from its tile.
-  // Lanes never touch global memory for the streams themselves: a lane-private 4-byte global load drags a 32-byte sector
-  // through L1 that is evicted before its neighbours are used (ncu r01h: 13 KB of L2->L1 traffic per 1.7 KB read, 40 warps
-  // slower than 24).  Lanes that ran out of reads stay in the loop (idle) until the whole warp is done so that the
+  // Lanes never read the streams with plain loads: a lane-private 4-byte global load drags a 32-byte sector through L1 that
+  // is evicted before its neighbours are used (ncu r01h: 13 KB of L2->L1 traffic per 1.7 KB read, 40 warps slower than 24).
+  // The tiles were first filled by the whole warp (coalesced 64-byte rows, two lanes served per step): correct, but the
+  // ballots, shuffles and clamps of that scheme were ~30 % of all issued instructions (ncu r01n).
+  // Lanes that ran out of reads stay in the loop (idle) until the whole warp is done so that the
   // full-mask __syncwarp is legal; without it the compiler lets every lane run on its own (ncu r01e: 7 of 32 lanes active).
   bool done = false;
-  uint32_t cs = 0;           // index of the first CIGAR word in my tile (valid for [cs, cs+16)); offsets are uint32 in the ABI
+  uint32_t cs = 0;           // index of the first CIGAR word in my tile (multiple of 4, valid for [cs, cs+20)); offsets are uint32 in the ABI
   uint32_t ckg = 0, cendg = 0;  // CIGAR cursor / end of this read
-  uint32_t ss = 0x80000000u; // first base word in my tile, relative to this read's first word (valid for [ss, ss+17))
-  const uint32_t* rp = seqw; // this read's first (4-byte aligned) base word
+  uint32_t ss = 0x80000000u; // first base word in my tile (multiple of 4), relative to rp16 (valid for [ss, ss+20))
+  long long rp16 = 0;        // word index of the 16-byte aligned chunk that holds this read's first base
   uint32_t dmask = 0; int dpos = 0;  // MODE 1: error positions of a D/X op, flushed in phase (B)
-  const unsigned half = lane >> 4, hl = lane & 15;
   for (;;) {
     __syncwarp();
     // ---- (A) up to two steps per iteration: the usual pattern is one I/D element between two M elements
@@ -164,11 +175,11 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
         if (ok) {
           alnStart = __ldg(b.pos + r);
           ckg = __ldg(b.cigar_off + r); cendg = __ldg(b.cigar_off + r + 1);
-          cs = ckg - (uint32_t)TILE_W;  // nothing staged yet
+          cs = ckg + 64u;               // nothing staged yet (ckg - cs wraps to a huge value)
           const unsigned long long so = __ldg(b.seq_off + r);
-          rp = seqw + (so >> 2);
+          rp16 = (long long)(so >> 4) << 2;
           ss = 0x80000000u;             // base tile belongs to another read
-          nib0 = (uint32_t)(so & 3) * 2;
+          nib0 = (uint32_t)(so & 15) * 2;
           if (MODE == 0) bdst = b.break_arena + r * BRK_INLINE;
           if (MODE == 2) {
             const unsigned n_all = (unsigned)b.nbreaks[r];
@@ -266,35 +277,45 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
     }
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
-    // ---- (R) one refill point per iteration.  CIGAR tiles: lanes whose staged ops ran out (the ops are consumed by the
-    // next iteration's phase A; a tile is valid by index, so filling it early is harmless).  Base tiles: the windows at
-    // read offset mRpos+mOff need words k..k+2 of this read's packed bases.  Two lanes are served per step, one by each
-    // half-warp (16 words = 64 bytes, coalesced).
-    {
-      unsigned need = __ballot_sync(0xffffffffu, active && ckg < cendg && ckg - cs >= (uint32_t)TILE_W);
-      while (need) {
-        const int La = __ffs(need) - 1; need &= need - 1;
-        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
-        const int L = half ? Lb : La;
-        const uint32_t start = __shfl_sync(0xffffffffu, ckg, L);
-        cigTile[L * TILE_STRIDE + hl] = __ldg(b.cigar + min((long long)start + hl, cig_last));
-        if ((int)lane == La || (int)lane == Lb) cs = ckg;
-      }
-    }
+    // ---- (R) one refill point per iteration.  CIGAR tile: the ops are consumed by the next iteration's phase A (a tile is
+    // valid by index, so filling it early is harmless).  Base tile: the windows at read offset mRpos+mOff need words
+    // kg..kg+2 (relative to rp16).  Each lane copies for itself; nothing is shared between lanes.
     const bool hasWin = !done && mOff < mN;
     const uint32_t nibw = nib0 + (uint32_t)(mRpos + mOff);
-    const uint32_t kg = nibw >> 3;  // word index relative to rp
+    const uint32_t kg = nibw >> 3;  // word index relative to rp16
     {
-      unsigned need = __ballot_sync(0xffffffffu, hasWin && kg - ss >= (uint32_t)(TILE_W - 1));
-      while (need) {
-        const int La = __ffs(need) - 1; need &= need - 1;
-        const int Lb = need ? __ffs(need) - 1 : La; need &= need - 1;
-        const int L = half ? Lb : La;
-        const long long start = (long long)(((const uint32_t*)__shfl_sync(0xffffffffu, (unsigned long long)rp, L)) - seqw) + __shfl_sync(0xffffffffu, kg, L);
-        seqTile[L * TILE_STRIDE + hl] = __ldg(seqw + min(start + hl, seq_last));
-        if (hl == 0) seqTile[L * TILE_STRIDE + TILE_W] = __ldg(seqw + min(start + TILE_W, seq_last));
-        if ((int)lane == La || (int)lane == Lb) ss = kg;
+      const bool needC = active && ckg < cendg && ckg - cs >= (uint32_t)TILE_W;
+      const bool needS = hasWin && kg - ss > (uint32_t)(TILE_W - 3);
+      if (needC) {
+        cs = ckg & ~3u;
+        const uint32_t* src = b.cigar + cs;
+        if ((long long)cs + TILE_W <= cig_words) {
+#pragma unroll
+          for (int j = 0; j < TILE_W / 4; j++) cp16(myCigS + 16 * j, src + 4 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < TILE_W / 4; j++) {
+            const long long left = (cig_words - ((long long)cs + 4 * j)) * 4;
+            cp16z(myCigS + 16 * j, left > 0 ? (const void*)(src + 4 * j) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
+          }
+        }
       }
+      if (needS) {
+        ss = kg & ~3u;
+        const long long w0 = rp16 + ss;
+        const uint32_t* src = seqw + w0;
+        if (w0 + TILE_W <= seq_words) {
+#pragma unroll
+          for (int j = 0; j < TILE_W / 4; j++) cp16(mySeqS + 16 * j, src + 4 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < TILE_W / 4; j++) {
+            const long long left = (seq_words - (w0 + 4 * j)) * 4;
+            cp16z(mySeqS + 16 * j, left > 0 ? (const void*)(src + 4 * j) : (const void*)seqw, (int)max(0LL, min(16LL, left)));
+          }
+        }
+      }
+      if (needC || needS) cp_wait_all();
     }
     __syncwarp();
     uint32_t misA = 0, misB = 0;
@@ -317,11 +338,33 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       // Fast path only when the last match lies BEFORE the windows and every position is within T of it (then no position can
       // be a break, whatever the matches inside).  After an '=' op prev can lie ahead of the window (advance-then-emit
       // quirk): matches then pull prev back and a gap of up to 15 can open inside the 16 bases.
-      if (per_base || prev >= pos0 || pos0 + cnt - 1 - prev > T) {
-        // a break or a mapStart/mapEnd event is possible inside these windows: exact per-base CigarCluster.add
+      if (per_base || prev >= pos0) {
+        // exact per-base CigarCluster.add (T < 16, or prev ahead of the window)
         slow_windows++;
         for (int i = 0; i < cntA; i++) add(pos0 + i, (matA >> (28 - 4 * i)) & 1u);
         for (int i = 0; i < cntB; i++) add(pos0 + 8 + i, (matB >> (28 - 4 * i)) & 1u);
+      } else if (pos0 + cnt - 1 - prev > T) {
+        // The step right after a junction (or after a long run without a match), in closed form.  Positions i >= i0 are
+        // more than T past the last match; every one of them up to and including the first match f of the step is a
+        // break_p position (mapStart[p]++, mapEnd[prev]++ each, CigarCluster.java:476-486), the first match itself closes
+        // the break (prev, p).  After that match every position of the step is within 15 <= T of a match: nothing more.
+        slow_windows++;
+        const int i0 = prev < 0 ? 0 : max(0, prev + T + 1 - pos0);
+        const int f = matA ? (__clz(matA) >> 2) : (matB ? 8 + (__clz(matB) >> 2) : cnt);
+        if (f >= i0) {
+          if (MODE == 1 && prev > 0) {
+            const int last = min(f, cnt - 1);
+            for (int i = i0; i <= last; i++) atomicAdd(cov + 2 * arr_stride + pos0 + i, 1);
+            atomicAdd(cov + 3 * arr_stride + prev, last - i0 + 1);
+          }
+          if (f < cnt) {
+            if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
+            if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = pos0 + f;
+            nb++;
+          }
+        }
+        if (matB) prev = pos0 + 15 - ((__ffs(matB) - 1) >> 2);
+        else if (matA) prev = pos0 + 7 - ((__ffs(matA) - 1) >> 2);
       } else if (matB) {
         prev = pos0 + 15 - ((__ffs(matB) - 1) >> 2);  // every position is within T of the last match before it
       } else if (matA) {
@@ -385,6 +428,30 @@ __device__ __forceinline__ int tok_down(const DevCfg& c, const int* ostart, cons
   for (int i = 0; i < c.n_orf; i++)
     if ((!c.enforce_strand || (int)fwd == ostrand[i]) && p - c.bin <= ostart[i]) return oname[i];
   return -2;  // NPT_TOK_END
+}
+
+// GFFAnnotation.nextUpstream(l1, r1, chrom_index, forward) :80-100 with contains :72-76: among the exon rows that contain
+// both block ends within the tolerance (and lie on the read's strand when it is known) the one with the smallest
+// |l1-start| + |r1-end|, lowest file row on ties (the TreeMap keeps the last put of the descending scan), accepted iff that
+// score <= 2*tolerance.  An accepted row has |l1-start| <= 2*tol, and `contains` needs start <= l1+tol, so only rows with
+// start in [l1-2tol, l1+tol] can be the answer: a binary search in the start-sorted table plus a short scan.
+// Returns the row's gene name id, -1 for null.
+__device__ int gff_upstream(const DevCfg& c, int l1, int r1, bool fwd_known, bool fwd) {
+  if (l1 < 0) return -1;
+  const int tol = c.bin;
+  int lo = 0, hi = c.gx_n;
+  const int smin = l1 - 2 * tol;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&c.gx[mid].x) < smin) lo = mid + 1; else hi = mid; }
+  int best = INT_MAX, best_row = INT_MAX, best_name = -1;
+  for (int i = lo; i < c.gx_n; i++) {
+    const int4 e = __ldg(c.gx + i);
+    if (e.x > l1 + tol) break;
+    if (fwd_known && (int)fwd != (e.z & 1)) continue;
+    if (!(r1 - tol <= e.y && r1 + tol >= e.x && l1 - tol <= e.y)) continue;
+    const int score = abs(l1 - e.x) + abs(r1 - e.y), row = e.z >> 1;
+    if (score < best || (score == best && row < best_row)) { best = score; best_row = row; best_name = e.w; }
+  }
+  return best <= 2 * tol ? best_name : -1;
 }
 
 // break-point matrix cell += 1   (BreakPoints.addBreakPoint, J/cluster/BreakPoints.java:102-108)
@@ -460,12 +527,62 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
     bool leader = false;
     if (c.coronavirus && nb > 1) leader = (c.annot_kind == 1) ? (br[1] < 100) : (br[1] < s_ostart[1] - c.bin);
 
+    // ---- GFF mode (:300-323): one exon lookup per block; the key is the set of genes hit, in the iteration order of the
+    // reference's HashSet<String>, or — when no block hits an exon — the binned coordinate of one block end
+    int gtok[GFF_MAX_GENES + 1];
+    int gff_n = 0;
+    if (c.annot_kind == 2) {
+      unsigned gh[GFF_MAX_GENES];
+      int ng = 0, coord_first = -1, coord_last = -1;
+      bool tree_bin = false;
+      unsigned cap = 16;  // HashMap table size: doubles past 0.75 load, or when a chain already holds 8 nodes (treeifyBin < 64)
+      const bool fwdOrNull = !fwd_known || fwd;
+      for (int i = 0; i + 1 < nb; i += 2) {
+        const int name = gff_upstream(c, br[i], br[i + 1], fwd_known, fwd);
+        if (name >= 0) {
+          bool seen = false;
+          for (int k = 0; k < ng; k++) seen |= gtok[1 + k] == name;
+          if (!seen) {
+            if (ng == GFF_MAX_GENES) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_GENESET); break; }
+            const unsigned h = __ldg(c.gx_hash + name);
+            int chain = 0;
+            for (int k = 0; k < ng; k++) chain += ((gh[k] ^ h) & (cap - 1)) == 0;
+            gtok[1 + ng] = name; gh[ng] = h; ng++;
+            if (chain >= 8) { if (cap < 64) cap <<= 1; else tree_bin = true; }
+            if ((unsigned)ng > cap * 3 / 4) cap <<= 1;
+          }
+        } else {
+          const int cv = (fwdOrNull ? br[i + 1] : br[i]) / c.bin;  // GFFAnnotation.getCoord :132-135 (positions are >= 1)
+          if (coord_first < 0) coord_first = cv;
+          coord_last = cv;
+        }
+      }
+      if (tree_bin) {  // a real tree bin (> 10 fully colliding names in one read): iteration order not restated, record dropped
+        b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0; b.rflags[r] = 0x10u;
+        continue;
+      }
+      if (ng > 0) {
+        // iteration order: by bucket, insertion order inside a bucket (stable insertion sort on the bucket index)
+        for (int i = 1; i < ng; i++) {
+          const int t = gtok[1 + i]; const unsigned h = gh[i];
+          int j = i;
+          while (j > 0 && (gh[j - 1] & (cap - 1)) > (h & (cap - 1))) { gtok[1 + j] = gtok[j]; gh[j] = gh[j - 1]; j--; }
+          gtok[1 + j] = t; gh[j] = h;
+        }
+        gtok[0] = -6;  // NPT_TOK_GENESET
+        gff_n = 1 + ng;
+      } else {
+        gtok[0] = fwdOrNull ? coord_last : coord_first;
+        gff_n = 1;
+      }
+    }
     // ---- key tokens (IdentityProfile1.java:266-299, 325-327) as a function of the token index
     const bool ends = c.include_start || nb == 2;
-    const int nbody = c.coronavirus ? (ends ? nb : nb - 1) : 1;
+    const int nbody = c.annot_kind == 2 ? gff_n : (c.coronavirus ? (ends ? nb : nb - 1) : 1);
     const int ntok = nbody + (c.enforce_strand ? 1 : 0);
     auto token = [&](int k) -> int {
       if (k >= nbody) return fwd ? -3 : -4;                                          // '+' / '-'
+      if (c.annot_kind == 2) return gtok[k];
       if (!c.coronavirus) return tok_up(c, s_ostart, s_oname, s_ostrand, (fwd_known && !fwd) ? br[0] : br[nb - 1], fwd);
       if (!ends && k == 0) return -5;                                                // NPT_TOK_NOENDS marker
       const bool isEnd = ends && (k == 0 || k == nb - 1);

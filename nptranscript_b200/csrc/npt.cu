@@ -89,6 +89,7 @@ struct npt_ctx {
   DBuf<uint32_t> d_ref;
   DBuf<int> d_ostart, d_oname;
   DBuf<uint8_t> d_ostrand;
+  DBuf<int4> d_gx; DBuf<unsigned> d_gxhash;
   DBuf<Slot> d_cl;
   DBuf<int> d_cl_rec;
   DBuf<Slot> d_sb;
@@ -477,7 +478,7 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();
-  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_cl.release();
+  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
   ctx->d_cov.release(); ctx->d_cov_out.release(); ctx->d_small.release(); ctx->d_counters.release(); ctx->d_keys.release();
@@ -511,10 +512,16 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   if (!ctx || !ref_codes || !annot || ref_len < 1) return fail(ctx, NPT_EINVAL, "bad argument");
   const npt_config& cf = ctx->cfg;
   if (ref_len > (1LL << 31) - 64) return fail(ctx, NPT_EINVAL, "reference too long");
-  if (annot->kind != NPT_ANNOT_CSV && annot->kind != NPT_ANNOT_EMPTY) return fail(ctx, NPT_EINVAL, "unknown annotation kind");
+  if (annot->kind != NPT_ANNOT_CSV && annot->kind != NPT_ANNOT_EMPTY && annot->kind != NPT_ANNOT_GFF) return fail(ctx, NPT_EINVAL, "unknown annotation kind");
+  const bool gff = annot->kind == NPT_ANNOT_GFF;
+  if (gff && cf.coronavirus) return fail(ctx, NPT_EINVAL, "a GFF exon table is a host-mode annotation (coronavirus=0); virus mode takes the CSV ORF table");
+  if (gff && annot->n > 0 && (!annot->start || !annot->end || !annot->strand || !annot->name_id || !annot->name_hash))
+    return fail(ctx, NPT_EINVAL, "GFF annotation needs start, end, strand, name_id and name_hash");
   if (annot->kind == NPT_ANNOT_CSV && cf.coronavirus && annot->n < 2)
     return fail(ctx, NPT_EINVAL, "coronavirus mode needs >= 2 annotation rows (Annotation.isLeader reads start.get(1), Annotation.java:214-216)");
-  if (annot->n < 0 || annot->n > 4096) return fail(ctx, NPT_EINVAL, "annotation rows out of range");
+  if (annot->n < 0 || annot->n > (gff ? (1 << 22) : 4096)) return fail(ctx, NPT_EINVAL, "annotation rows out of range");
+  if (gff) for (int i = 0; i < annot->n; i++) if (annot->name_id[i] < 0 || annot->name_id[i] >= annot->n) return fail(ctx, NPT_EINVAL, "name_id out of range");
+  const int n_orf = gff ? 0 : annot->n;  // ORF rows (shared-memory tables, spliced/unspliced counters): CSV only
   const bool calc_breaks1 = cf.calc_breaks && cf.coronavirus && (int64_t)cf.break_thresh < ref_len;  // ViralTranscriptAnalysisCmd2.java:882
   if ((cf.record_depth || calc_breaks1) && ref_len + 2 >= (1LL << 29))
     return fail(ctx, NPT_EINVAL, "dense coverage / break-point matrix need seqlen < 2^29");
@@ -522,7 +529,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(cudaDeviceSynchronize());
   free_batches(ctx);
   ctx->in_chrom = true; ctx->finalized = false;
-  ctx->chrom_index = chrom_index; ctx->G = ref_len; ctx->n_orf = annot->n;
+  ctx->chrom_index = chrom_index; ctx->G = ref_len; ctx->n_orf = n_orf;
   ctx->idx_base = ctx->idx_user_base;
   ctx->walk_ms = ctx->fin_ms = 0; ctx->walk_launches = ctx->total_launches = 0;
 
@@ -535,7 +542,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   dc.S = cf.num_sources; dc.min_fl_exon = cf.coronavirus ? 0 : 10;
   dc.rna_mask = 0;
   for (int s = 0; s < cf.num_sources; s++) if (cf.rna[s]) dc.rna_mask |= 1u << s;
-  dc.annot_kind = annot->kind; dc.n_orf = annot->n; dc.G = (int)ref_len; dc.stride = (int)ref_len + 2;
+  dc.annot_kind = annot->kind; dc.n_orf = n_orf; dc.G = (int)ref_len; dc.stride = (int)ref_len + 2;
 
   // reference: 8 bases per word, first base in the top nibble, 4 words of padding
   const int nwords = (int)((ref_len + 7) / 8) + 4;
@@ -544,11 +551,26 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(ctx->d_ref.ensure(nwords));
   CK(cudaMemcpy(ctx->d_ref.p, words.data(), (size_t)nwords * 4, cudaMemcpyHostToDevice));
   dc.ref_words = ctx->d_ref.p; dc.ref_nwords = nwords;
-  CK(ctx->d_ostart.ensure(annot->n)); CK(ctx->d_oname.ensure(annot->n)); CK(ctx->d_ostrand.ensure(annot->n));
-  if (annot->n) {
-    CK(cudaMemcpy(ctx->d_ostart.p, annot->start, (size_t)annot->n * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_oname.p, annot->name_id, (size_t)annot->n * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ostrand.p, annot->strand, (size_t)annot->n, cudaMemcpyHostToDevice));
+  CK(ctx->d_ostart.ensure(n_orf)); CK(ctx->d_oname.ensure(n_orf)); CK(ctx->d_ostrand.ensure(n_orf));
+  if (n_orf) {
+    CK(cudaMemcpy(ctx->d_ostart.p, annot->start, (size_t)n_orf * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_oname.p, annot->name_id, (size_t)n_orf * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ostrand.p, annot->strand, (size_t)n_orf, cudaMemcpyHostToDevice));
+  }
+  if (gff) {
+    // exon rows sorted by start (ties: file order) so that a block's candidates are one contiguous range
+    // (GFFAnnotation.nextUpstream :80-100 scans every row; the accepted one has |l1 - start| <= 2*tolerance)
+    std::vector<int> ord(annot->n);
+    for (int i = 0; i < annot->n; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return annot->start[a] < annot->start[b]; });
+    std::vector<int4> gx(annot->n);
+    for (int i = 0; i < annot->n; i++) { const int o = ord[i]; gx[i] = make_int4(annot->start[o], annot->end[o], (o << 1) | (annot->strand[o] ? 1 : 0), annot->name_id[o]); }
+    CK(ctx->d_gx.ensure(annot->n)); CK(ctx->d_gxhash.ensure(annot->n));
+    if (annot->n) {
+      CK(cudaMemcpy(ctx->d_gx.p, gx.data(), (size_t)annot->n * sizeof(int4), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(ctx->d_gxhash.p, annot->name_hash, (size_t)annot->n * 4, cudaMemcpyHostToDevice));
+    }
+    dc.gx = ctx->d_gx.p; dc.gx_n = annot->n; dc.gx_hash = ctx->d_gxhash.p;
   }
   dc.orf_start = ctx->d_ostart.p; dc.orf_name = ctx->d_oname.p; dc.orf_strand = ctx->d_ostrand.p;
 
@@ -597,7 +619,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
 
   // shared memory plan: the packed reference lives on chip when it fits (30 kb genome = 15 KB)
   ctx->ref_smem = (size_t)nwords * 4 <= 96 * 1024;
-  ctx->walk_smem = (ctx->ref_smem ? (size_t)nwords * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4;
+  ctx->walk_smem = (ctx->ref_smem ? (size_t)((nwords + 3) & ~3) * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4;
   ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
   if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
   CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -676,7 +698,8 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     S.busy = true; S.batch_index = (int)ctx->batches.size();
     B.staging = si;
   } else if (b->location == NPT_MEM_DEVICE) {
-    if (((uintptr_t)b->seq4 & 3) != 0) return fail(ctx, NPT_EINVAL, "device seq4 must be 4-byte aligned");
+    if (((uintptr_t)b->seq4 & 15) != 0 || ((uintptr_t)b->cigar & 15) != 0)
+      return fail(ctx, NPT_EINVAL, "device seq4 and cigar must be 16-byte aligned (the walk stages them with 16-byte cp.async copies)");
     uint64_t nseq = 0;
     uint32_t ncig = 0;
     CK(cudaMemcpy(&nseq, b->seq_off + n, 8, cudaMemcpyDeviceToHost));
@@ -770,6 +793,7 @@ int npt_end_chrom(npt_ctx* ctx) {
     if (er & ERR_COV_FULL) m += " coverage rows(max_coverage_clusters)";
     if (er & ERR_ARENA_FULL) m += " key arena";
     if (er & ERR_TOO_MANY_BREAKS) m += " a read has more than 2^20 breaks";
+    if (er & ERR_GENESET) m += " a read overlaps more than 32 annotated genes";
     ctx->in_chrom = false;
     return fail(ctx, NPT_ECAPACITY, "%s", m.c_str());
   }

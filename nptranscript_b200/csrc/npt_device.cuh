@@ -17,7 +17,8 @@ enum {
   CN_COUNT
 };
 
-enum { ERR_CL_FULL = 1, ERR_SUB_FULL = 2, ERR_PAIR_FULL = 4, ERR_COV_FULL = 8, ERR_ARENA_FULL = 16, ERR_TOO_MANY_BREAKS = 32 };
+enum { ERR_CL_FULL = 1, ERR_SUB_FULL = 2, ERR_PAIR_FULL = 4, ERR_COV_FULL = 8, ERR_ARENA_FULL = 16, ERR_TOO_MANY_BREAKS = 32, ERR_GENESET = 64 };
+constexpr int GFF_MAX_GENES = 32;  // distinct genes one read may hit (GFF mode)
 
 // Hash-table slot (clusters and sub-clusters): `word` = 0 while empty, else (hash32 << 32) | record offset in the arena.
 // The record is fully written before the CAS that publishes it, so readers never wait.  The slot index is the identity
@@ -49,6 +50,9 @@ struct DevCfg {
   const int* orf_start;
   const int* orf_name;
   const uint8_t* orf_strand;
+  // GFF mode: exon rows sorted by start: {start, end, (file row << 1) | strand, name id}; gx_hash is indexed by name id
+  const int4* gx; int gx_n;
+  const unsigned* gx_hash;
   // ---- tables
   Slot* cl; unsigned cl_mask; int cl_cap;
   int* cl_rec; unsigned tok_cap;

@@ -57,6 +57,10 @@ def key_string(tokens, annotation, chrom_index, coronavirus=True):
         suffix = "+" if toks[-1] == abi.NPT_TOK_PLUS else "-"
         toks = toks[:-1]
     nm = lambda t: token_name(t, annotation, chrom_index)
+    if annotation.kind == abi.NPT_ANNOT_GFF:  # :300-323: gene names in HashSet order, else the coordinate of one block end
+        if toks and toks[0] == abi.NPT_TOK_GENESET:
+            return "".join(annotation.genes[t] + "_" for t in toks[1:]) + suffix
+        return f"{chrom_index}.{toks[0]}" + suffix
     if not coronavirus:
         return "".join(nm(t) for t in toks) + suffix
     if toks and toks[0] == abi.NPT_TOK_NOENDS:

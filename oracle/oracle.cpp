@@ -319,7 +319,7 @@ void per_read(const Cfg& cfg, const Annot& annot, const uint8_t* ref, int64_t re
       if (upst >= 0) genes.add(annot.name_id[upst], annot.name_hash[upst]);
       else coords.push_back(Annot::jround(fwdOrNull ? breaks[i + 1] : breaks[i], annot.round));
     }
-    if (!genes.ok) { o.ok = false; return; }  // tree bins: not restated
+    if (!genes.ok) { o.ok = false; o.startPos = o.endPos = 0; return; }  // tree bins: not restated, record dropped
     if (genes.size > 0) {
       o.key.push_back(NPT_TOK_GENESET);
       genes.for_each([&](int id) { o.key.push_back(id); });

@@ -40,14 +40,76 @@ def jround(pos, rnd):
     return int(math.floor(float(pos) / float(rnd)))
 
 
+def java_string_hash(s):
+    """String.hashCode() as a signed 32-bit value computed mod 2^32."""
+    h = 0
+    for ch in s:
+        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    return h
+
+
+def java_hashset_order(items):
+    """Iteration order of a java.util.HashSet<String> after add()ing `items` in order (OpenJDK 8+ HashMap):
+    16 buckets, load factor 0.75, bucket = (h ^ h>>>16) & (cap-1), chains in insertion order, a chain that already holds
+    8 nodes at an append doubles the table while it is smaller than 64 (treeifyBin -> resize).  Returns None if a real
+    tree bin would be needed (not restated)."""
+    cap, chains, size = 16, {}, 0
+    spread = lambda x: (java_string_hash(x) ^ (java_string_hash(x) >> 16)) & 0xFFFFFFFF
+
+    def rehash(newcap, old):
+        new = {}
+        for b in sorted(old):
+            for x in old[b]:
+                new.setdefault(spread(x) & (newcap - 1), []).append(x)
+        return new
+
+    for x in items:
+        b = spread(x) & (cap - 1)
+        ch = chains.setdefault(b, [])
+        if x in ch:
+            continue
+        before = len(ch)
+        ch.append(x)
+        if before >= 8:
+            if cap >= 64:
+                return None
+            cap *= 2
+            chains = rehash(cap, chains)
+        size += 1
+        if size > cap * 3 // 4:
+            cap *= 2
+            chains = rehash(cap, chains)
+    return [x for b in sorted(chains) for x in chains[b]]
+
+
 class Annot:
     """J/cluster/Annotation.java (CSV rows) / EmptyAnnotation.java (no rows)."""
 
-    def __init__(self, genes, start, end, strand, seqlen, flags: Flags, empty=False, chrom_index=0):
+    def __init__(self, genes, start, end, strand, seqlen, flags: Flags, empty=False, chrom_index=0, gff=False):
         self.genes, self.start, self.end, self.strand = list(genes), list(start), list(end), list(strand)
-        self.seqlen, self.f, self.empty, self.chrom_index = seqlen, flags, empty, chrom_index
-        self.spliced = [[0] * len(self.start) for _ in range(flags.num_sources)]
-        self.unspliced = [[0] * len(self.start) for _ in range(flags.num_sources)]
+        self.seqlen, self.f, self.empty, self.chrom_index, self.gff = seqlen, flags, empty, chrom_index, gff
+        n_orf = 0 if gff else len(self.start)
+        self.spliced = [[0] * n_orf for _ in range(flags.num_sources)]
+        self.unspliced = [[0] * n_orf for _ in range(flags.num_sources)]
+
+    # ---- GFFAnnotation.java (host mode)
+    def gff_contains(self, l2, r2, i):  # :72-76
+        t = self.f.bin
+        return r2 - t <= self.end[i] and r2 + t >= self.start[i] and l2 - t <= self.end[i] and l2 + t >= self.start[i]
+
+    def gff_next_upstream(self, l1, r1, forward):  # :80-100; exon row or None
+        if l1 < 0:
+            return None
+        best = {}  # TreeMap<score,row>: later put (lower row) wins on equal score
+        for i in range(len(self.start) - 1, -1, -1):
+            if forward is None or forward == self.strand[i]:
+                if self.gff_contains(l1, r1, i):
+                    best[abs(l1 - self.start[i]) + abs(r1 - self.end[i])] = i
+        if best:
+            k = min(best)
+            if k <= 2 * self.f.bin:
+                return best[k]
+        return None
 
     def next_downstream(self, right_break, forward):  # :62-72 / Empty :18-20
         if self.empty:
@@ -231,6 +293,23 @@ class Run:
                     first = False
             if f.include_start or nb == 2:
                 key += a.next_upstream(breaks[-1], forward)
+        elif a.gff:  # :300-323
+            genes_in, coords = [], []
+            fwd_or_null = forward is None or forward
+            for i in range(0, nb - 1, 2):
+                upst = a.gff_next_upstream(breaks[i], breaks[i + 1], forward)
+                if upst is not None:
+                    genes_in.append(a.genes[upst])
+                else:
+                    coords.append(f"{a.chrom_index}.{jround(breaks[i + 1] if fwd_or_null else breaks[i], f.bin)}")
+            if genes_in:
+                order = java_hashset_order(genes_in)
+                if order is None:  # a real tree bin: not restated, treated like a record the reference throws on
+                    self.rows.append(dict(ok=False))
+                    return
+                key += "".join(g + "_" for g in order)
+            else:
+                key += coords[-1] if fwd_or_null else coords[0]
         else:  # EmptyAnnotation branch :293-299
             if forward is not None and not forward:
                 key += a.next_upstream(breaks[0], forward)

@@ -81,3 +81,74 @@ def random_batch(rng, n, genome_len, genome_codes, num_sources=1, weird=0.3, max
     seq4 = np.frombuffer(bytes(seq) + b"\0" * 16, dtype=np.uint8).copy()[: len(seq)] if len(seq) else np.zeros(0, np.uint8)
     return Batch(np.array(pos, np.int32), np.array(flag, np.uint16), np.array(src, np.uint16), np.array(coff, np.uint32),
                  np.array(cig, np.uint32), np.array(soff, np.uint64), seq4)
+
+
+def gff_case(rng, n_reads, genome_len, genome_str, n_genes=40, num_sources=2, jitter=6, hash_collide=False):
+    """Host-mode case on a stand-in chromosome: a random exon table (several transcripts per gene, overlapping genes, both
+    strands, rows in 'file order' = gene by gene) and spliced reads that follow exon chains with jittered ends, skipped and
+    novel exons, plus reads between genes.  Returns (Annotation.gff, synth.Batch).  hash_collide: gene names chosen so that
+    many land in the same HashSet bucket (insertion-order dependence of the key)."""
+    from nptranscript_b200 import synth, workloads
+    genes, start, end, strand, chains = [], [], [], [], []
+    names = []
+    if hash_collide:
+        # Java: "Aa".hashCode() == "BB".hashCode(); concatenations of such pairs collide in full
+        import itertools
+        names = ["".join(p) for p in itertools.product(("Aa", "BB"), repeat=4)][:n_genes]
+    while len(names) < n_genes:
+        names.append(f"ENSG{int(rng.integers(0, 10**8)):011d}")
+    for gi in range(n_genes):
+        g0 = int(rng.integers(200, genome_len - 4000))
+        fwd = bool(rng.random() < 0.5)
+        for _t in range(int(rng.integers(1, 4))):
+            p = g0 + int(rng.integers(0, 60))
+            chain = []
+            for _e in range(int(rng.integers(1, 7))):
+                ln = int(rng.integers(30, 300))
+                if p + ln >= genome_len - 50:
+                    break
+                chain.append((p, p + ln - 1))
+                genes.append(names[gi]); start.append(p); end.append(p + ln - 1); strand.append(fwd)
+                p += ln + int(rng.integers(70, 600))
+            if chain:
+                chains.append((chain, fwd))
+    reads = []
+    for _ in range(n_reads):
+        src = int(rng.integers(0, num_sources))
+        u = rng.random()
+        if u < 0.8:
+            chain, fwd = chains[int(rng.integers(0, len(chains)))]
+            ex = [list(e) for e in chain if rng.random() > 0.15] or [list(chain[0])]
+            if rng.random() < 0.2 and len(chains) > 1:  # chimeric: append exons of another gene further right
+                other, _f = chains[int(rng.integers(0, len(chains)))]
+                ex += [list(e) for e in other if e[0] > ex[-1][1] + 80]
+            for e in ex:
+                e[0] += int(rng.integers(-jitter, jitter + 1)); e[1] += int(rng.integers(-jitter, jitter + 1))
+                if rng.random() < 0.1:
+                    e[1] += int(rng.integers(15, 60))  # novel exon end: outside 2*tolerance for small bins
+            ex = [e for e in ex if e[1] - e[0] >= 5 and e[0] >= 1 and e[1] < genome_len]
+            if not ex:
+                continue
+            flag = 0 if (fwd if rng.random() < 0.9 else not fwd) else 16
+        else:
+            p = int(rng.integers(1, genome_len - 700))
+            ex = [[p, p + int(rng.integers(20, 300))]]
+            if rng.random() < 0.5:
+                q = ex[0][1] + int(rng.integers(60, 300))
+                ex.append([q, q + int(rng.integers(5, 200))])
+            flag = 16 if rng.random() < 0.5 else 0
+        cig, bases, last = "", [], None
+        for (a, b) in ex:
+            if last is not None:
+                if a <= last + 1:
+                    continue
+                cig += f"{a - last - 1}N"
+            seg = list(genome_str[a - 1:b])
+            for k in range(len(seg)):
+                if rng.random() < 0.05:
+                    seg[k] = "ACGT"[int(rng.integers(0, 4))]
+            cig += f"{len(seg)}M"
+            bases += seg
+            last = b
+        reads.append((ex[0][0], flag, src, cig, "".join(bases)))
+    return workloads.Annotation.gff(genes, start, end, strand), synth.from_reads(reads)

@@ -5,7 +5,7 @@ import pytest
 from nptranscript_b200 import abi, engine, synth, workloads
 from oracle import oracle
 from tests.common import assert_same
-from tests.fuzz import random_batch
+from tests.fuzz import gff_case, random_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -87,6 +87,35 @@ def test_fuzz_host_mode_empty_annotation(kw):
     bs = [random_batch(rng, 2000, w.genome_len, g, num_sources=2, big_n=300)]
     dev, ora = _both(dict(kw, num_sources=2, max_coverage_clusters=4096), w, bs, annotation=workloads.Annotation.empty(), chrom_index=3)
     assert_same(dev, ora)
+
+
+@pytest.mark.parametrize("kw,collide", [
+    (dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1], first_is_transcriptome=1), False),  # opts_host.txt
+    (dict(bin=10, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 0]), False),
+    (dict(bin=5, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, rna=[0, 0]), True),
+    (dict(bin=10, break_thresh=50, coronavirus=0, include_start=0, enforce_strand=1, record_depth=0, rna=[1, 1]), True),
+    (dict(bin=1, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1]), False),
+])
+def test_fuzz_host_mode_gff_annotation(kw, collide):
+    """Host mode with an exon table (GFFAnnotation): per-block exon lookup, gene-set keys in HashSet order, coordinate keys."""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    lut = np.full(16, ord("N"), np.uint8)
+    lut[[1, 2, 4, 8]] = [ord(ch) for ch in "ACGT"]
+    rng = np.random.default_rng(23 + kw["bin"])
+    ann, b = gff_case(rng, 6000, w.genome_len, lut[g].tobytes().decode(), n_genes=60, hash_collide=collide)
+    bs = [b, random_batch(rng, 500, w.genome_len, g, num_sources=2, big_n=300)]
+    dev, ora = _both(dict(kw, num_sources=2, max_coverage_clusters=8192), w, bs, annotation=ann, chrom_index=3)
+    assert_same(dev, ora)
+    toks = dev["cl_key_tok"]
+    assert (toks == abi.NPT_TOK_GENESET).sum() > 20 and dev["n_clusters"] > (toks == abi.NPT_TOK_GENESET).sum()
+
+
+def test_gff_needs_host_mode():
+    w = workloads.SARS2
+    ann = workloads.Annotation.gff(["g"], [10], [100], [True])
+    with pytest.raises(engine.NptError):
+        engine.run(engine.make_config(coronavirus=1), synth.genome_codes(w), ann, [synth.generate(w, 1, 10)])
 
 
 def test_small_tables_report_capacity():

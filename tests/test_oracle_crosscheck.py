@@ -19,7 +19,8 @@ def _compare(kw, annotation, batches, chrom_index=0):
                          num_sources=kw.get("num_sources", 1), rna=tuple(bool(x) for x in kw.get("rna", [1] * 16)),
                          first_is_transcriptome=bool(kw.get("first_is_transcriptome", 0)))
     empty = annotation.kind == abi.NPT_ANNOT_EMPTY
-    ann = py_oracle.Annot(annotation.genes, annotation.start, annotation.end, annotation.strand, len(g), fl, empty=empty, chrom_index=chrom_index)
+    ann = py_oracle.Annot(annotation.genes, annotation.start, annotation.end, annotation.strand, len(g), fl, empty=empty, chrom_index=chrom_index,
+                          gff=annotation.kind == abi.NPT_ANNOT_GFF)
     run = py_oracle.Run(fl, g.tolist(), ann, chrom_index)
     names, srcs = [], []
     for b in batches:
@@ -109,3 +110,35 @@ def test_threads_do_not_change_results():
     for k, v in a.items():
         if isinstance(v, np.ndarray):
             assert np.array_equal(v, c[k]), k
+
+
+def _genome_str(g):
+    lut = np.full(16, ord("N"), np.uint8)
+    lut[[1, 2, 4, 8]] = [ord(c) for c in "ACGT"]
+    return lut[g].tobytes().decode()
+
+
+@pytest.mark.parametrize("kw,collide", [
+    (dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, num_sources=2, rna=[1, 1], first_is_transcriptome=1), False),
+    (dict(bin=10, break_thresh=50, coronavirus=0, include_start=0, num_sources=2, rna=[1, 0]), False),
+    (dict(bin=5, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, num_sources=2, rna=[0, 0]), True),
+    (dict(bin=10, break_thresh=50, coronavirus=0, include_start=0, enforce_strand=1, num_sources=2, rna=[1, 1]), True),
+])
+def test_host_mode_gff_annotation(kw, collide):
+    from tests.fuzz import gff_case
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(17 + kw["bin"])
+    ann, b = gff_case(rng, 400, w.genome_len, _genome_str(g), hash_collide=collide)
+    _compare(kw, ann, [b, random_batch(rng, 80, w.genome_len, g, num_sources=2, big_n=300)], chrom_index=3)
+
+
+def test_java_hashset_order_known_cases():
+    # "Aa" and "BB" share String.hashCode() 2112: same bucket, insertion order decides
+    assert py_oracle.java_string_hash("Aa") == py_oracle.java_string_hash("BB") == 2112
+    assert py_oracle.java_hashset_order(["BB", "Aa"]) == ["BB", "Aa"] and py_oracle.java_hashset_order(["Aa", "BB", "Aa"]) == ["Aa", "BB"]
+    # single characters hash to their code point: buckets 1, 2, 3 in a 16-bucket table whatever the insertion order
+    assert py_oracle.java_hashset_order(["c", "a", "b"]) == ["a", "b", "c"]
+    # 13 entries exceed 0.75 * 16: the table doubles, 'q' (113 & 31 = 17) now sorts before 'a' (97 & 31 = 1)?  no: 1 < 17
+    thirteen = [chr(97 + i) for i in range(12)] + ["q"]
+    assert py_oracle.java_hashset_order(thirteen) == sorted(thirteen, key=lambda s: ord(s) & 31)
