@@ -27,6 +27,8 @@ constexpr int WALK_THREADS = 256;
 constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
 constexpr int MAX_BREAKS = 1 << 20;
 constexpr int TILE_W = 20;        // words per lane tile: five 16-byte chunks fetched by the owning lane with cp.async
+constexpr int STEP_WINS = 4;      // 8-base windows compared per loop iteration
+constexpr int STEP_BASES = 8 * STEP_WINS;
 constexpr int DEL_HIST = 4;        // deletion lengths recorded in the per-length histogram rows (coverage arrays 4..7)
 constexpr int COV_ARRAYS = 4 + DEL_HIST;
 constexpr int TILE_STRIDE = 20;   // 80 bytes: keeps every lane tile 16-byte aligned for cp.async
@@ -39,23 +41,6 @@ __device__ __forceinline__ uint32_t ref_win8(const uint32_t* w, uint32_t nib) {
   const uint32_t k = nib >> 3, o = (nib & 7) << 2;
   return __funnelshift_l(w[k + 1], w[k], o);
 }
-// 8 read bases from the BAM-packed byte stream (little-endian word loads, byte-swapped to base order).
-// Reads one word past the window: batches carry >= 8 readable bytes after seq4 (npt.h).
-__device__ __forceinline__ uint32_t read_win8(const uint32_t* w, uint32_t nib) {
-  const uint32_t k = nib >> 3, o = (nib & 7) << 2;
-  const uint32_t a = __byte_perm(__ldg(w + k), 0, 0x0123);
-  const uint32_t b = __byte_perm(__ldg(w + k + 1), 0, 0x0123);
-  return __funnelshift_l(b, a, o);
-}
-// mismatch / match masks of an 8-base window (bit 28-4j <-> base j), cnt valid bases
-__device__ __forceinline__ void cmp8(uint32_t rw, uint32_t gw, int cnt, uint32_t& mis, uint32_t& mat) {
-  const uint32_t x = rw ^ gw;
-  const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
-  const uint32_t vm = 0x11111111u & (0xFFFFFFFFu << ((8 - cnt) << 2));
-  mis = nz & vm;
-  mat = vm & ~nz;
-}
-
 // 16-byte global -> shared copies of the owning lane (LDGSTS, L2 only); n < 16 zero-fills the rest without reading it
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -95,7 +80,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   const long long cig_words = (long long)b.cigar_words;
   const uint32_t myCigS = (uint32_t)__cvta_generic_to_shared(myCig), mySeqS = (uint32_t)__cvta_generic_to_shared(mySeq);
   const int T = c.T, G = c.G;
-  const bool per_base = T < 16;  // a break could hide inside one 16-base step: always take the exact per-base path
+  const bool per_base = T < STEP_BASES;  // a break could hide inside one step: always take the exact per-base path
   unsigned* cursor = b.bctr + 2 + MODE;  // one read cursor per pass
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
 
@@ -139,7 +124,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   //   (A)  a lane whose M op has no windows left takes up to TWO steps: set up the next read, finish the current one, or
   //        consume one CIGAR element from its tile (straight-line predicated code);
   //   (R)  lanes that ran out of staged CIGAR / base words refill their own 80-byte tile with five 16-byte cp.async copies;
-  //   (B)  every lane that is inside an M op compares up to 16 bases (two 8-base windows) from its tile.
+  //   (B)  every lane that is inside an M op compares up to 32 bases (four 8-base windows) from its tile.
   // Lanes never read the streams with plain loads: a lane-private 4-byte global load drags a 32-byte sector through L1 that
   // is evicted before its neighbours are used (ncu r01h: 13 KB of L2->L1 traffic per 1.7 KB read, 40 warps slower than 24).
   // The tiles were first filled by the whole warp (coalesced 64-byte rows, two lanes served per step): correct, but the
@@ -279,13 +264,13 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
     if (__all_sync(0xffffffffu, done)) break;
     // ---- (R) one refill point per iteration.  CIGAR tile: the ops are consumed by the next iteration's phase A (a tile is
     // valid by index, so filling it early is harmless).  Base tile: the windows at read offset mRpos+mOff need words
-    // kg..kg+2 (relative to rp16).  Each lane copies for itself; nothing is shared between lanes.
+    // kg..kg+STEP_WINS (relative to rp16).  Each lane copies for itself; nothing is shared between lanes.
     const bool hasWin = !done && mOff < mN;
     const uint32_t nibw = nib0 + (uint32_t)(mRpos + mOff);
     const uint32_t kg = nibw >> 3;  // word index relative to rp16
     {
       const bool needC = active && ckg < cendg && ckg - cs >= (uint32_t)TILE_W;
-      const bool needS = hasWin && kg - ss > (uint32_t)(TILE_W - 3);
+      const bool needS = hasWin && kg - ss > (uint32_t)(TILE_W - 1 - STEP_WINS);
       if (needC) {
         cs = ckg & ~3u;
         const uint32_t* src = b.cigar + cs;
@@ -318,39 +303,50 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       if (needC || needS) cp_wait_all();
     }
     __syncwarp();
-    uint32_t misA = 0, misB = 0;
+    uint32_t mis = 0;  // mismatches of this step: bit 4j+q <-> base 8q + 7 - j
     int pos0 = 0;
     if (hasWin) {
-      // ---- (B) up to 16 bases (two 8-base windows) of the current M op
-      const int cnt = min(16, mN - mOff);
-      const int cntA = min(8, cnt), cntB = cnt - cntA;
+      // ---- (B) up to STEP_BASES bases (8-base windows) of the current M op
+      const int cnt = min(STEP_BASES, mN - mOff);
       pos0 = mStart0 + 1 + mOff;
       const int ki = (int)(kg - ss);
       const uint32_t sh = (nibw & 7) << 2;
-      const uint32_t w0 = __byte_perm(mySeq[ki], 0, 0x0123), w1 = __byte_perm(mySeq[ki + 1], 0, 0x0123), w2 = __byte_perm(mySeq[ki + 2], 0, 0x0123);
       const uint32_t rn = (uint32_t)(mStart0 + mOff), rk = rn >> 3, rs = (rn & 7) << 2;
-      const uint32_t g0 = refw[rk], g1 = refw[rk + 1], g2 = refw[rk + 2];
-      uint32_t matA, matB = 0;
-      cmp8(__funnelshift_l(w1, w0, sh), __funnelshift_l(g1, g0, rs), cntA, misA, matA);
-      if (cntB > 0) cmp8(__funnelshift_l(w2, w1, sh), __funnelshift_l(g2, g1, rs), cntB, misB, matB);
-      mOff += 16;
-      errs += __popc(misA) + __popc(misB);
-      // Fast path only when the last match lies BEFORE the windows and every position is within T of it (then no position can
-      // be a break, whatever the matches inside).  After an '=' op prev can lie ahead of the window (advance-then-emit
-      // quirk): matches then pull prev back and a gap of up to 15 can open inside the 16 bases.
-      if (per_base || prev >= pos0) {
-        // exact per-base CigarCluster.add (T < 16, or prev ahead of the window)
+      uint32_t w[STEP_WINS + 1], g[STEP_WINS + 1];
+#pragma unroll
+      for (int q = 0; q <= STEP_WINS; q++) { w[q] = __byte_perm(mySeq[ki + q], 0, 0x0123); g[q] = refw[rk + q]; }
+      uint32_t mat = 0;  // matches, same layout as mis
+#pragma unroll
+      for (int q = 0; q < STEP_WINS; q++) {
+        const uint32_t x = __funnelshift_l(w[q + 1], w[q], sh) ^ __funnelshift_l(g[q + 1], g[q], rs);
+        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
+        const uint32_t vm = __funnelshift_rc(0u, 0x11111111u, (uint32_t)(4 * min(8, max(0, cnt - 8 * q))));  // top nibbles valid
+        mis |= (nz & vm) << q;
+        mat |= (vm & ~nz) << q;
+      }
+      mOff += STEP_BASES;
+      errs += __popc(mis);
+      // base index of the first / last match of the step (cnt / -1 if none)
+      int f = cnt, l = -1;
+#pragma unroll
+      for (int q = STEP_WINS - 1; q >= 0; q--) { const uint32_t m = (mat >> q) & 0x11111111u; if (m) f = 8 * q + (__clz(m) >> 2); }
+#pragma unroll
+      for (int q = 0; q < STEP_WINS; q++) { const uint32_t m = (mat >> q) & 0x11111111u; if (m) l = 8 * q + 7 - ((__ffs(m) - 1) >> 2); }
+      // Fast path only when the last match does not lie AHEAD of the step and every position is within T of it (then no
+      // position can be a break, whatever the matches inside).  After an '=' op prev can lie ahead of the step (advance-
+      // then-emit quirk): matches then pull prev back and a gap can open inside the step.
+      if (per_base || prev > pos0) {
+        // exact per-base CigarCluster.add (T < STEP_BASES, or prev ahead of the step)
         slow_windows++;
-        for (int i = 0; i < cntA; i++) add(pos0 + i, (matA >> (28 - 4 * i)) & 1u);
-        for (int i = 0; i < cntB; i++) add(pos0 + 8 + i, (matB >> (28 - 4 * i)) & 1u);
+#pragma unroll 1
+        for (int i = 0; i < cnt; i++) add(pos0 + i, (mat >> (((7 - (i & 7)) << 2) + (i >> 3))) & 1u);
       } else if (pos0 + cnt - 1 - prev > T) {
         // The step right after a junction (or after a long run without a match), in closed form.  Positions i >= i0 are
         // more than T past the last match; every one of them up to and including the first match f of the step is a
         // break_p position (mapStart[p]++, mapEnd[prev]++ each, CigarCluster.java:476-486), the first match itself closes
-        // the break (prev, p).  After that match every position of the step is within 15 <= T of a match: nothing more.
+        // the break (prev, p).  After that match every position of the step is within STEP_BASES-1 <= T of a match.
         slow_windows++;
         const int i0 = prev < 0 ? 0 : max(0, prev + T + 1 - pos0);
-        const int f = matA ? (__clz(matA) >> 2) : (matB ? 8 + (__clz(matB) >> 2) : cnt);
         if (f >= i0) {
           if (MODE == 1 && prev > 0) {
             const int last = min(f, cnt - 1);
@@ -363,26 +359,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
             nb++;
           }
         }
-        if (matB) prev = pos0 + 15 - ((__ffs(matB) - 1) >> 2);
-        else if (matA) prev = pos0 + 7 - ((__ffs(matA) - 1) >> 2);
-      } else if (matB) {
-        prev = pos0 + 15 - ((__ffs(matB) - 1) >> 2);  // every position is within T of the last match before it
-      } else if (matA) {
-        prev = pos0 + 7 - ((__ffs(matA) - 1) >> 2);
+        if (l >= 0) prev = pos0 + l;
+      } else if (l >= 0) {
+        prev = pos0 + l;  // every position is within T of the last match before it
       }
     }
     if (MODE == 1) {
-      // error positions: mismatches of this window and/or the D/X op consumed in phase (A)
+      // error positions: mismatches of this step and/or the D/X op consumed in phase (A)
       int* err_row = cov + arr_stride;
-      while (misA) {
-        const int bit = 31 - __clz(misA);
-        misA &= ~(1u << bit);
-        atomicAdd(err_row + pos0 + ((28 - bit) >> 2), 1);
-      }
-      while (misB) {
-        const int bit = 31 - __clz(misB);
-        misB &= ~(1u << bit);
-        atomicAdd(err_row + pos0 + 8 + ((28 - bit) >> 2), 1);
+      while (mis) {
+        const int bit = 31 - __clz(mis);
+        mis &= ~(1u << bit);
+        atomicAdd(err_row + pos0 + ((bit & 3) << 3) + 7 - (bit >> 2), 1);
       }
       while (dmask) {
         const int bit = 31 - __clz(dmask);
