@@ -120,9 +120,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
     pendingEnd = base + n;
   };
 
-  // Fixed loop body, re-converged with __syncwarp at two points per iteration:
-  //   (A)  a lane whose M op has no windows left takes up to TWO steps: set up the next read, finish the current one, or
-  //        consume one CIGAR element from its tile (straight-line predicated code);
+  // Fixed loop body, re-converged with __syncwarp between the phases:
+  //   (A0) a lane whose read is finished writes its results and takes the next read from the cursor; (Rc) stages its CIGAR;
+  //   (A1) a lane whose M op has no windows left consumes at most one element that is not M, then (A2) at most one M
+  //        element (straight-line predicated code);
   //   (R)  lanes that ran out of staged CIGAR / base words refill their own 80-byte tile with five 16-byte cp.async copies;
   //   (B)  every lane that is inside an M op compares up to 32 bases (four 8-base windows) from its tile.
   // Lanes never read the streams with plain loads: a lane-private 4-byte global load drags a 32-byte sector through L1 that
@@ -139,11 +140,34 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   uint32_t dmask = 0; int dpos = 0;  // MODE 1: error positions of a D/X op, flushed in phase (B)
   for (;;) {
     __syncwarp();
-    // ---- (A) up to two steps per iteration: the usual pattern is one I/D element between two M elements
-#pragma unroll 1
-    for (int step = 0; step < 2; step++)
-    if (!done && mOff >= mN) {
-      if (!active) {
+    // ---- (A0) read transitions: finish the current read and/or take the next one from the cursor
+    if (!done && mOff >= mN && (!active || ckg == cendg)) {
+      if (active) {
+        // ---- end of read: CigarCluster.addEnd :466-469, read offsets of alignment start/end
+        const int alnEnd = refPos;  // alnStart + reference span - 1
+        if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = alnEnd;
+        nb++;
+        if (MODE == 0) {
+          b.nbreaks[r] = nb;
+          b.break_loc[r] = 0xFFFFFFFFu;
+          b.read_st[r] = st_r;
+          b.read_en[r] = (alnEnd > 0 && maxEnd == alnEnd) ? (alnEnd < eBs ? 0 : alnEnd - eBs + eRs) : 0;
+          b.maps_sum[r] = c.record_depth ? maps : 0;
+          b.err_sum[r] = c.record_depth ? errs : 0;
+          b.rflags[r] = 0;
+          if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
+        }
+        if (MODE == 1) {
+          if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
+          // CigarCluster.setStartEnd :360-365 with the (trimmed) start/end of the read; positions past seqlen+1 only come
+          // from alignments that run off the reference and are dropped by the dense rows
+          const int sp = b.start_pos[r], ep = b.end_pos[r];
+          if (sp >= 0 && sp < c.stride) atomicAdd(cov + 2 * arr_stride + sp, 1);
+          if (ep >= 0 && ep < c.stride) atomicAdd(cov + 3 * arr_stride + ep, 1);
+        }
+        active = false;
+      }
+      {
         bool ok = true;
         r = (long long)atomicAdd(cursor, 1u);
         if (r >= b.n) { done = true; ok = false; }
@@ -185,85 +209,95 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           prev = alnStart;
           active = true;
         }
-      } else if (ckg == cendg) {
-        // ---- end of read: CigarCluster.addEnd :466-469, read offsets of alignment start/end
-        const int alnEnd = refPos;  // alnStart + reference span - 1
-        if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = alnEnd;
-        nb++;
-        if (MODE == 0) {
-          b.nbreaks[r] = nb;
-          b.break_loc[r] = 0xFFFFFFFFu;
-          b.read_st[r] = st_r;
-          b.read_en[r] = (alnEnd > 0 && maxEnd == alnEnd) ? (alnEnd < eBs ? 0 : alnEnd - eBs + eRs) : 0;
-          b.maps_sum[r] = c.record_depth ? maps : 0;
-          b.err_sum[r] = c.record_depth ? errs : 0;
-          b.rflags[r] = 0;
-          if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
-        }
-        if (MODE == 1) {
-          if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
-          // CigarCluster.setStartEnd :360-365 with the (trimmed) start/end of the read; positions past seqlen+1 only come
-          // from alignments that run off the reference and are dropped by the dense rows
-          const int sp = b.start_pos[r], ep = b.end_pos[r];
-          if (sp >= 0 && sp < c.stride) atomicAdd(cov + 2 * arr_stride + sp, 1);
-          if (ep >= 0 && ep < c.stride) atomicAdd(cov + 3 * arr_stride + ep, 1);
-        }
-        active = false;
-      } else if (ckg - cs < (uint32_t)TILE_W) {
-        // ---- one CIGAR element, as straight-line predicated code (lanes handle different op types side by side)
-        const uint32_t w = myCig[(int)(ckg - cs)];
-        ckg++;
-        const int len = (int)(w >> 4), op = (int)(w & 15);
-        if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
-          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
-          active = false;
-        } else {
-          const bool isM = op == 0, isDX = (op == 2) | (op == 8), isEQ = op == 7;
-          const int ref0 = refPos, read0 = readPos;
-          refPos += ((0x18D >> op) & 1) ? len : 0;    // M D N = X consume reference
-          readPos += ((0x193 >> op) & 1) ? len : 0;   // M I S = X consume read
-          if (isM | isEQ | (op == 8)) {
-            // htsjdk AlignmentBlock(readStart, refStart, len) bookkeeping for getReadPositionAtReferencePosition
-            const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
-            if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
-            if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
-          }
-          // M emits from its own start; D / = / X advance first and emit afterwards (quirk :513-522, :552-576)
-          const int e0 = isM ? ref0 : refPos;
-          const int nE = (isM | isDX | isEQ) ? max(0, min(len, G - e0)) : 0;
-          const int base = e0 + 1;
-          maps += nE;
-          errs += isDX ? nE : 0;
-          if (isM) { mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE; }
-          // Short deletions (the bulk of the coverage events of a noisy read) are recorded as ONE point in a per-length
-          // histogram instead of 4 depth-difference events + len error points: when the previous depth run ends right before
-          // the deletion the run is simply carried across it, and coverage_rows_kernel removes the deleted positions and adds
-          // the "advance, then emit" positions (depth and error) from the histogram at end of chromosome.
-          if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 &&
-              !(prev > 0 && base + nE - 1 - prev > T)) {
-            atomicAdd(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
-            pendingEnd = base;
-          } else
-          if (MODE == 1 && nE > 0) {
-            depth_run(base, nE);
-            if (isDX) {
-              if (nE <= 8 && dmask == 0) { dmask = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); dpos = base; }  // flushed in (B)
-              else for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
-              if (prev > 0 && base + nE - 1 - prev > T)
-                for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
-            }
-          }
-          if (isEQ && nE > 0) {
-            if (per_base || base + nE - 1 - prev > T) for (int i = 0; i < nE; i++) add(base + i, true);
-            else prev = base + nE - 1;
-          }
+      }
+    }
+    // ---- (Rc) CIGAR tile of the lanes that ran out of staged elements (a tile is valid by index)
+    if (active && ckg < cendg && ckg - cs >= (uint32_t)TILE_W) {
+      cs = ckg & ~3u;
+      const uint32_t* src = b.cigar + cs;
+      if ((long long)cs + TILE_W <= cig_words) {
+#pragma unroll
+        for (int j = 0; j < TILE_W / 4; j++) cp16(myCigS + 16 * j, src + 4 * j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TILE_W / 4; j++) {
+          const long long left = (cig_words - ((long long)cs + 4 * j)) * 4;
+          cp16z(myCigS + 16 * j, left > 0 ? (const void*)(src + 4 * j) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
         }
       }
+      cp_wait_all();
+    }
+    __syncwarp();
+    // ---- (A1) at most one element that is not M, then (A2) at most one M element: the usual pattern is one I/D element
+    // between two M elements, so a lane normally enters (B) with a fresh window every iteration.  Both are straight-line
+    // predicated code (lanes handle different op types side by side).
+    bool haveW = active && mOff >= mN && ckg < cendg;
+    uint32_t w = haveW ? myCig[(int)(ckg - cs)] : 0u;
+    if (haveW && (w & 15u) != 0u) {
+      ckg++;
+      const int len = (int)(w >> 4), op = (int)(w & 15);
+      if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
+        if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+        active = false;
+      } else {
+        const bool isDX = (op == 2) | (op == 8), isEQ = op == 7;
+        const int ref0 = refPos, read0 = readPos;
+        refPos += ((0x18C >> op) & 1) ? len : 0;    // D N = X consume reference
+        readPos += ((0x192 >> op) & 1) ? len : 0;   // I S = X consume read
+        if (isEQ | (op == 8)) {
+          // htsjdk AlignmentBlock(readStart, refStart, len) bookkeeping for getReadPositionAtReferencePosition
+          const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
+          if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
+          if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
+        }
+        // D / = / X advance first and emit afterwards (quirk :513-522, :552-576)
+        const int nE = (isDX | isEQ) ? max(0, min(len, G - refPos)) : 0;
+        const int base = refPos + 1;
+        maps += nE;
+        errs += isDX ? nE : 0;
+        // Short deletions (the bulk of the coverage events of a noisy read) are recorded as ONE point in a per-length
+        // histogram instead of 4 depth-difference events + len error points: when the previous depth run ends right before
+        // the deletion the run is simply carried across it, and coverage_rows_kernel removes the deleted positions and adds
+        // the "advance, then emit" positions (depth and error) from the histogram at end of chromosome.
+        if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 &&
+            !(prev > 0 && base + nE - 1 - prev > T)) {
+          atomicAdd(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
+          pendingEnd = base;
+        } else if (MODE == 1 && nE > 0) {
+          depth_run(base, nE);
+          if (isDX) {
+            if (nE <= 8) { dmask = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); dpos = base; }  // flushed after (B)
+            else for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
+            if (prev > 0 && base + nE - 1 - prev > T)
+              for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+          }
+        }
+        if (isEQ && nE > 0) {
+          if (per_base || base + nE - 1 - prev > T) for (int i = 0; i < nE; i++) add(base + i, true);
+          else prev = base + nE - 1;
+        }
+      }
+      haveW = active && ckg < cendg && ckg - cs < (uint32_t)TILE_W;
+      w = haveW ? myCig[(int)(ckg - cs)] : 0u;
+    }
+    if (haveW && (w & 15u) == 0u) {
+      // M emits from its own start
+      ckg++;
+      const int len = (int)(w >> 4);
+      const int ref0 = refPos, read0 = readPos;
+      refPos += len; readPos += len;
+      const int bStart = ref0 + 1, bEnd = ref0 + len, rStart = read0 + 1;
+      if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
+      if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
+      const int nE = max(0, min(len, G - ref0));
+      maps += nE;
+      mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE;
+      if (MODE == 1 && nE > 0) depth_run(ref0 + 1, nE);
     }
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
-    // ---- (R) one refill point per iteration.  CIGAR tile: the ops are consumed by the next iteration's phase A (a tile is
-    // valid by index, so filling it early is harmless).  Base tile: the windows at read offset mRpos+mOff need words
+    // ---- (R) the refill point of running reads.  CIGAR tile: the elements are consumed by the next iteration's phase A (a
+    // tile is valid by index, so filling it early is harmless; (Rc) then only serves reads that have just started).  Base tile: the windows at read offset mRpos+mOff need words
     // kg..kg+STEP_WINS (relative to rp16).  Each lane copies for itself; nothing is shared between lanes.
     const bool hasWin = !done && mOff < mN;
     const uint32_t nibw = nib0 + (uint32_t)(mRpos + mOff);
