@@ -68,12 +68,17 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* cigTile = s_dyn + ref_words + warp * (2 * 32 * TILE_STRIDE);
   uint32_t* seqTile = cigTile + 32 * TILE_STRIDE;
+  uint32_t* s_vm = s_dyn + ref_words + (WALK_THREADS / 32) * (2 * 32 * TILE_STRIDE);  // valid-base masks by step length
   uint32_t* myCig = cigTile + lane * TILE_STRIDE;
   uint32_t* mySeq = seqTile + lane * TILE_STRIDE;
-  if (REF_SMEM) {
+  if (REF_SMEM)
     for (int i = threadIdx.x; i < c.ref_nwords; i += blockDim.x) s_ref[i] = c.ref_words[i];
-    __syncthreads();
+  if (threadIdx.x <= STEP_BASES) {  // s_vm[n]: bit 4j+q set iff base 8q + 7 - j < n (the layout of the step masks below)
+    uint32_t m = 0;
+    for (int i = 0; i < (int)threadIdx.x; i++) m |= 1u << (((7 - (i & 7)) << 2) + (i >> 3));
+    s_vm[threadIdx.x] = m;
   }
+  __syncthreads();
   const uint32_t* refw = REF_SMEM ? s_ref : c.ref_words;
   const uint32_t* seqw = (const uint32_t*)b.seq4;
   const long long seq_words = (b.seq_bytes + 3) >> 2;  // tiles never read past the arrays: the last chunks are clamped
@@ -89,6 +94,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   // state of the read being walked
   uint32_t nib0 = 0;
   int alnStart = 0, refPos = 0, readPos = 0, prev = 0, nb = 0, maps = 0, errs = 0;
+  // prev is kept lazily: while pmat != 0 the last match is the last set base of pmat, a step mask at position ppos0; it is
+  // decoded only when a comparison against T could come out true (junctions), which needs the exact value
+  uint32_t pmat = 0; int ppos0 = 0;
   int mStart0 = 0, mRpos = 0, mN = 0, mOff = 0;  // M op being windowed: windows remain while mOff < mN
   int st_r = 0, maxEnd = 0, eBs = 0, eRs = 0;
   bool stFound = false;
@@ -97,6 +105,13 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   int* bdst = nullptr;      // MODE 0/2: where this read's breaks go
   int slow_windows = 0;
 
+  auto last_match = [](uint32_t m) -> int {  // base index of the last set base of a step mask, -1 if none
+    int l = -1;
+#pragma unroll
+    for (int q = 0; q < STEP_WINS; q++) { const uint32_t mq = (m >> q) & 0x11111111u; if (mq) l = 8 * q + 7 - ((__ffs(mq) - 1) >> 2); }
+    return l;
+  };
+  auto sync_prev = [&]() { if (pmat) { prev = ppos0 + last_match(pmat); pmat = 0; } };
   // CigarCluster.add for one emitted position (exact, used only near junctions or when T < 8)
   auto add = [&](int p, bool match) {
     const bool break_p = prev < 0 || p - prev > T;
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           stFound = false; st_r = 0; maxEnd = INT_MIN; eBs = 0; eRs = 0;
           if (MODE != 1) bdst[0] = alnStart;  // CigarCluster.addStart :442-446
           nb = 1;
-          prev = alnStart;
+          prev = alnStart; pmat = 0;
           active = true;
         }
       }
@@ -259,8 +274,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
         // histogram instead of 4 depth-difference events + len error points: when the previous depth run ends right before
         // the deletion the run is simply carried across it, and coverage_rows_kernel removes the deleted positions and adds
         // the "advance, then emit" positions (depth and error) from the histogram at end of chromosome.
-        if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 &&
-            !(prev > 0 && base + nE - 1 - prev > T)) {
+        // emitted positions more than T past the last match are mapStart/mapEnd events (and breaks for '=')
+        bool far = false;
+        if (nE > 0 && (isEQ || base + nE - 1 - (pmat ? ppos0 : prev) > T)) { sync_prev(); far = prev > 0 && base + nE - 1 - prev > T; }
+        if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 && !far) {
           atomicAdd(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
           pendingEnd = base;
         } else if (MODE == 1 && nE > 0) {
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (isDX) {
             if (nE <= 8) { dmask = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); dpos = base; }  // flushed after (B)
             else for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
-            if (prev > 0 && base + nE - 1 - prev > T)
+            if (far)
               for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
           }
         }
@@ -349,53 +366,57 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       uint32_t w[STEP_WINS + 1], g[STEP_WINS + 1];
 #pragma unroll
       for (int q = 0; q <= STEP_WINS; q++) { w[q] = __byte_perm(mySeq[ki + q], 0, 0x0123); g[q] = refw[rk + q]; }
-      uint32_t mat = 0;  // matches, same layout as mis
+      uint32_t nzc = 0;  // bases that differ (valid or not), same layout as mis
 #pragma unroll
       for (int q = 0; q < STEP_WINS; q++) {
         const uint32_t x = __funnelshift_l(w[q + 1], w[q], sh) ^ __funnelshift_l(g[q + 1], g[q], rs);
-        const uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;
-        const uint32_t vm = __funnelshift_rc(0u, 0x11111111u, (uint32_t)(4 * min(8, max(0, cnt - 8 * q))));  // top nibbles valid
-        mis |= (nz & vm) << q;
-        mat |= (vm & ~nz) << q;
+        nzc |= ((x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u) << q;
       }
+      const uint32_t vm = s_vm[cnt];
+      mis = nzc & vm;
+      const uint32_t mat = vm & ~nzc;  // matches
       mOff += STEP_BASES;
       errs += __popc(mis);
-      // base index of the first / last match of the step (cnt / -1 if none)
-      int f = cnt, l = -1;
-#pragma unroll
-      for (int q = STEP_WINS - 1; q >= 0; q--) { const uint32_t m = (mat >> q) & 0x11111111u; if (m) f = 8 * q + (__clz(m) >> 2); }
-#pragma unroll
-      for (int q = 0; q < STEP_WINS; q++) { const uint32_t m = (mat >> q) & 0x11111111u; if (m) l = 8 * q + 7 - ((__ffs(m) - 1) >> 2); }
-      // Fast path only when the last match does not lie AHEAD of the step and every position is within T of it (then no
-      // position can be a break, whatever the matches inside).  After an '=' op prev can lie ahead of the step (advance-
-      // then-emit quirk): matches then pull prev back and a gap can open inside the step.
-      if (per_base || prev > pos0) {
-        // exact per-base CigarCluster.add (T < STEP_BASES, or prev ahead of the step)
-        slow_windows++;
+      // Fast path when every position of the step is within T of the last match and that match does not lie AHEAD of the
+      // step (then no position can be a break, whatever the matches inside).  The test uses a lower bound of prev; only
+      // if it fails is prev decoded.  After an '=' op prev can lie ahead of the step (advance-then-emit quirk): matches
+      // then pull prev back and a gap can open inside the step.
+      if (per_base || pos0 + cnt - 1 - (pmat ? ppos0 : prev) > T || (pmat == 0 && prev > pos0)) {
+        sync_prev();
+        const int l = last_match(mat);
+        if (per_base || prev > pos0) {
+          // exact per-base CigarCluster.add (T < STEP_BASES, or prev ahead of the step)
+          slow_windows++;
 #pragma unroll 1
-        for (int i = 0; i < cnt; i++) add(pos0 + i, (mat >> (((7 - (i & 7)) << 2) + (i >> 3))) & 1u);
-      } else if (pos0 + cnt - 1 - prev > T) {
-        // The step right after a junction (or after a long run without a match), in closed form.  Positions i >= i0 are
-        // more than T past the last match; every one of them up to and including the first match f of the step is a
-        // break_p position (mapStart[p]++, mapEnd[prev]++ each, CigarCluster.java:476-486), the first match itself closes
-        // the break (prev, p).  After that match every position of the step is within STEP_BASES-1 <= T of a match.
-        slow_windows++;
-        const int i0 = prev < 0 ? 0 : max(0, prev + T + 1 - pos0);
-        if (f >= i0) {
-          if (MODE == 1 && prev > 0) {
-            const int last = min(f, cnt - 1);
-            for (int i = i0; i <= last; i++) atomicAdd(cov + 2 * arr_stride + pos0 + i, 1);
-            atomicAdd(cov + 3 * arr_stride + prev, last - i0 + 1);
+          for (int i = 0; i < cnt; i++) add(pos0 + i, (mat >> (((7 - (i & 7)) << 2) + (i >> 3))) & 1u);
+        } else if (pos0 + cnt - 1 - prev > T) {
+          // The step right after a junction (or after a long run without a match), in closed form.  Positions i >= i0 are
+          // more than T past the last match; every one of them up to and including the first match f of the step is a
+          // break_p position (mapStart[p]++, mapEnd[prev]++ each, CigarCluster.java:476-486), the first match itself
+          // closes the break (prev, p).  After that match every position of the step is within STEP_BASES-1 <= T of one.
+          slow_windows++;
+          int f = cnt;
+#pragma unroll
+          for (int q = STEP_WINS - 1; q >= 0; q--) { const uint32_t m = (mat >> q) & 0x11111111u; if (m) f = 8 * q + (__clz(m) >> 2); }
+          const int i0 = prev < 0 ? 0 : max(0, prev + T + 1 - pos0);
+          if (f >= i0) {
+            if (MODE == 1 && prev > 0) {
+              const int last = min(f, cnt - 1);
+              for (int i = i0; i <= last; i++) atomicAdd(cov + 2 * arr_stride + pos0 + i, 1);
+              atomicAdd(cov + 3 * arr_stride + prev, last - i0 + 1);
+            }
+            if (f < cnt) {
+              if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
+              if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = pos0 + f;
+              nb++;
+            }
           }
-          if (f < cnt) {
-            if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
-            if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = pos0 + f;
-            nb++;
-          }
+          if (l >= 0) prev = pos0 + l;
+        } else if (l >= 0) {
+          prev = pos0 + l;
         }
-        if (l >= 0) prev = pos0 + l;
-      } else if (l >= 0) {
-        prev = pos0 + l;  // every position is within T of the last match before it
+      } else if (mat) {
+        pmat = mat; ppos0 = pos0;  // every position is within T of the last match before it
       }
     }
     if (MODE == 1) {

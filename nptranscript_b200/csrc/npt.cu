@@ -620,7 +620,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   // shared memory plan: the packed reference lives on chip when it fits (30 kb genome = 15 KB)
   ctx->ref_smem = (size_t)nwords * 4 <= 96 * 1024;
   if (const char* e = getenv("NPT_REF_SMEM")) if (atoi(e) == 0) ctx->ref_smem = false;  // experiments: reference through L1 instead
-  ctx->walk_smem = (ctx->ref_smem ? (size_t)((nwords + 3) & ~3) * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4;
+  ctx->walk_smem = (ctx->ref_smem ? (size_t)((nwords + 3) & ~3) * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4 + 36 * 4;
   ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
   if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
   CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
