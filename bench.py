@@ -278,6 +278,28 @@ def run_ours(args, rank, world, local_rank):
         e2e_t = float(tt.item())
     e2e_value = world * e2e_reads / (e2e_t / 1e3)
 
+    # ---- untimed self-check of the same end-to-end result: conservation sums that hold whatever the input size
+    eng.set_read_index_base(first)
+    eng.begin_chrom(0, g, w.annotation)
+    for b in host_chunks:
+        eng.submit(b)
+    eng.end_chrom()
+    res = eng.fetch()
+    n_ok = int((res["cluster_id"] >= 0).sum())
+    checks = {
+        "reads_clustered == total_counts == sum(cluster counts) == sum(sub-cluster counts)":
+            n_ok == int(res["total_counts"].sum()) == int(res["cl_read_count"].sum()) == int(res["sub_count"].sum()),
+        "sum(depth) == sum(per-read emitted positions)": int(res["depth"].sum(dtype=np.int64)) == int(res["maps_sum"].sum(dtype=np.int64)),
+        "sum(errors) == sum(per-read error positions)": int(res["errors"].sum(dtype=np.int64)) == int(res["err_sum"].sum(dtype=np.int64)),
+        "sum(mapStart) == sum(mapEnd)": int(res["map_start"].sum(dtype=np.int64)) == int(res["map_end"].sum(dtype=np.int64)),
+        "sum(sub-cluster break sums) == sum(per-read breaks)": int(res["sub_sums"].sum(dtype=np.int64)) == int(res["breaks"].sum(dtype=np.int64)),
+        "cluster ids in first-appearance order": bool((np.diff(res["cl_first_read"]) > 0).all()),
+    }
+    eng.release()
+    bad = [k for k, v in checks.items() if not v]
+    if bad:
+        raise SystemExit("bench self-check failed: " + "; ".join(bad))
+
     # ---- roofline of the dominant kernel: the one with the largest live CUDA-event share of the step.  The path needs all
     # of them, so the all-kernel pipeline figure is reported beside it ("pipeline").
     peak, peak_kind = peaks()
@@ -285,7 +307,7 @@ def run_ours(args, rank, world, local_rank):
     wk = float(np.mean(walk_ms))
     st = np.mean(np.array(stages), axis=0)
     names = ["walk_kernel<0> (CIGAR walk + base compare -> breaks)", "walk_kernel<2> (long break lists)",
-             "cluster_kernel (tokens, hash tables, counters)", "walk_kernel<1> (coverage: second walk + RED.ADD)"]
+             "cluster_kernel (tokens, hash tables, counters)", "walk_kernel<1> (coverage pass: second walk, RED.ADD into the cluster rows)"]
     dom = int(np.argmax(st))
     dom_ms = float(st[dom])
     achieved = alg / (dom_ms / 1e3) / 1e9
@@ -322,7 +344,8 @@ def run_ours(args, rank, world, local_rank):
                        "genome_len": w.genome_len, "flags": CFG_KW, "mean_read_bases": float(2 * (d['seq4'].numel() - 64) / n_reads),
                        "mean_cigar_ops": float(d["cigar"].numel() / n_reads), "input_bytes_per_read": in_bytes / n_reads,
                        "l2_policy": "inputs (%.1f GB) larger than L2; no flush needed" % (in_bytes / 1e9),
-                       "clusters": n_clusters, "sub_clusters": n_subs, "serial_path_reads": n_slow, "gen_seconds": gen_s,
+                       "clusters": n_clusters, "sub_clusters": n_subs, "junction_steps": n_slow,
+                       "self_check": {"reads": e2e_reads, "passed": sorted(checks)}, "gen_seconds": gen_s,
                        "merge_breakdown_ms": getattr(__import__("nptranscript_b200.multigpu", fromlist=["x"]).merge_across_ranks, "last", None) if world > 1 else None,
                        "timing": "CUDA events inside libnpt on its compute stream (npt_last_step_ms / npt_last_kernel_ms); wall ms/step %.2f" % wall_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
