@@ -220,17 +220,38 @@ int npt_end_chrom(npt_ctx* ctx);
 int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out);
 int npt_release_results(npt_ctx* ctx);
 
-/* Multi-GPU hooks (reads shard across ranks; tables merge by key on the host; aggregates are summed by the
- * caller's collective, e.g. NCCL all-reduce on these device pointers). */
+/* Multi-GPU (reads shard across ranks in contiguous ranges of the submit order, npt_set_read_index_base).
+ *
+ * Device-side protocol, one exchange of keys and one sum of counters (nptranscript_b200/multigpu.py drives it over NCCL):
+ *   every rank:  npt_submit ...; npt_export_keys -> packed int32 device buffer with the keys of its cluster, sub-cluster
+ *                and break-point-pair tables and their first-appearance indices;
+ *   all-gather the buffers; npt_import_keys(buffer of every OTHER rank): the keys are inserted without counts, so every
+ *                rank now holds the same key set and the same minima;
+ *   npt_end_chrom: the sort-and-rank numbers clusters and sub-clusters identically on every rank (CigarClusters.java:83,
+ *                CigarCluster.java:660 as if all reads had gone through one process in global submit order); per-read ids
+ *                are global;
+ *   all-reduce (sum) the device arrays of npt_device_view in place; then npt_fetch_results returns the global tables. */
 typedef struct npt_device_view {
-  int32_t n_clusters;           /* local clusters after npt_end_chrom */
+  int32_t n_clusters;           /* clusters after npt_end_chrom */
   int32_t cov_stride;
-  void* coverage;               /* device int32 [4][n_slots][num_sources][cov_stride] in GLOBAL cluster order once npt_remap_clusters ran */
+  void* coverage;               /* device int32 [4][n_clusters][num_sources][cov_stride], rows in cluster-id order */
   int64_t coverage_elems;
   void* small_counts;           /* device int32: total_counts[S], spliced[S][n_orf], unspliced[S][n_orf] */
   int64_t small_elems;
+  int32_t n_subs, n_pairs;
+  void* sub_count;              /* device int32 [n_subs][num_sources], sub-clusters in result order */
+  int64_t sub_count_elems;
+  void* sub_break_sum;          /* device int32 [n_subs] */
+  int64_t sub_break_sum_elems;
+  void* sub_sums;               /* device int64 [sub_sum_off[n_subs]] */
+  int64_t sub_sums_elems;
+  void* pair_count;             /* device int32 [n_pairs], pairs in result order (sorted by src, level, start, end) */
+  int64_t pair_count_elems;
 } npt_device_view;
-/* Reorders/zero-extends coverage rows so that local cluster i lands at row global_id[i] of n_global rows. */
+int npt_export_keys(npt_ctx* ctx, const int32_t** dev_buf, int64_t* n_words);
+int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words);
+/* Host-side alternative (tables merged on the host by npt_merge_tables): reorders/zero-extends coverage rows so that
+ * local cluster i lands at row global_id[i] of n_global rows. */
 int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global);
 int npt_device_view_get(npt_ctx* ctx, npt_device_view* out);
 /* Host-side merge of the table part of every rank's npt_results (first-read indices already global, see

@@ -57,7 +57,9 @@ class npt_results(C.Structure):
 
 class npt_device_view(C.Structure):
     _fields_ = [("n_clusters", i32), ("cov_stride", i32), ("coverage", C.c_void_p), ("coverage_elems", i64),
-                ("small_counts", C.c_void_p), ("small_elems", i64)]
+                ("small_counts", C.c_void_p), ("small_elems", i64), ("n_subs", i32), ("n_pairs", i32),
+                ("sub_count", C.c_void_p), ("sub_count_elems", i64), ("sub_break_sum", C.c_void_p), ("sub_break_sum_elems", i64),
+                ("sub_sums", C.c_void_p), ("sub_sums_elems", i64), ("pair_count", C.c_void_p), ("pair_count_elems", i64)]
 
 
 # every symbol include/npt.h declares (checked by tests/test_abi.py against the header text and the built .so)
@@ -66,6 +68,7 @@ SYMBOLS = [
     "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_remap_clusters", "npt_device_view_get",
     "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
     "npt_merge_tables", "npt_merged_results", "npt_merged_cluster_map", "npt_merged_sub_map", "npt_merge_free",
+    "npt_export_keys", "npt_import_keys",
 ]
 
 
@@ -105,8 +108,10 @@ def declare(lib):
     lib.npt_merged_sub_map.restype = P(i32)
     lib.npt_merge_free.argtypes = [vp]
     lib.npt_merge_free.restype = None
+    lib.npt_export_keys.argtypes = [vp, P(vp), P(i64)]
+    lib.npt_import_keys.argtypes = [vp, vp, i64]
     for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_wait", "npt_end_chrom", "npt_fetch_results",
               "npt_release_results", "npt_remap_clusters", "npt_device_view_get", "npt_set_read_index_base",
-              "npt_last_kernel_ms", "npt_last_step_ms"):
+              "npt_last_kernel_ms", "npt_last_step_ms", "npt_export_keys", "npt_import_keys"):
         getattr(lib, s).restype = C.c_int
     return lib

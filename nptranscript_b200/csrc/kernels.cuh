@@ -498,9 +498,30 @@ __device__ int gff_upstream(const DevCfg& c, int l1, int r1, bool fwd_known, boo
 }
 
 // break-point matrix cell += 1   (BreakPoints.addBreakPoint, J/cluster/BreakPoints.java:102-108)
+__device__ __forceinline__ unsigned long long pair_key(int src, int level, int st, int en) {
+  return (1ULL << 63) | ((unsigned long long)src << 59) | ((unsigned long long)level << 58) | ((unsigned long long)(unsigned)st << 29) |
+         (unsigned long long)(unsigned)en;
+}
+// find-or-insert of a cell without counting (keys imported from another rank)
+__device__ void pair_touch(const DevCfg& c, unsigned long long key) {
+  unsigned slot = (unsigned)mix64(key) & c.pr_mask;
+  for (unsigned probe = 0; probe <= c.pr_mask; probe++, slot = (slot + 1) & c.pr_mask) {
+    PairEntry* e = c.pr + slot;
+    unsigned long long k = ldcg(&e->key);
+    if (k == 0) {
+      k = atomicCAS(&e->key, 0ULL, key);
+      if (k == 0) {
+        const unsigned np = atomicAdd(c.counters + CN_PAIRS, 1u);
+        if ((int)np >= c.pr_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
+        return;
+      }
+    }
+    if (k == key) return;
+  }
+  atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
+}
 __device__ void pair_add(const DevCfg& c, int src, int level, int st, int en) {
-  const unsigned long long key = (1ULL << 63) | ((unsigned long long)src << 59) | ((unsigned long long)level << 58) |
-                                 ((unsigned long long)(unsigned)st << 29) | (unsigned long long)(unsigned)en;
+  const unsigned long long key = pair_key(src, level, st, en);
   unsigned slot = (unsigned)mix64(key) & c.pr_mask;
   for (unsigned probe = 0; probe <= c.pr_mask; probe++, slot = (slot + 1) & c.pr_mask) {
     PairEntry* e = c.pr + slot;
@@ -521,6 +542,82 @@ __device__ void pair_add(const DevCfg& c, int src, int level, int st, int en) {
     }
   }
   atomicOr(c.counters + CN_ERROR, (unsigned)ERR_PAIR_FULL);
+}
+
+// ------------------------------------------------------------------------------------------------ table inserts
+// Cluster table: find or insert a token list (token(k), k < ntok).  Returns the slot, -1 if the table or arena is full.
+template <typename TokenFn>
+__device__ int cluster_find_or_insert(const DevCfg& c, int ntok, TokenFn token) {
+  unsigned long long h = 0x1234ULL ^ ((unsigned long long)ntok << 48);
+  for (int k = 0; k < ntok; k++) h = mix64(h + (unsigned)token(k));
+  const unsigned h32 = (unsigned)(h >> 32) | 1u;
+  int cl_slot = -1;
+  unsigned slot = (unsigned)h & c.cl_mask;
+  unsigned my_off = 0xFFFFFFFFu;
+  for (unsigned probe = 0; probe <= c.cl_mask; probe++, slot = (slot + 1) & c.cl_mask) {
+    unsigned long long w = ldcg(&c.cl[slot].word);
+    if (w == 0) {
+      if (my_off == 0xFFFFFFFFu) {  // write the record first, publish it with the CAS
+        my_off = atomicAdd(c.counters + CN_TOK_USED, (unsigned)(CL_REC_HDR + ntok));
+        if (my_off + CL_REC_HDR + ntok > c.tok_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); break; }
+        c.cl_rec[my_off] = -1; c.cl_rec[my_off + 1] = ntok;
+        for (int k = 0; k < ntok; k++) c.cl_rec[my_off + CL_REC_HDR + k] = token(k);
+        __threadfence();
+      }
+      w = atomicCAS(&c.cl[slot].word, 0ULL, ((unsigned long long)h32 << 32) | my_off);
+      if (w == 0) {
+        const unsigned prov = atomicAdd(c.counters + CN_CLUSTERS, 1u);
+        if ((int)prov >= c.cl_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
+        c.cl_rec[my_off] = (int)prov;  // read by the coverage pass (a later kernel) and at end of chromosome
+        cl_slot = (int)slot;
+        break;
+      }
+    }
+    if ((unsigned)(w >> 32) == h32) {  // verify the full key
+      const unsigned off = (unsigned)(w & 0xffffffffu);
+      bool eq = ldcg(c.cl_rec + off + 1) == ntok;
+      for (int k = 0; eq && k < ntok; k++) eq = ldcg(c.cl_rec + off + CL_REC_HDR + k) == token(k);
+      if (eq) { cl_slot = (int)slot; break; }
+    }
+  }
+  if (cl_slot < 0) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
+  return cl_slot;
+}
+// Sub-cluster table: key = (cluster slot, key(i), i < nkey) — CigarCluster.cloneBreaks :620-631.  nsum = entries reserved in the
+// int64 break-sum arena when the record is created.  Returns the slot, -1 if full.
+template <typename KeyFn>
+__device__ int sub_find_or_insert(const DevCfg& c, int cl_slot, int nkey, int nsum, KeyFn key) {
+  unsigned long long hs = 0x77ULL + (unsigned long long)(unsigned)cl_slot * 0x9E3779B97F4A7C15ULL + ((unsigned long long)nkey << 48);
+  for (int i = 0; i < nkey; i++) hs = mix64(hs + (unsigned)key(i));
+  const unsigned hs32 = (unsigned)(hs >> 32) | 1u;
+  unsigned slot = (unsigned)hs & c.sb_mask;
+  unsigned my_off = 0xFFFFFFFFu;
+  for (unsigned probe = 0; probe <= c.sb_mask; probe++, slot = (slot + 1) & c.sb_mask) {
+    unsigned long long w = ldcg(&c.sb[slot].word);
+    if (w == 0) {
+      if (my_off == 0xFFFFFFFFu) {
+        my_off = atomicAdd(c.counters + CN_SUBKEY_USED, (unsigned)(SB_REC_HDR + nkey));
+        const unsigned soff = nsum ? atomicAdd(c.counters + CN_SUMS_USED, (unsigned)nsum) : 0u;
+        if (my_off + SB_REC_HDR + nkey > c.sbkey_cap || soff + nsum > c.sums_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); return -1; }
+        c.sb_rec[my_off] = cl_slot; c.sb_rec[my_off + 1] = nkey; c.sb_rec[my_off + 2] = (int)soff; c.sb_rec[my_off + 3] = nsum;
+        for (int i = 0; i < nkey; i++) c.sb_rec[my_off + SB_REC_HDR + i] = key(i);
+        __threadfence();
+      }
+      w = atomicCAS(&c.sb[slot].word, 0ULL, ((unsigned long long)hs32 << 32) | my_off);
+      if (w == 0) {
+        const unsigned ns = atomicAdd(c.counters + CN_SUBS, 1u);
+        if ((int)ns >= c.sb_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL);
+        return (int)slot;
+      }
+    }
+    if ((unsigned)(w >> 32) == hs32) {
+      const unsigned off = (unsigned)(w & 0xffffffffu);
+      bool eq = ldcg(c.sb_rec + off) == cl_slot && ldcg(c.sb_rec + off + 1) == nkey;
+      for (int i = 0; eq && i < nkey; i++) eq = ldcg(c.sb_rec + off + SB_REC_HDR + i) == key(i);
+      if (eq) return (int)slot;
+    }
+  }
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------------ clustering
@@ -660,41 +757,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
 
     // ---- cluster table: find or insert the token list
     const unsigned long long gidx = (unsigned long long)(b.idx_base + r);
-    unsigned long long h = 0x1234ULL ^ ((unsigned long long)ntok << 48);
-    for (int k = 0; k < ntok; k++) h = mix64(h + (unsigned)token(k));
-    const unsigned h32 = (unsigned)(h >> 32) | 1u;
-    int cl_slot = -1;
-    {
-      unsigned slot = (unsigned)h & c.cl_mask;
-      unsigned my_off = 0xFFFFFFFFu;
-      for (unsigned probe = 0; probe <= c.cl_mask; probe++, slot = (slot + 1) & c.cl_mask) {
-        unsigned long long w = ldcg(&c.cl[slot].word);
-        if (w == 0) {
-          if (my_off == 0xFFFFFFFFu) {  // write the record first, publish it with the CAS
-            my_off = atomicAdd(c.counters + CN_TOK_USED, (unsigned)(CL_REC_HDR + ntok));
-            if (my_off + CL_REC_HDR + ntok > c.tok_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); break; }
-            c.cl_rec[my_off] = -1; c.cl_rec[my_off + 1] = ntok;
-            for (int k = 0; k < ntok; k++) c.cl_rec[my_off + CL_REC_HDR + k] = token(k);
-            __threadfence();
-          }
-          w = atomicCAS(&c.cl[slot].word, 0ULL, ((unsigned long long)h32 << 32) | my_off);
-          if (w == 0) {
-            const unsigned prov = atomicAdd(c.counters + CN_CLUSTERS, 1u);
-            if ((int)prov >= c.cl_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
-            c.cl_rec[my_off] = (int)prov;  // read by the coverage pass (a later kernel) and at end of chromosome
-            cl_slot = (int)slot;
-            break;
-          }
-        }
-        if ((unsigned)(w >> 32) == h32) {  // verify the full key
-          const unsigned off = (unsigned)(w & 0xffffffffu);
-          bool eq = ldcg(c.cl_rec + off + 1) == ntok;
-          for (int k = 0; eq && k < ntok; k++) eq = ldcg(c.cl_rec + off + CL_REC_HDR + k) == token(k);
-          if (eq) { cl_slot = (int)slot; break; }
-        }
-      }
-      if (cl_slot < 0) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_CL_FULL);
-    }
+    const int cl_slot = cluster_find_or_insert(c, ntok, token);
     // ---- sub-cluster table: key = (cluster slot, binned breaks) — CigarCluster.cloneBreaks :620-631
     int sb_slot = -1;
     if (cl_slot >= 0) {
@@ -703,37 +766,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
       if (!c.include_start && fwd_known) { if (fwd) a = 1; else e = nb - 1; }
       const int nkey = e - a;
       const int nsum = c.track_sums ? nb : 0;
-      unsigned long long hs = 0x77ULL + (unsigned long long)(unsigned)cl_slot * 0x9E3779B97F4A7C15ULL + ((unsigned long long)nkey << 48);
-      for (int i = a; i < e; i++) hs = mix64(hs + (unsigned)(br[i] / c.bin));
-      const unsigned hs32 = (unsigned)(hs >> 32) | 1u;
-      unsigned slot = (unsigned)hs & c.sb_mask;
-      unsigned my_off = 0xFFFFFFFFu;
-      for (unsigned probe = 0; probe <= c.sb_mask; probe++, slot = (slot + 1) & c.sb_mask) {
-        unsigned long long w = ldcg(&c.sb[slot].word);
-        if (w == 0) {
-          if (my_off == 0xFFFFFFFFu) {
-            my_off = atomicAdd(c.counters + CN_SUBKEY_USED, (unsigned)(SB_REC_HDR + nkey));
-            const unsigned soff = nsum ? atomicAdd(c.counters + CN_SUMS_USED, (unsigned)nsum) : 0u;
-            if (my_off + SB_REC_HDR + nkey > c.sbkey_cap || soff + nsum > c.sums_cap) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_ARENA_FULL); break; }
-            c.sb_rec[my_off] = cl_slot; c.sb_rec[my_off + 1] = nkey; c.sb_rec[my_off + 2] = (int)soff; c.sb_rec[my_off + 3] = nsum;
-            for (int i = a; i < e; i++) c.sb_rec[my_off + SB_REC_HDR + i - a] = br[i] / c.bin;
-            __threadfence();
-          }
-          w = atomicCAS(&c.sb[slot].word, 0ULL, ((unsigned long long)hs32 << 32) | my_off);
-          if (w == 0) {
-            const unsigned ns = atomicAdd(c.counters + CN_SUBS, 1u);
-            if ((int)ns >= c.sb_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL);
-            sb_slot = (int)slot;
-            break;
-          }
-        }
-        if ((unsigned)(w >> 32) == hs32) {
-          const unsigned off = (unsigned)(w & 0xffffffffu);
-          bool eq = ldcg(c.sb_rec + off) == cl_slot && ldcg(c.sb_rec + off + 1) == nkey;
-          for (int i = a; eq && i < e; i++) eq = ldcg(c.sb_rec + off + SB_REC_HDR + i - a) == br[i] / c.bin;
-          if (eq) { sb_slot = (int)slot; break; }
-        }
-      }
+      sb_slot = sub_find_or_insert(c, cl_slot, nkey, nsum, [&](int i) { return br[a + i] / c.bin; });
       if (sb_slot < 0) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL);
       else {
         const unsigned long long idxf = (gidx << 2) | (unsigned long long)(((fwd_known && fwd) ? 1 : 0) | (neg ? 2 : 0));
@@ -769,6 +802,48 @@ __global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x) if (s_cnt[i]) atomicAdd(c.small + i, s_cnt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ multi-rank key exchange
+// Packed key buffer of one rank (int32 words), produced by npt_export_keys and consumed by npt_import_keys on the other ranks:
+//   [0..16) header: magic, cl_n, cl_rec_words, sb_n, sb_rec_words, pr_n, cl_slots, S, then the word offsets of the five sections
+//   cl_list  [cl_n][4]  slot, record offset, first index lo, hi
+//   cl_rec   the rank's cluster record arena (records [id, ntok, tokens...])
+//   sb_list  [sb_n][6]  record offset, (first index << 2 | flags) lo, hi, first source-0 index lo, hi, 0
+//   sb_rec   the rank's sub-cluster record arena (records [cluster slot, nkey, -, nsum, keys...])
+//   pr_keys  [pr_n][2]  break-point pair key lo, hi
+// Importing inserts the KEYS with their first-appearance indices and no counts: afterwards every rank's tables hold the
+// same key set and minima, so the sort-and-rank at end of chromosome yields the same global numbering everywhere and the
+// counters (in that order) can be summed with one all-reduce.
+constexpr int KX_MAGIC = 0x4b58, KX_HDR = 16;
+
+__global__ void import_clusters_kernel(const DevCfg c, const int* list, int n, const int* rec, int* slotmap) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int rslot = list[4 * i], off = list[4 * i + 1];
+    const unsigned long long first = (unsigned)list[4 * i + 2] | ((unsigned long long)(unsigned)list[4 * i + 3] << 32);
+    const int ntok = rec[off + 1];
+    const int slot = cluster_find_or_insert(c, ntok, [&](int k) { return rec[off + CL_REC_HDR + k]; });
+    slotmap[rslot] = slot;
+    if (slot >= 0 && first < ldcg(&c.cl[slot].min_idx)) atomicMin(&c.cl[slot].min_idx, first);
+  }
+}
+__global__ void import_subs_kernel(const DevCfg c, const int* list, int n, const int* rec, const int* slotmap) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int off = list[6 * i];
+    const unsigned long long first = (unsigned)list[6 * i + 1] | ((unsigned long long)(unsigned)list[6 * i + 2] << 32);
+    const unsigned long long first0 = (unsigned)list[6 * i + 3] | ((unsigned long long)(unsigned)list[6 * i + 4] << 32);
+    const int cl_slot = slotmap[rec[off]];
+    if (cl_slot < 0) continue;  // its cluster did not fit: already flagged
+    const int nkey = rec[off + 1], nsum = rec[off + 3];
+    const int slot = sub_find_or_insert(c, cl_slot, nkey, nsum, [&](int k) { return rec[off + SB_REC_HDR + k]; });
+    if (slot < 0) { atomicOr(c.counters + CN_ERROR, (unsigned)ERR_SUB_FULL); continue; }
+    if (first < ldcg(&c.sb[slot].min_idx)) atomicMin(&c.sb[slot].min_idx, first);
+    if (c.fit && first0 < ldcg(c.sub_min0 + slot)) atomicMin(c.sub_min0 + slot, first0);
+  }
+}
+__global__ void import_pairs_kernel(const DevCfg c, const int* keys, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    pair_touch(c, (unsigned)keys[2 * i] | ((unsigned long long)(unsigned)keys[2 * i + 1] << 32));
 }
 
 }  // namespace npt

@@ -107,7 +107,6 @@ struct npt_ctx {
   DBuf<unsigned char> d_cub;
   DBuf<long long> d_break_off;
   DBuf<int> d_breaks_out;
-  DBuf<int> d_pairs_out;
   // device block pool: cudaFree of large blocks is synchronous and slow (hundreds of ms per chromosome in the e2e trace),
   // so per-batch output blocks are recycled across batches and chromosomes and only freed in npt_destroy
   std::vector<std::pair<void*, size_t>> pool_free;
@@ -127,6 +126,16 @@ struct npt_ctx {
   DBuf<unsigned> d_ex_u[5];
   DBuf<int> d_ex_i[2];
   DBuf<unsigned char> d_ex_flags;
+  // end-of-chromosome columns in final (rank) order that a multi-rank caller sums in place before fetching
+  DBuf<long long> d_exc_first; DBuf<unsigned> d_exc_u[2];  // cluster columns (fetch)
+  DBuf<unsigned> d_fin_sum_off;              // [n_subs + 1]
+  DBuf<long long> d_fin_sums;                // [total_sums]
+  long long total_sums = 0;
+  DBuf<unsigned long long> d_pair_keys, d_pair_keys2;  // compacted / sorted break-point pair keys
+  DBuf<int> d_pair_cnt, d_pair_cnt2;
+  // multi-rank key exchange
+  DBuf<int> d_kx, d_kx_slotmap;
+  DBuf<unsigned> d_kx_ctr;
   npt_results res{};
   // host results (pinned for the large per-read arrays)
   HBuf<int> r_cluster, r_sub, r_start, r_end, r_rst, r_ren, r_maps, r_err, r_breaks;
@@ -258,15 +267,50 @@ __global__ void export_subs_kernel(const Slot* sb, const int* sb_rec, const int*
   }
 }
 
-__global__ void compact_pairs_kernel(const PairEntry* pr, unsigned nslots, int* out, unsigned* counter, int cap) {
+__global__ void compact_pairs_kernel(const PairEntry* pr, unsigned nslots, unsigned long long* keys, int* counts, unsigned* counter, int cap) {
   for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
     const unsigned long long k = pr[s].key;
     if (k) {
       const unsigned o = atomicAdd(counter, 1u);
+      if ((int)o < cap) { keys[o] = k; counts[o] = pr[s].count; }
+    }
+  }
+}
+// break sums of the sub-clusters, from arena order to final (rank) order
+__global__ void gather_sums_kernel(int n, const unsigned* arena_off, const unsigned* nsum, const unsigned* fin_off, const unsigned long long* arena,
+                                   long long* out) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
+    for (unsigned i = 0; i < nsum[g]; i++) out[fin_off[g] + i] = (long long)arena[arena_off[g] + i];
+}
+// multi-rank key exchange: live slots of the three tables as lists (order irrelevant)
+__global__ void kx_list_clusters_kernel(const Slot* cl, unsigned nslots, int* list, unsigned* counter, int cap) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long w = cl[s].word;
+    if (w) {
+      const unsigned o = atomicAdd(counter, 1u);
+      if ((int)o < cap) { list[4 * o] = (int)s; list[4 * o + 1] = (int)(w & 0xffffffffu); list[4 * o + 2] = (int)(cl[s].min_idx & 0xffffffffu); list[4 * o + 3] = (int)(cl[s].min_idx >> 32); }
+    }
+  }
+}
+__global__ void kx_list_subs_kernel(const Slot* sb, unsigned nslots, const unsigned long long* min0, int* list, unsigned* counter, int cap) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long w = sb[s].word;
+    if (w) {
+      const unsigned o = atomicAdd(counter, 1u);
       if ((int)o < cap) {
-        out[o * 5 + 0] = (int)((k >> 59) & 0xF); out[o * 5 + 1] = (int)((k >> 58) & 1);
-        out[o * 5 + 2] = (int)((k >> 29) & 0x1FFFFFFF); out[o * 5 + 3] = (int)(k & 0x1FFFFFFF); out[o * 5 + 4] = pr[s].count;
+        const unsigned long long m = sb[s].min_idx, m0 = min0 ? min0[s] : ~0ULL;
+        list[6 * o] = (int)(w & 0xffffffffu); list[6 * o + 1] = (int)(m & 0xffffffffu); list[6 * o + 2] = (int)(m >> 32);
+        list[6 * o + 3] = (int)(m0 & 0xffffffffu); list[6 * o + 4] = (int)(m0 >> 32); list[6 * o + 5] = 0;
       }
+    }
+  }
+}
+__global__ void kx_list_pairs_kernel(const PairEntry* pr, unsigned nslots, int* keys, unsigned* counter, int cap) {
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+    const unsigned long long k = pr[s].key;
+    if (k) {
+      const unsigned o = atomicAdd(counter, 1u);
+      if ((int)o < cap) { keys[2 * o] = (int)(k & 0xffffffffu); keys[2 * o + 1] = (int)(k >> 32); }
     }
   }
 }
@@ -478,13 +522,14 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();
-  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
+  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
+  ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
   ctx->d_cov.release(); ctx->d_cov_out.release(); ctx->d_small.release(); ctx->d_counters.release(); ctx->d_keys.release();
   ctx->d_keys2.release(); ctx->d_vals.release(); ctx->d_vals2.release(); ctx->d_cl_slot.release(); ctx->d_sb_slot.release();
   ctx->d_cl_rank.release(); ctx->d_cl_slot_rank.release(); ctx->d_sb_grank.release(); ctx->d_cl_sub_off.release(); ctx->d_cub.release(); ctx->d_break_off.release();
-  ctx->d_breaks_out.release(); ctx->d_pairs_out.release(); ctx->d_ex_first.release(); ctx->d_ex_flags.release();
+  ctx->d_breaks_out.release(); ctx->d_ex_first.release(); ctx->d_ex_flags.release();
   for (auto& b : ctx->d_ex_u) b.release();
   for (auto& b : ctx->d_ex_i) b.release();
   for (auto& s : ctx->stg) { s.buf.release(); if (s.done) cudaEventDestroy(s.done); }
@@ -874,15 +919,51 @@ int npt_end_chrom(npt_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->d_break_off.p + n_total, &total_breaks, 8, cudaMemcpyHostToDevice, ctx->s_comp));
   CK(cudaGetLastError());
   // break-point pairs -> dense list
+  // break-point pairs -> dense list sorted by key = (src, level, start, end): the order of the results, and the same on
+  // every rank once the keys were exchanged
   ctx->n_pairs = 0;
   if (dc.calc_breaks1) {
     const int np = (int)ctx->h_counters[CN_PAIRS];
-    CK(ctx->d_pairs_out.ensure((size_t)std::max(np, 1) * 5));
+    const size_t np1 = (size_t)std::max(np, 1);
+    CK(ctx->d_pair_keys.ensure(np1)); CK(ctx->d_pair_keys2.ensure(np1)); CK(ctx->d_pair_cnt.ensure(np1)); CK(ctx->d_pair_cnt2.ensure(np1));
     unsigned* ctr = ctx->d_counters.p + CN_PAIRS;
     CK(cudaMemsetAsync(ctr, 0, 4, ctx->s_comp));
-    compact_pairs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.pr, dc.pr_mask + 1, ctx->d_pairs_out.p, ctr, np);
+    compact_pairs_kernel<<<ctx->sm_count * 2, 256, 0, ctx->s_comp>>>(dc.pr, dc.pr_mask + 1, ctx->d_pair_keys.p, ctx->d_pair_cnt.p, ctr, np);
     ctx->total_launches++;
+    if (np > 0 && (rc = sort_pairs(ctx, ctx->d_pair_keys.p, ctx->d_pair_keys2.p, ctx->d_pair_cnt.p, ctx->d_pair_cnt2.p, np))) return rc;
     ctx->n_pairs = np;
+  }
+  // sub-cluster columns in final order (counts, break sums): device copies that fetch reads and a multi-rank caller sums
+  {
+    const int S = dc.S, nc1 = std::max(nc, 1), ns1 = std::max(ns, 1);
+    CK(ctx->d_ex_first.ensure(std::max(nc1, ns1)));
+    for (auto& b : ctx->d_ex_u) CK(b.ensure(std::max(nc1, ns1)));
+    CK(ctx->d_ex_i[0].ensure((size_t)ns1 * S)); CK(ctx->d_ex_i[1].ensure(ns1));
+    CK(ctx->d_ex_flags.ensure(ns1));
+    CK(ctx->d_fin_sum_off.ensure(ns1 + 1));
+    ctx->total_sums = 0;
+    if (ns > 0) {
+      export_subs_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(dc.sb, dc.sb_rec, ctx->d_sb_slot.p, ns, S, dc.sub_count, dc.sub_break_sum,
+                                                                     ctx->d_ex_first.p, ctx->d_ex_u[0].p, ctx->d_ex_u[1].p, ctx->d_ex_i[0].p, ctx->d_ex_i[1].p,
+                                                                     ctx->d_ex_u[2].p, ctx->d_ex_u[3].p, ctx->d_ex_flags.p);
+      size_t tmp = 0;
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_ex_u[3].p, ctx->d_fin_sum_off.p, ns, ctx->s_comp));
+      CK(ctx->d_cub.ensure(tmp));
+      CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, tmp, ctx->d_ex_u[3].p, ctx->d_fin_sum_off.p, ns, ctx->s_comp));
+      unsigned last_off = 0, last_n = 0;
+      CK(cudaMemcpyAsync(&last_off, ctx->d_fin_sum_off.p + ns - 1, 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+      CK(cudaMemcpyAsync(&last_n, ctx->d_ex_u[3].p + ns - 1, 4, cudaMemcpyDeviceToHost, ctx->s_comp));
+      CK(cudaStreamSynchronize(ctx->s_comp));
+      ctx->total_sums = dc.track_sums ? (long long)last_off + last_n : 0;
+      const unsigned tot = (unsigned)((long long)last_off + last_n);
+      CK(cudaMemcpyAsync(ctx->d_fin_sum_off.p + ns, &tot, 4, cudaMemcpyHostToDevice, ctx->s_comp));
+      CK(ctx->d_fin_sums.ensure((size_t)std::max<long long>(ctx->total_sums, 1)));
+      if (ctx->total_sums)
+        gather_sums_kernel<<<(ns + 255) / 256, 256, 0, ctx->s_comp>>>(ns, ctx->d_ex_u[2].p, ctx->d_ex_u[3].p, ctx->d_fin_sum_off.p, dc.sub_sums,
+                                                                       ctx->d_fin_sums.p);
+      ctx->total_launches += 4;
+      CK(cudaGetLastError());
+    }
   }
   // coverage: difference rows -> depth, rows in cluster-id order
   if (dc.record_depth) {
@@ -944,20 +1025,17 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
   }
   if (what & NPT_FETCH_TABLES) {
     const int nc1 = std::max(nc, 1), ns1 = std::max(ns, 1);
-    CK(ctx->d_ex_first.ensure(std::max(nc1, ns1)));
-    for (auto& b : ctx->d_ex_u) CK(b.ensure(std::max(nc1, ns1)));
-    CK(ctx->d_ex_i[0].ensure((size_t)ns1 * S)); CK(ctx->d_ex_i[1].ensure(ns1));
-    CK(ctx->d_ex_flags.ensure(ns1));
+    CK(ctx->d_exc_first.ensure(nc1)); CK(ctx->d_exc_u[0].ensure(nc1)); CK(ctx->d_exc_u[1].ensure(nc1));
     // clusters
     std::vector<long long> first(nc1);
     std::vector<unsigned> toff(nc1), ntok(nc1);
     if (nc > 0) {
-      export_clusters_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dc.cl, dc.cl_rec, ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_ex_first.p,
-                                                              ctx->d_ex_u[0].p, ctx->d_ex_u[1].p);
+      export_clusters_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dc.cl, dc.cl_rec, ctx->d_cl_slot.p, ctx->d_cl_rank.p, nc, ctx->d_exc_first.p,
+                                                              ctx->d_exc_u[0].p, ctx->d_exc_u[1].p);
       CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(first.data(), ctx->d_ex_first.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(toff.data(), ctx->d_ex_u[0].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(ntok.data(), ctx->d_ex_u[1].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(first.data(), ctx->d_exc_first.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(toff.data(), ctx->d_exc_u[0].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ntok.data(), ctx->d_exc_u[1].p, (size_t)nc * 4, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int> tok_arena(std::max<unsigned>(ctx->h_counters[CN_TOK_USED], 1));
     CK(cudaMemcpyAsync(tok_arena.data(), dc.cl_rec, (size_t)ctx->h_counters[CN_TOK_USED] * 4, cudaMemcpyDeviceToHost, st));
@@ -973,63 +1051,58 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
     }
     ctx->t_cl_key_off[nc] = (uint32_t)ctx->t_cl_key_tok.size();
     ctx->t_cl_sub_off.assign(cl_sub_off.begin(), cl_sub_off.end());
-    // sub-clusters
+    // sub-clusters: columns were put in final order on the device at end of chromosome (and possibly summed across ranks since)
     std::vector<long long> sfirst(ns1);
-    std::vector<unsigned> koff(ns1), nkey(ns1), soff(ns1), nsum(ns1);
-    std::vector<int> cnt((size_t)ns1 * S), bsum(ns1);
+    std::vector<unsigned> koff(ns1), nkey(ns1);
     std::vector<unsigned char> sflags(ns1);
+    ctx->t_sub_count.assign((size_t)ns * S, 0); ctx->t_sub_break_sum.assign(ns, 0);
+    ctx->t_sub_sum_off.assign(ns + 1, 0); ctx->t_sub_sums.assign((size_t)ctx->total_sums, 0);
     if (ns > 0) {
-      export_subs_kernel<<<(ns + 255) / 256, 256, 0, st>>>(dc.sb, dc.sb_rec, ctx->d_sb_slot.p, ns, S, dc.sub_count, dc.sub_break_sum,
-                                                          ctx->d_ex_first.p, ctx->d_ex_u[0].p, ctx->d_ex_u[1].p, ctx->d_ex_i[0].p, ctx->d_ex_i[1].p,
-                                                          ctx->d_ex_u[2].p, ctx->d_ex_u[3].p, ctx->d_ex_flags.p);
-      CK(cudaGetLastError());
       CK(cudaMemcpyAsync(sfirst.data(), ctx->d_ex_first.p, (size_t)ns * 8, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(koff.data(), ctx->d_ex_u[0].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(nkey.data(), ctx->d_ex_u[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(cnt.data(), ctx->d_ex_i[0].p, (size_t)ns * S * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(bsum.data(), ctx->d_ex_i[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(soff.data(), ctx->d_ex_u[2].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(nsum.data(), ctx->d_ex_u[3].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->t_sub_count.data(), ctx->d_ex_i[0].p, (size_t)ns * S * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->t_sub_break_sum.data(), ctx->d_ex_i[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
       CK(cudaMemcpyAsync(sflags.data(), ctx->d_ex_flags.p, (size_t)ns, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->t_sub_sum_off.data(), ctx->d_fin_sum_off.p, (size_t)(ns + 1) * 4, cudaMemcpyDeviceToHost, st));
+      if (ctx->total_sums)
+        CK(cudaMemcpyAsync(ctx->t_sub_sums.data(), ctx->d_fin_sums.p, (size_t)ctx->total_sums * 8, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int> key_arena(std::max<unsigned>(ctx->h_counters[CN_SUBKEY_USED], 1));
     CK(cudaMemcpyAsync(key_arena.data(), dc.sb_rec, (size_t)ctx->h_counters[CN_SUBKEY_USED] * 4, cudaMemcpyDeviceToHost, st));
-    std::vector<long long> sums_arena(std::max<unsigned>(ctx->h_counters[CN_SUMS_USED], 1));
-    if (dc.track_sums)
-      CK(cudaMemcpyAsync(sums_arena.data(), dc.sub_sums, (size_t)ctx->h_counters[CN_SUMS_USED] * 8, cudaMemcpyDeviceToHost, st));
     const int nsmall = S * (1 + 2 * dc.n_orf);
     ctx->t_small.assign(nsmall, 0);
     CK(cudaMemcpyAsync(ctx->t_small.data(), dc.small, (size_t)nsmall * 4, cudaMemcpyDeviceToHost, st));
-    std::vector<int> pr((size_t)std::max<int64_t>(ctx->n_pairs, 1) * 5);
-    if (ctx->n_pairs) CK(cudaMemcpyAsync(pr.data(), ctx->d_pairs_out.p, (size_t)ctx->n_pairs * 5 * 4, cudaMemcpyDeviceToHost, st));
+    const size_t np = (size_t)ctx->n_pairs;
+    std::vector<unsigned long long> pkeys(std::max<size_t>(np, 1));
+    ctx->t_pair[4].assign(np, 0);
+    if (np) {
+      CK(cudaMemcpyAsync(pkeys.data(), ctx->d_pair_keys2.p, np * 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(ctx->t_pair[4].data(), ctx->d_pair_cnt2.p, np * 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     ctx->t_sub_first.assign(sfirst.begin(), sfirst.begin() + ns);
-    ctx->t_sub_key_off.assign(ns + 1, 0); ctx->t_sub_sum_off.assign(ns + 1, 0);
-    ctx->t_sub_key.clear(); ctx->t_sub_sums.clear();
-    ctx->t_sub_count.assign(cnt.begin(), cnt.begin() + (size_t)ns * S);
-    ctx->t_sub_break_sum.assign(bsum.begin(), bsum.begin() + ns);
+    ctx->t_sub_key_off.assign(ns + 1, 0);
+    ctx->t_sub_key.clear();
     ctx->t_sub_flags.assign(sflags.begin(), sflags.begin() + ns);
     for (int r = 0; r < ns; r++) {
       ctx->t_sub_key_off[r] = (uint32_t)ctx->t_sub_key.size();
       ctx->t_sub_key.insert(ctx->t_sub_key.end(), key_arena.begin() + koff[r], key_arena.begin() + koff[r] + nkey[r]);
-      ctx->t_sub_sum_off[r] = (uint32_t)ctx->t_sub_sums.size();
-      if (dc.track_sums) ctx->t_sub_sums.insert(ctx->t_sub_sums.end(), sums_arena.begin() + soff[r], sums_arena.begin() + soff[r] + nsum[r]);
     }
     ctx->t_sub_key_off[ns] = (uint32_t)ctx->t_sub_key.size();
-    ctx->t_sub_sum_off[ns] = (uint32_t)ctx->t_sub_sums.size();
+    if (!dc.track_sums) ctx->t_sub_sum_off.assign(ns + 1, 0);
     // cluster readCount[src] = sum over its sub-clusters (CigarCluster.merge :679-682)
     ctx->t_cl_read_count.assign((size_t)nc * S, 0);
     for (int c = 0; c < nc; c++)
       for (int k = cl_sub_off[c]; k < cl_sub_off[c + 1]; k++)
         for (int s = 0; s < S; s++) ctx->t_cl_read_count[(size_t)c * S + s] += ctx->t_sub_count[(size_t)k * S + s];
-    // break-point pairs sorted by (src, level, start, end)
-    std::vector<int> order((size_t)ctx->n_pairs);
-    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-      for (int j = 0; j < 4; j++) if (pr[(size_t)a * 5 + j] != pr[(size_t)b * 5 + j]) return pr[(size_t)a * 5 + j] < pr[(size_t)b * 5 + j];
-      return false;
-    });
-    for (int j = 0; j < 5; j++) { ctx->t_pair[j].resize(order.size()); for (size_t i = 0; i < order.size(); i++) ctx->t_pair[j][i] = pr[(size_t)order[i] * 5 + j]; }
+    // break-point pairs: sorted by key = (src, level, start, end) on the device
+    for (int j = 0; j < 4; j++) ctx->t_pair[j].resize(np);
+    for (size_t i = 0; i < np; i++) {
+      const unsigned long long k = pkeys[i];
+      ctx->t_pair[0][i] = (int)((k >> 59) & 0xF); ctx->t_pair[1][i] = (int)((k >> 58) & 1);
+      ctx->t_pair[2][i] = (int)((k >> 29) & 0x1FFFFFFF); ctx->t_pair[3][i] = (int)(k & 0x1FFFFFFF);
+    }
     R.cl_first_read = ctx->t_cl_first.data(); R.cl_key_off = ctx->t_cl_key_off.data(); R.cl_key_tok = ctx->t_cl_key_tok.data();
     R.cl_read_count = ctx->t_cl_read_count.data(); R.cl_sub_off = ctx->t_cl_sub_off.data();
     R.sub_first_read = ctx->t_sub_first.data(); R.sub_key_off = ctx->t_sub_key_off.data(); R.sub_key = ctx->t_sub_key.data();
@@ -1092,6 +1165,78 @@ int npt_device_view_get(npt_ctx* ctx, npt_device_view* out) {
   out->coverage_elems = ctx->dc.record_depth ? 4ll * ctx->cov_rows * ctx->dc.S * ctx->dc.stride : 0;
   out->small_counts = ctx->d_small.p;
   out->small_elems = (int64_t)ctx->dc.S * (1 + 2 * ctx->dc.n_orf);
+  out->n_subs = ctx->n_subs;
+  out->n_pairs = (int32_t)ctx->n_pairs;
+  out->sub_count = ctx->n_subs ? ctx->d_ex_i[0].p : nullptr;
+  out->sub_count_elems = (int64_t)ctx->n_subs * ctx->dc.S;
+  out->sub_break_sum = ctx->n_subs ? ctx->d_ex_i[1].p : nullptr;
+  out->sub_break_sum_elems = ctx->n_subs;
+  out->sub_sums = ctx->total_sums ? ctx->d_fin_sums.p : nullptr;
+  out->sub_sums_elems = ctx->total_sums;
+  out->pair_count = ctx->n_pairs ? ctx->d_pair_cnt2.p : nullptr;
+  out->pair_count_elems = ctx->n_pairs;
+  return NPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-rank key exchange
+int npt_export_keys(npt_ctx* ctx, const int32_t** dev_buf, int64_t* n_words) {
+  if (!ctx || !dev_buf || !n_words) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_export_keys belongs between the last npt_submit and npt_end_chrom");
+  int rc = npt_wait(ctx);
+  if (rc) return rc;
+  const DevCfg& dc = ctx->dc;
+  unsigned hc[CN_COUNT];
+  CK(cudaMemcpy(hc, ctx->d_counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+  const int cl_n = (int)std::min<unsigned>(hc[CN_CLUSTERS], (unsigned)dc.cl_cap), sb_n = (int)std::min<unsigned>(hc[CN_SUBS], (unsigned)dc.sb_cap);
+  const int pr_n = dc.calc_breaks1 ? (int)std::min<unsigned>(hc[CN_PAIRS], (unsigned)dc.pr_cap) : 0;
+  const long long clw = std::min<unsigned>(hc[CN_TOK_USED], dc.tok_cap), sbw = std::min<unsigned>(hc[CN_SUBKEY_USED], dc.sbkey_cap);
+  int hdr[KX_HDR] = {0};
+  long long o = KX_HDR;
+  hdr[0] = KX_MAGIC; hdr[1] = cl_n; hdr[2] = (int)clw; hdr[3] = sb_n; hdr[4] = (int)sbw; hdr[5] = pr_n; hdr[6] = (int)(dc.cl_mask + 1); hdr[7] = dc.S;
+  hdr[8] = (int)o; o += 4ll * cl_n;
+  hdr[9] = (int)o; o += clw;
+  hdr[10] = (int)o; o += 6ll * sb_n;
+  hdr[11] = (int)o; o += sbw;
+  hdr[12] = (int)o; o += 2ll * pr_n;
+  if (o >= (1ll << 31)) return fail(ctx, NPT_ECAPACITY, "key exchange buffer too large");
+  CK(ctx->d_kx.ensure((size_t)o));
+  CK(ctx->d_kx_ctr.ensure(4));
+  CK(cudaMemsetAsync(ctx->d_kx_ctr.p, 0, 16, ctx->s_comp));
+  CK(cudaMemcpyAsync(ctx->d_kx.p, hdr, sizeof hdr, cudaMemcpyHostToDevice, ctx->s_comp));
+  const int g = ctx->sm_count * 2;
+  if (cl_n) kx_list_clusters_kernel<<<g, 256, 0, ctx->s_comp>>>(dc.cl, dc.cl_mask + 1, ctx->d_kx.p + hdr[8], ctx->d_kx_ctr.p, cl_n);
+  if (clw) CK(cudaMemcpyAsync(ctx->d_kx.p + hdr[9], dc.cl_rec, (size_t)clw * 4, cudaMemcpyDeviceToDevice, ctx->s_comp));
+  if (sb_n) kx_list_subs_kernel<<<g, 256, 0, ctx->s_comp>>>(dc.sb, dc.sb_mask + 1, dc.fit ? dc.sub_min0 : nullptr, ctx->d_kx.p + hdr[10], ctx->d_kx_ctr.p + 1, sb_n);
+  if (sbw) CK(cudaMemcpyAsync(ctx->d_kx.p + hdr[11], dc.sb_rec, (size_t)sbw * 4, cudaMemcpyDeviceToDevice, ctx->s_comp));
+  if (pr_n) kx_list_pairs_kernel<<<g, 256, 0, ctx->s_comp>>>(dc.pr, dc.pr_mask + 1, ctx->d_kx.p + hdr[12], ctx->d_kx_ctr.p + 2, pr_n);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  ctx->total_launches += 3;
+  *dev_buf = ctx->d_kx.p;
+  *n_words = o;
+  return NPT_OK;
+}
+
+int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words) {
+  if (!ctx || !dev_buf) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_import_keys belongs between the last npt_submit and npt_end_chrom");
+  if (n_words < KX_HDR) return fail(ctx, NPT_EINVAL, "key buffer too short");
+  CK(cudaSetDevice(ctx->device));
+  const DevCfg& dc = ctx->dc;
+  int hdr[KX_HDR];
+  CK(cudaMemcpy(hdr, dev_buf, sizeof hdr, cudaMemcpyDeviceToHost));
+  if (hdr[0] != KX_MAGIC || hdr[7] != dc.S) return fail(ctx, NPT_EINVAL, "not a key buffer of a context with the same configuration");
+  const long long end = (long long)hdr[12] + 2ll * hdr[5];
+  if (hdr[1] < 0 || hdr[3] < 0 || hdr[5] < 0 || hdr[6] < 1 || end > n_words) return fail(ctx, NPT_EINVAL, "inconsistent key buffer header");
+  CK(ctx->d_kx_slotmap.ensure((size_t)hdr[6]));
+  CK(cudaMemsetAsync(ctx->d_kx_slotmap.p, 0xFF, (size_t)hdr[6] * 4, ctx->s_comp));
+  const int g = ctx->sm_count * 2;
+  if (hdr[1]) import_clusters_kernel<<<g, 128, 0, ctx->s_comp>>>(dc, dev_buf + hdr[8], hdr[1], dev_buf + hdr[9], ctx->d_kx_slotmap.p);
+  if (hdr[3]) import_subs_kernel<<<g, 128, 0, ctx->s_comp>>>(dc, dev_buf + hdr[10], hdr[3], dev_buf + hdr[11], ctx->d_kx_slotmap.p);
+  if (hdr[5] && dc.calc_breaks1) import_pairs_kernel<<<g, 128, 0, ctx->s_comp>>>(dc, dev_buf + hdr[12], hdr[5]);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->s_comp));
+  ctx->total_launches += 3;
   return NPT_OK;
 }
 

@@ -192,6 +192,15 @@ class Engine:
         self._ck(self.L.npt_device_view_get(self.h, C.byref(v)))
         return v
 
+    def export_keys(self):
+        """(device pointer, int32 words) of this rank's packed key buffer; valid until the next export or npt_destroy."""
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.L.npt_export_keys(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def import_keys(self, dev_ptr, n_words):
+        self._ck(self.L.npt_import_keys(self.h, dev_ptr, n_words))
+
     def remap_clusters(self, global_id, n_global):
         g = np.ascontiguousarray(global_id, dtype=np.int32)
         self._ck(self.L.npt_remap_clusters(self.h, g.ctypes.data, n_global))

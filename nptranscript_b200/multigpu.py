@@ -1,16 +1,15 @@
 """Multi-GPU: reads shard across ranks (contiguous ranges of the global submit order); there is no data-path collective
-while reads are walked.  At end of chromosome the per-shard tables merge by key:
+while reads are walked.  At end of chromosome the per-shard tables merge by key.
 
-  1. all-gather of the small per-rank tables {cluster key tokens, first global read index, counts} and
-     {cluster key, binned breaks, first index, counts, break sums}                       (torch.distributed, object gather)
-  2. every rank merges them deterministically: global cluster id = rank of min first index over ranks
-     (CigarClusters.java:83), global sub id = rank inside the cluster (CigarCluster.java:660), counts and sums add
-  3. each rank permutes its dense coverage rows into global cluster order on the device (npt_remap_clusters) and the
-     rows are summed with one all-reduce (NCCL over NVLink on GPUs; gloo in the CPU tests); ORF counters likewise
-  4. per-read ids never leave their rank: local ids are rewritten through the local→global maps.
+Device path (exchange_keys / reduce_aggregates, NCCL): every rank exports the KEYS of its cluster, sub-cluster and
+break-point-pair tables with their first-appearance indices as one packed device buffer (npt_export_keys); one all-gather;
+every rank inserts the other ranks' keys into its own tables (npt_import_keys).  All ranks then hold the same key set with
+the same minima, so npt_end_chrom numbers clusters (CigarClusters.java:83) and sub-clusters (CigarCluster.java:660)
+identically everywhere, per-read ids come out global, and the counters — coverage rows, ORF counters, sub-cluster counts,
+break sums, pair counts, now in the same order on every rank — are summed in place with all-reduces.
 
-The merge works on plain result dicts with vectorised numpy (tables of 1e4-1e6 sub-clusters merge in milliseconds), so
-the CPU tests drive it with oracle output under gloo.
+Host path (merge_tables, also through libnpt's npt_merge_tables): the same merge on plain result dicts with vectorised
+numpy; the CPU tests drive it with oracle output under gloo, and it is the independent check of the device path.
 """
 import time
 
@@ -223,12 +222,50 @@ def permute_rows(rows, cmap, n_global):
 class _DevPtr:
     """Expose a raw device pointer to torch (zero-copy) through __cuda_array_interface__."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def merge_across_ranks(eng, rank, world, timing=False):
-    """GPU path: merge the tables, permute + all-reduce the coverage rows and small counters in place on the device.
+def exchange_keys(eng, rank, world):
+    """Step 1 of the device-side protocol (after the last submit, before end_chrom): every rank's table keys reach every
+    other rank over NCCL and are inserted into its tables.  Returns ms."""
+    import torch
+    import torch.distributed as dist
+    t0 = time.perf_counter()
+    ptr, n = eng.export_keys()
+    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
+    sizes[rank] = n
+    dist.all_reduce(sizes)
+    sizes = sizes.cpu().tolist()
+    m = int(max(sizes))
+    mine = torch.zeros(m, dtype=torch.int32, device="cuda")
+    mine[:n] = torch.as_tensor(_DevPtr(ptr, n, "<i4"), device="cuda")
+    allbuf = torch.empty(world * m, dtype=torch.int32, device="cuda")
+    dist.all_gather_into_tensor(allbuf, mine)
+    torch.cuda.synchronize()
+    for r in range(world):
+        if r != rank:
+            eng.import_keys(allbuf[r * m:].data_ptr(), int(sizes[r]))
+    return 1e3 * (time.perf_counter() - t0)
+
+
+def reduce_aggregates(eng):
+    """Step 2 (after end_chrom): sum the counters, which are now in the same global order on every rank.  Returns ms."""
+    import torch
+    import torch.distributed as dist
+    t0 = time.perf_counter()
+    v = eng.device_view()
+    for ptr, n, dt in ((v.coverage, v.coverage_elems, "<i4"), (v.small_counts, v.small_elems, "<i4"), (v.sub_count, v.sub_count_elems, "<i4"),
+                       (v.sub_break_sum, v.sub_break_sum_elems, "<i4"), (v.sub_sums, v.sub_sums_elems, "<i8"), (v.pair_count, v.pair_count_elems, "<i4")):
+        if ptr and n:
+            dist.all_reduce(torch.as_tensor(_DevPtr(ptr, n, dt), device="cuda"))
+    torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0)
+
+
+def merge_across_ranks_host(eng, rank, world, timing=False):
+    """Older GPU path, kept for comparison (call after end_chrom): tables fetched and merged on the host, coverage rows permuted on
+    the device and all-reduced.  0.18 s per step at 10 M reads per rank (sorting and hashing ~0.5 M break-point pairs on the host).
     Returns the merge time in ms (timing=True) or (global tables, (cluster_map, sub_map), local cl_sub_off)."""
     import torch
     import torch.distributed as dist
@@ -254,5 +291,5 @@ def merge_across_ranks(eng, rank, world, timing=False):
     torch.cuda.synchronize()
     t4 = time.perf_counter()
     ms = 1e3 * (t4 - t0)
-    merge_across_ranks.last = dict(fetch_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), merge_ms=1e3 * (t3 - t2), device_ms=1e3 * (t4 - t3))
+    merge_across_ranks_host.last = dict(fetch_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), merge_ms=1e3 * (t3 - t2), device_ms=1e3 * (t4 - t3))
     return ms if timing else (glob, (cmap, smap), res["cl_sub_off"])

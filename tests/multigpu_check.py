@@ -1,5 +1,5 @@
-"""Run under torchrun on N GPUs: every rank walks its shard on its GPU, tables merge by key, coverage rows are permuted on
-the device and summed with an NCCL all-reduce; rank 0 checks ids, tables and coverage against the oracle on the
+"""Run under torchrun on N GPUs: every rank walks its shard on its GPU, table keys are exchanged over NCCL and inserted on
+the device, counters are summed with NCCL all-reduces; rank 0 checks ids, tables and coverage against the oracle on the
 unsharded input.   torchrun --nproc-per-node 2 tests/multigpu_check.py"""
 import os
 import sys
@@ -26,13 +26,13 @@ eng = engine.Engine(engine.make_config(device=local, **KW))
 eng.set_read_index_base(rank * per)
 eng.begin_chrom(0, g, w.annotation)
 eng.submit(b)
+multigpu.exchange_keys(eng, rank, world)
 eng.end_chrom()
-glob, (cmap, smap), cl_sub_off = multigpu.merge_across_ranks(eng, rank, world)
-res = eng.fetch(abi.NPT_FETCH_READS)
-cl, sb = multigpu.remap_reads(res, cmap, smap, cl_sub_off)
-v = eng.device_view()
-cov = torch.as_tensor(multigpu._DevPtr(v.coverage, v.coverage_elems), device="cuda").cpu().numpy().reshape(4, glob["n_clusters"], 2, v.cov_stride)
-small = torch.as_tensor(multigpu._DevPtr(v.small_counts, v.small_elems), device="cuda").cpu().numpy()
+multigpu.reduce_aggregates(eng)
+glob = eng.fetch(abi.NPT_FETCH_ALL)   # global tables and coverage on every rank; per-read ids are global ids of the local reads
+cl, sb = glob["cluster_id"], glob["sub_id"]
+cov = np.stack([glob[k] for k in ("depth", "errors", "map_start", "map_end")])
+small = np.concatenate([glob["total_counts"].ravel(), glob["spliced"].ravel(), glob["unspliced"].ravel()])
 ids = [None] * world
 dist.all_gather_object(ids, (cl, sb))
 if rank == 0:
@@ -41,8 +41,8 @@ if rank == 0:
     ref = oracle.run(oracle.make_config(**KW), g, w.annotation, [full])
     assert np.array_equal(np.concatenate([i[0] for i in ids]), ref["cluster_id"])
     assert np.array_equal(np.concatenate([i[1] for i in ids]), ref["sub_id"])
-    for k in ("cl_first_read", "cl_key_tok", "cl_read_count", "cl_sub_off", "sub_first_read", "sub_key", "sub_count", "sub_break_sum", "sub_sums",
-              "sub_flags", "pair_start", "pair_end", "pair_count"):
+    for k in ("cl_first_read", "cl_key_off", "cl_key_tok", "cl_read_count", "cl_sub_off", "sub_first_read", "sub_key_off", "sub_key", "sub_count",
+              "sub_break_sum", "sub_sum_off", "sub_sums", "sub_flags", "pair_src", "pair_level", "pair_start", "pair_end", "pair_count"):
         assert np.array_equal(glob[k], ref[k]), k
     for i, k in enumerate(("depth", "errors", "map_start", "map_end")):
         assert np.array_equal(cov[i], ref[k]), k
