@@ -133,6 +133,8 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = workloads.SARS2
     g = synth.genome_codes(w)
@@ -260,7 +262,12 @@ def run_ours(args, rank, world, local_rank):
         eng.begin_chrom(0, g, w.annotation)
         for b in host_chunks:
             eng.submit(b)
+        if world > 1:
+            from nptranscript_b200 import multigpu
+            multigpu.exchange_keys(eng, rank, world)
         eng.end_chrom()
+        if world > 1:
+            multigpu.reduce_aggregates(eng)
         r = eng.fetch_raw(abi.NPT_FETCH_ALL)
         nb = int(np.ctypeslib.as_array(r.break_off, shape=(e2e_reads + 1,))[-1])
         d2h = e2e_reads * (9 * 4 + 8) + nb * 4 + 4 * r.n_clusters * cfg.num_sources * r.cov_stride * 4

@@ -109,7 +109,10 @@ class OracleRun:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def results(self, coverage=True):
         L, h, S = lib(), self.h, self.S
