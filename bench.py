@@ -133,8 +133,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL logs its banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = workloads.SARS2
     g = synth.genome_codes(w)
