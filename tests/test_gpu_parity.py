@@ -136,3 +136,65 @@ def test_many_breaks_overflow_area():
     nb = np.diff(ora["break_off"].astype(np.int64))
     assert (nb > 6).sum() > 1500
     assert_same(dev, ora)
+
+
+EDGE_READS = [
+    (5, 0, 0, "10S65M28190N1600M30S", None),          # KAT1 shape
+    (1, 0, 0, "1M", None),                             # shortest possible alignment
+    (100, 16, 0, "20S", None),                         # no reference-consuming op at all
+    (100, 0, 0, "5I", None),
+    (100, 0, 0, "3H2P4S", None),
+    (29890, 0, 0, "10M", None),                        # runs past the end of the reference
+    (29893, 0, 0, "1M5D3M", None),
+    (200, 0, 0, "0M5M0D0N7M", None),                   # zero-length elements
+    (300, 0, 0, "4M268435455N4M", None),               # the longest CIGAR element BAM can hold
+    (400, 0, 0, "50M1200D50M", None),                  # a deletion longer than the break threshold
+    (500, 0, 0, "33M1I31M2D65M1X3=40M", None),         # step boundaries at 32/33 bases
+    (600, 16, 0, "5M3N5M3N5M3N5M3N5M3N5M3N5M3N5M", None),
+]
+
+
+def _edge_batch(g):
+    lut = np.full(16, ord("N"), np.uint8)
+    lut[[1, 2, 4, 8]] = [ord(ch) for ch in "ACGT"]
+    gs = lut[g].tobytes().decode()
+    import re
+    reads = []
+    for pos, flag, src, cig, _ in EDGE_READS:
+        ref, bases = pos - 1, []
+        for ln, op in re.findall(r"(\d+)([MIDNSHP=X])", cig):
+            ln = int(ln)
+            if op in "M=X":
+                seg = "".join(gs[i] if 0 <= i < len(gs) else "A" for i in range(ref, min(ref + ln, ref + 4096)))
+                bases.append(seg if op != "X" else "".join("ACGT"[("ACGT".index(c) + 1) % 4] if c in "ACGT" else "A" for c in seg))
+                ref += ln
+            elif op in "IS":
+                bases.append("C" * ln)
+            elif op in "DN":
+                ref += ln
+        reads.append((pos, flag, src, cig, "".join(bases)))
+    return synth.from_reads(reads)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(bin=10, break_thresh=1000, record_depth=1),
+    dict(bin=10, break_thresh=2, record_depth=1),
+    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=1),
+])
+def test_edge_case_reads(kw):
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    b = _edge_batch(g)
+    ann = w.annotation if kw.get("coronavirus", 1) else workloads.Annotation.empty()
+    dev, ora = _both(dict(kw, max_coverage_clusters=64), w, [b, b.slice(0, 0), b.slice(3, 4), b], annotation=ann)
+    assert_same(dev, ora)
+
+
+def test_no_reads_at_all():
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    empty = synth.generate(w, 1, 4).slice(0, 0)
+    for batches in ([], [empty]):
+        dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1), w, batches)
+        assert dev["n_reads"] == 0 and dev["n_clusters"] == 0 and dev["n_subs"] == 0 and dev["n_pairs"] == 0
+        assert_same(dev, ora)

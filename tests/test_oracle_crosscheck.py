@@ -142,3 +142,14 @@ def test_java_hashset_order_known_cases():
     # 13 entries exceed 0.75 * 16: the table doubles, 'q' (113 & 31 = 17) now sorts before 'a' (97 & 31 = 1)?  no: 1 < 17
     thirteen = [chr(97 + i) for i in range(12)] + ["q"]
     assert py_oracle.java_hashset_order(thirteen) == sorted(thirteen, key=lambda s: ord(s) & 31)
+
+
+def test_edge_case_reads():
+    """Shortest alignment, reads without reference-consuming ops, clips/pads only, alignment past the reference end,
+    zero-length and maximum-length elements, deletion longer than the threshold, 32/33-base step boundaries, many junctions."""
+    from tests.test_gpu_parity import _edge_batch
+    w = workloads.SARS2
+    b = _edge_batch(synth.genome_codes(w))
+    for kw in (dict(bin=10, break_thresh=1000, record_depth=1), dict(bin=10, break_thresh=2, record_depth=1)):
+        _compare(kw, w.annotation, [b, b.slice(3, 4), b])
+    _compare(dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=1), workloads.Annotation.empty(), [b])
