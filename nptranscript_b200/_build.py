@@ -9,6 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBNPT = os.path.join(CSRC, "libnpt.so")
 LIBSYNTH = os.path.join(HERE, "synth", "libnptsynth.so")
+LIBBAM = os.path.join(HERE, "bam", "libnptbam.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
@@ -62,5 +63,18 @@ def build_synth(force=False):
     return LIBSYNTH
 
 
+def build_bam(force=False):
+    """BAM (BGZF) -> SoA packer: host C++ + zlib, no CUDA."""
+    src = os.path.join(HERE, "bam", "bam_pack.cpp")
+    if not force and not _stale(LIBBAM, [src, os.path.join(ROOT, "include", "npt_bam.h")]):
+        return LIBBAM
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-pthread", "-shared", "-Wall", "-Wextra", "-o", LIBBAM, src, "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return LIBBAM
+
+
 def build_all(force=False):
-    return build_libnpt(force), build_synth(force)
+    return build_libnpt(force), build_synth(force), build_bam(force)

@@ -1,0 +1,317 @@
+// BAM (BGZF) -> structure-of-arrays packer: see include/npt_bam.h for the reference lines this replaces.
+//
+// Layout of the work: the file is memory-mapped; BGZF block headers are scanned sequentially (18 bytes each), a window of
+// blocks is inflated in parallel (one zlib raw-inflate stream per thread, each block straight into its place of one
+// contiguous buffer: the ISIZE trailers give the offsets), and records are parsed from that buffer in file order.  A BAM
+// record already holds CIGAR as (len<<4)|op words and SEQ as 4-bit codes, so every field is one memcpy.
+#include <zlib.h>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/npt_bam.h"
+
+namespace {
+
+constexpr size_t WINDOW_BLOCKS = 4096;  // BGZF blocks inflated per refill (<= 256 MB of BAM bytes)
+
+inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+template <typename T>
+struct Buf {  // grow-only array from the caller's allocator
+  T* p = nullptr;
+  size_t cap = 0;
+  void* (*alloc)(size_t) = nullptr;
+  void (*free_)(void*) = nullptr;
+  bool reserve(size_t n, size_t keep) {
+    if (n <= cap) return true;
+    size_t nc = std::max<size_t>(n, cap + cap / 2 + 1024);
+    T* q = (T*)alloc(nc * sizeof(T));
+    if (!q) return false;
+    if (keep) memcpy(q, p, keep * sizeof(T));
+    if (p) free_(p);
+    p = q; cap = nc;
+    return true;
+  }
+  void release() { if (p) free_(p); p = nullptr; cap = 0; }
+};
+
+struct BlockRef { size_t coff; uint32_t csize, usize; size_t uoff; };
+
+}  // namespace
+
+struct nptb_reader {
+  int fd = -1;
+  const uint8_t* map = nullptr;
+  size_t fsize = 0, cpos = 0;
+  std::vector<uint8_t> ubuf;
+  size_t upos = 0, uend = 0;
+  bool ceof = false;
+  int nthreads = 1;
+  std::vector<std::string> ref_names;
+  std::vector<int64_t> ref_lens;
+  std::string err;
+  // batch buffers
+  Buf<int32_t> pos; Buf<uint16_t> flag, src; Buf<uint32_t> cigar_off, cigar, name_off; Buf<uint64_t> seq_off; Buf<uint8_t> seq4, mapq;
+  Buf<double> q1; Buf<char> names;
+  // totals
+  int64_t n_records = 0, n_unmapped = 0, n_excluded_ref = 0, n_low_quality = 0, n_short = 0, n_low_mapq = 0, n_secondary = 0;
+  int64_t num_reads = 0;  // "numReads" of the reference's loop
+  double err_prob[256];   // pow(10, -q/10) for every byte value: the same calls the per-base loop would make, made once
+  bool stopped = false;
+};
+
+namespace {
+
+int fail(nptb_reader* r, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  r->err = buf;
+  return -1;
+}
+
+// Inflate the next window of BGZF blocks behind the unread bytes.  Returns 0 ok (possibly nothing added at EOF), -1 error.
+int refill(nptb_reader* r) {
+  if (r->upos > 0) {  // keep the unread tail at the front
+    const size_t left = r->uend - r->upos;
+    if (left) memmove(r->ubuf.data(), r->ubuf.data() + r->upos, left);
+    r->upos = 0; r->uend = left;
+  }
+  std::vector<BlockRef> blocks;
+  size_t uoff = r->uend;
+  while (blocks.size() < WINDOW_BLOCKS && r->cpos < r->fsize) {
+    const uint8_t* h = r->map + r->cpos;
+    if (r->fsize - r->cpos < 28) return fail(r, "truncated BGZF block header at offset %zu", r->cpos);
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return fail(r, "not a BGZF block at offset %zu", r->cpos);
+    const unsigned xlen = le16(h + 10);
+    if (r->fsize - r->cpos < 12 + (size_t)xlen + 8) return fail(r, "truncated BGZF extra field at offset %zu", r->cpos);
+    int bsize = -1;
+    for (unsigned o = 0; o + 4 <= xlen;) {
+      const uint8_t* x = h + 12 + o;
+      const unsigned slen = le16(x + 2);
+      if (x[0] == 'B' && x[1] == 'C' && slen == 2 && o + 6 <= xlen) bsize = le16(x + 4);
+      o += 4 + slen;
+    }
+    if (bsize < 0) return fail(r, "gzip member without a BGZF BC field at offset %zu", r->cpos);
+    const size_t total = (size_t)bsize + 1;
+    if (total < 12 + (size_t)xlen + 8 || r->fsize - r->cpos < total) return fail(r, "truncated BGZF block at offset %zu", r->cpos);
+    const uint32_t isize = le32(h + total - 4);
+    if (isize > 65536) return fail(r, "BGZF block larger than 64 KiB at offset %zu", r->cpos);
+    blocks.push_back({r->cpos + 12 + xlen, (uint32_t)(total - 12 - xlen - 8), isize, uoff});
+    uoff += isize;
+    r->cpos += total;
+  }
+  if (r->cpos >= r->fsize) r->ceof = true;
+  if (blocks.empty()) return 0;
+  r->ubuf.resize(uoff);
+  std::atomic<size_t> next{0};
+  std::atomic<int> bad{0};
+  auto work = [&]() {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= blocks.size() || bad.load()) break;
+      const BlockRef& b = blocks[i];
+      if (b.usize == 0) continue;  // the empty EOF marker block
+      zs.next_in = const_cast<Bytef*>(r->map + b.coff); zs.avail_in = b.csize;
+      zs.next_out = r->ubuf.data() + b.uoff; zs.avail_out = b.usize;
+      const int rc = inflate(&zs, Z_FINISH);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; break; }
+      const uint32_t crc = le32(r->map + b.coff + b.csize);
+      if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), r->ubuf.data() + b.uoff, b.usize) != crc) { bad = 2; break; }
+      inflateReset(&zs);
+    }
+    inflateEnd(&zs);
+  };
+  const int nt = (int)std::min<size_t>((size_t)r->nthreads, blocks.size());
+  std::vector<std::thread> th;
+  for (int t = 1; t < nt; t++) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (bad.load()) return fail(r, bad.load() == 2 ? "BGZF block fails its CRC32" : "corrupt deflate data in a BGZF block");
+  r->uend = uoff;
+  return 0;
+}
+
+// n contiguous unread bytes, or nullptr at end of file (*short_read set if some but fewer than n bytes remain)
+const uint8_t* peek(nptb_reader* r, size_t n, bool* short_read, int* rc) {
+  *short_read = false; *rc = 0;
+  while (r->uend - r->upos < n) {
+    if (r->ceof) { *short_read = r->uend > r->upos; return nullptr; }
+    if (refill(r) < 0) { *rc = -1; return nullptr; }
+  }
+  return r->ubuf.data() + r->upos;
+}
+
+int read_header(nptb_reader* r) {
+  bool sh; int rc;
+  const uint8_t* p = peek(r, 12, &sh, &rc);
+  if (!p) return rc ? rc : fail(r, "file too short for a BAM header");
+  if (memcmp(p, "BAM\1", 4) != 0) return fail(r, "not a BAM file (magic)");
+  const uint32_t l_text = le32(p + 4);
+  p = peek(r, 12 + (size_t)l_text, &sh, &rc);
+  if (!p) return rc ? rc : fail(r, "truncated BAM header text");
+  const uint32_t n_ref = le32(p + 8 + l_text);
+  r->upos += 12 + (size_t)l_text;
+  for (uint32_t i = 0; i < n_ref; i++) {
+    p = peek(r, 4, &sh, &rc);
+    if (!p) return rc ? rc : fail(r, "truncated BAM reference list");
+    const uint32_t l_name = le32(p);
+    p = peek(r, 8 + (size_t)l_name, &sh, &rc);
+    if (!p) return rc ? rc : fail(r, "truncated BAM reference list");
+    r->ref_names.emplace_back((const char*)p + 4, l_name ? l_name - 1 : 0);
+    r->ref_lens.push_back(le32(p + 4 + l_name));
+    r->upos += 8 + (size_t)l_name;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+nptb_reader* nptb_open(const char* path, int nthreads, void* (*alloc)(size_t), void (*free_)(void*), char* err, size_t errlen) {
+  auto say = [&](const char* m) { if (err && errlen) snprintf(err, errlen, "%s: %s", path ? path : "(null)", m); };
+  if (!path) { say("null path"); return nullptr; }
+  if ((alloc == nullptr) != (free_ == nullptr)) { say("alloc and free must be given together"); return nullptr; }
+  nptb_reader* r = new nptb_reader();
+  r->fd = open(path, O_RDONLY);
+  struct stat st;
+  if (r->fd < 0 || fstat(r->fd, &st) != 0) { say("cannot open"); if (r->fd >= 0) close(r->fd); delete r; return nullptr; }
+  r->fsize = (size_t)st.st_size;
+  if (r->fsize) {
+    void* m = mmap(nullptr, r->fsize, PROT_READ, MAP_PRIVATE, r->fd, 0);
+    if (m == MAP_FAILED) { say("mmap failed"); close(r->fd); delete r; return nullptr; }
+    r->map = (const uint8_t*)m;
+    madvise(m, r->fsize, MADV_SEQUENTIAL);
+  }
+  r->nthreads = nthreads > 0 ? nthreads : (int)std::max(1u, std::thread::hardware_concurrency());
+  void* (*a)(size_t) = alloc ? alloc : malloc;
+  void (*f)(void*) = free_ ? free_ : free;
+#define INIT(b) r->b.alloc = a; r->b.free_ = f
+  INIT(pos); INIT(flag); INIT(src); INIT(cigar_off); INIT(cigar); INIT(name_off); INIT(seq_off); INIT(seq4); INIT(mapq); INIT(q1); INIT(names);
+#undef INIT
+  for (int v = 0; v < 256; v++) r->err_prob[v] = std::pow(10.0, -(double)(int8_t)(uint8_t)v / 10.0);
+  if (read_header(r) < 0) { say(r->err.c_str()); nptb_close(r); return nullptr; }
+  return r;
+}
+
+void nptb_close(nptb_reader* r) {
+  if (!r) return;
+  r->pos.release(); r->flag.release(); r->src.release(); r->cigar_off.release(); r->cigar.release(); r->name_off.release();
+  r->seq_off.release(); r->seq4.release(); r->mapq.release(); r->q1.release(); r->names.release();
+  if (r->map) munmap((void*)r->map, r->fsize);
+  if (r->fd >= 0) close(r->fd);
+  delete r;
+}
+
+int32_t nptb_n_refs(const nptb_reader* r) { return r ? (int32_t)r->ref_names.size() : 0; }
+const char* nptb_ref_name(const nptb_reader* r, int32_t i) { return (r && i >= 0 && i < (int32_t)r->ref_names.size()) ? r->ref_names[i].c_str() : nullptr; }
+int64_t nptb_ref_len(const nptb_reader* r, int32_t i) { return (r && i >= 0 && i < (int32_t)r->ref_lens.size()) ? r->ref_lens[i] : -1; }
+const char* nptb_last_error(const nptb_reader* r) { return r ? r->err.c_str() : "null reader"; }
+
+int nptb_next_batch(nptb_reader* r, const nptb_filter* f, int32_t src, int64_t max_batch_reads, nptb_batch* out) {
+  if (!r || !f || !out || max_batch_reads < 1) return r ? fail(r, "bad argument") : -1;
+  memset(out, 0, sizeof *out);
+  int64_t n = 0;
+  size_t ncig = 0, nseq = 0, nname = 0;
+  int32_t ref = -2;
+  const int32_t nrefs = (int32_t)r->ref_names.size();
+  if (!r->cigar_off.reserve(1, 0) || !r->seq_off.reserve(1, 0) || !r->name_off.reserve(1, 0)) return fail(r, "out of memory");
+  r->cigar_off.p[0] = 0; r->seq_off.p[0] = 0; r->name_off.p[0] = 0;
+  while (n < max_batch_reads && !r->stopped) {
+    bool sh; int rc;
+    const uint8_t* p = peek(r, 4, &sh, &rc);
+    if (!p) { if (rc) return rc; if (sh) return fail(r, "truncated BAM record"); break; }
+    const uint32_t bs = le32(p);
+    if (bs < 32) return fail(r, "BAM record shorter than its fixed fields");
+    p = peek(r, 4 + (size_t)bs, &sh, &rc);
+    if (!p) return rc ? rc : fail(r, "truncated BAM record");
+    const int32_t refID = (int32_t)le32(p + 4), pos0 = (int32_t)le32(p + 8);
+    const unsigned l_name = p[12], mq = p[13], n_cig = le16(p + 16), flg = le16(p + 18);
+    const uint32_t l_seq = le32(p + 20);
+    const size_t need = 32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+    if (need > bs) return fail(r, "BAM record fields exceed its block_size");
+    const uint8_t* name = p + 36;
+    const uint8_t* cig = name + l_name;
+    const uint8_t* seq = cig + 4 * (size_t)n_cig;
+    const uint8_t* qual = seq + (l_seq + 1) / 2;
+    // ---- the reference's filter chain, in its order.  Decide first, count afterwards: a record that opens the next
+    // chromosome is left unread (and uncounted) for the next call.
+    enum { KEEP, UNMAPPED, EXCLUDED, LOWQ, SHORT, STOP, LOWMAPQ, SECONDARY } what = KEEP;
+    bool counted = false, pre = false;  // counted: reached numReads++ (:804); pre: reached the chromosome switch (:830)
+    double q1 = 500;
+    if (flg & 0x4) what = UNMAPPED;                                                                          // :716
+    else if (f->ref_include && (refID < 0 || refID >= nrefs || !f->ref_include[refID])) what = EXCLUDED;     // :721-730
+    else {
+      if (l_seq > 0 && qual[0] != 0xFF) {                                                                    // :738-752
+        double sump = 0;
+        for (uint32_t i = 0; i < l_seq; i++) sump += r->err_prob[qual[i]];  // Math.pow(10, -b[i]/10.0), b[i] a signed byte
+        sump = sump / (double)l_seq;
+        q1 = -10.0 * std::log10(sump);
+      }
+      if (q1 < f->fail_thresh) what = LOWQ;
+      else if (l_seq <= 1) what = SHORT;                                                                     // :797
+      else {
+        counted = true;                                                                                      // :804-808
+        if (f->max_reads > 0 && r->num_reads + 1 > f->max_reads) what = STOP;
+        else if ((int)mq < f->min_mapq) what = LOWMAPQ;                                                      // :813
+        else { pre = true; if (flg & 0x900) what = SECONDARY; }                                              // :938-959
+      }
+    }
+    if (pre && n > 0 && refID != ref) break;                          // chromosome switch (:830)
+    if (what == KEEP && ncig + n_cig >= (1ull << 32)) break;          // cigar_off is 32-bit in npt_batch: next batch
+    if (pre && n == 0) ref = refID;
+    if (counted) r->num_reads++;
+    if (what == STOP) { r->stopped = true; break; }
+    r->n_records++;
+    r->upos += 4 + (size_t)bs;
+    switch (what) {
+      case UNMAPPED: r->n_unmapped++; break;
+      case EXCLUDED: r->n_excluded_ref++; break;
+      case LOWQ: r->n_low_quality++; break;
+      case SHORT: r->n_short++; break;
+      case LOWMAPQ: r->n_low_mapq++; break;
+      case SECONDARY: r->n_secondary++; break;
+      default: break;
+    }
+    if (what != KEEP) continue;
+    const size_t sb = (l_seq + 1) / 2, nl = l_name ? l_name - 1 : 0;
+    if (!r->pos.reserve(n + 1, n) || !r->flag.reserve(n + 1, n) || !r->src.reserve(n + 1, n) || !r->mapq.reserve(n + 1, n) || !r->q1.reserve(n + 1, n) ||
+        !r->cigar_off.reserve(n + 2, n + 1) || !r->seq_off.reserve(n + 2, n + 1) || !r->name_off.reserve(n + 2, n + 1) ||
+        !r->cigar.reserve(ncig + n_cig, ncig) || !r->seq4.reserve(nseq + sb + 16, nseq) || !r->names.reserve(nname + nl, nname))
+      return fail(r, "out of memory");
+    r->pos.p[n] = pos0 + 1; r->flag.p[n] = (uint16_t)flg; r->src.p[n] = (uint16_t)src; r->mapq.p[n] = (uint8_t)mq; r->q1.p[n] = q1;
+    memcpy(r->cigar.p + ncig, cig, 4 * (size_t)n_cig); ncig += n_cig;
+    memcpy(r->seq4.p + nseq, seq, sb); nseq += sb;
+    memcpy(r->names.p + nname, name, nl); nname += nl;
+    n++;
+    r->cigar_off.p[n] = (uint32_t)ncig; r->seq_off.p[n] = nseq; r->name_off.p[n] = (uint32_t)nname;
+  }
+  out->ref_id = ref == -2 ? -1 : ref;
+  out->n = n;
+  out->pos = r->pos.p; out->flag = r->flag.p; out->src = r->src.p; out->cigar_off = r->cigar_off.p; out->cigar = r->cigar.p;
+  out->seq_off = r->seq_off.p; out->seq4 = r->seq4.p; out->q1 = r->q1.p; out->mapq = r->mapq.p; out->name_off = r->name_off.p; out->names = r->names.p;
+  out->n_records = r->n_records; out->n_unmapped = r->n_unmapped; out->n_excluded_ref = r->n_excluded_ref; out->n_low_quality = r->n_low_quality;
+  out->n_short = r->n_short; out->n_low_mapq = r->n_low_mapq; out->n_secondary = r->n_secondary;
+  out->stopped_at_max_reads = r->stopped ? 1 : 0;
+  return n > 0 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -198,3 +198,35 @@ def test_no_reads_at_all():
         dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1), w, batches)
         assert dev["n_reads"] == 0 and dev["n_clusters"] == 0 and dev["n_subs"] == 0 and dev["n_pairs"] == 0
         assert_same(dev, ora)
+
+
+def test_bam_file_to_results(tmp_path):
+    """The caller's side of the seam: BAM file -> libnptbam (filter chain, pinned SoA batches) -> npt_submit, two source
+    files one after the other (sequential multi-BAM order, src = file index) -> same results as the oracle on the reads."""
+    import os
+    from nptranscript_b200 import bam
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    parts = [synth.generate(w, 31 + k, 4000, num_sources=2, src_fixed=k) for k in range(2)]
+    paths = []
+    for k, b in enumerate(parts):
+        p = os.path.join(str(tmp_path), f"s{k}.bam")
+        bam.write_bam(p, [(w.name, w.genome_len)], bam.records_from_batch(b), block_bytes=20000)
+        paths.append(p)
+    kw = dict(bin=10, break_thresh=1000, record_depth=1, num_sources=2)
+    eng = engine.Engine(engine.make_config(**kw))
+    try:
+        eng.begin_chrom(0, g, w.annotation)
+        for k, p in enumerate(paths):
+            rd = bam.Reader(p, nthreads=2, pinned_from=engine.lib())
+            for ref_id, b, extra in rd.batches(src=k, max_batch_reads=1500, copy=False):
+                assert ref_id == 0
+                eng.submit(b)
+                eng.wait()  # the reader reuses its buffers for the next batch
+            rd.close()
+        eng.end_chrom()
+        dev = eng.fetch()
+    finally:
+        eng.close()
+    ora = oracle.run(oracle.make_config(**kw), g, w.annotation, parts)
+    assert_same(dev, ora)
