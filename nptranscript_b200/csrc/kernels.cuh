@@ -22,6 +22,14 @@
 
 namespace npt {
 
+// coverage updates of the walk; the experiment switch keeps every address computation and loop but issues no RED
+// (profiles/NOTES.md: how much of walk_kernel<1> is the atomics themselves)
+#ifdef NPT_EXPERIMENT_NORED
+#define COV_RED(addr, v) do { int* a__ = (addr); if (a__ == nullptr) atomicAdd(a__, (v)); } while (0)
+#else
+#define COV_RED(addr, v) atomicAdd((addr), (v))
+#endif
+
 constexpr int BRK_INLINE = 6;     // breaks stored in the per-read inline slot
 constexpr int WALK_THREADS = 256;
 constexpr int GRAB = 1;           // reads a lane takes from the cursor at a time
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   // CigarCluster.add for one emitted position (exact, used only near junctions or when T < 8)
   auto add = [&](int p, bool match) {
     const bool break_p = prev < 0 || p - prev > T;
-    if (MODE == 1 && break_p && prev > 0) { atomicAdd(cov + 2 * arr_stride + p, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+    if (MODE == 1 && break_p && prev > 0) { COV_RED(cov + 2 * arr_stride + p, 1); COV_RED(cov + 3 * arr_stride + prev, 1); }
     if (match) {
       if (break_p) {
         if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
@@ -129,8 +137,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   auto depth_run = [&](int base, int n) {
     if (MODE != 1 || n <= 0) return;
     if (pendingEnd != base) {
-      if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
-      atomicAdd(cov + base, 1);
+      if (pendingEnd >= 0) COV_RED(cov + pendingEnd, -1);
+      COV_RED(cov + base, 1);
     }
     pendingEnd = base + n;
   };
@@ -173,12 +181,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
         }
         if (MODE == 1) {
-          if (pendingEnd >= 0) atomicAdd(cov + pendingEnd, -1);
+          if (pendingEnd >= 0) COV_RED(cov + pendingEnd, -1);
           // CigarCluster.setStartEnd :360-365 with the (trimmed) start/end of the read; positions past seqlen+1 only come
           // from alignments that run off the reference and are dropped by the dense rows
           const int sp = b.start_pos[r], ep = b.end_pos[r];
-          if (sp >= 0 && sp < c.stride) atomicAdd(cov + 2 * arr_stride + sp, 1);
-          if (ep >= 0 && ep < c.stride) atomicAdd(cov + 3 * arr_stride + ep, 1);
+          if (sp >= 0 && sp < c.stride) COV_RED(cov + 2 * arr_stride + sp, 1);
+          if (ep >= 0 && ep < c.stride) COV_RED(cov + 3 * arr_stride + ep, 1);
         }
         active = false;
       }
@@ -278,15 +286,15 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
         bool far = false;
         if (nE > 0 && (isEQ || base + nE - 1 - (pmat ? ppos0 : prev) > T)) { sync_prev(); far = prev > 0 && base + nE - 1 - prev > T; }
         if (MODE == 1 && op == 2 && nE == len && len >= 1 && len <= DEL_HIST && pendingEnd == ref0 + 1 && !far) {
-          atomicAdd(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
+          COV_RED(cov + (long long)(3 + len) * arr_stride + ref0 + 1, 1);
           pendingEnd = base;
         } else if (MODE == 1 && nE > 0) {
           depth_run(base, nE);
           if (isDX) {
             if (nE <= 8) { dmask = 0x11111111u & (0xFFFFFFFFu << ((8 - nE) << 2)); dpos = base; }  // flushed after (B)
-            else for (int i = 0; i < nE; i++) atomicAdd(cov + arr_stride + base + i, 1);
+            else for (int i = 0; i < nE; i++) COV_RED(cov + arr_stride + base + i, 1);
             if (far)
-              for (int i = max(0, prev + T + 1 - base); i < nE; i++) { atomicAdd(cov + 2 * arr_stride + base + i, 1); atomicAdd(cov + 3 * arr_stride + prev, 1); }
+              for (int i = max(0, prev + T + 1 - base); i < nE; i++) { COV_RED(cov + 2 * arr_stride + base + i, 1); COV_RED(cov + 3 * arr_stride + prev, 1); }
           }
         }
         if (isEQ && nE > 0) {
@@ -402,8 +410,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (f >= i0) {
             if (MODE == 1 && prev > 0) {
               const int last = min(f, cnt - 1);
-              for (int i = i0; i <= last; i++) atomicAdd(cov + 2 * arr_stride + pos0 + i, 1);
-              atomicAdd(cov + 3 * arr_stride + prev, last - i0 + 1);
+              for (int i = i0; i <= last; i++) COV_RED(cov + 2 * arr_stride + pos0 + i, 1);
+              COV_RED(cov + 3 * arr_stride + prev, last - i0 + 1);
             }
             if (f < cnt) {
               if (prev > 0) { if (MODE == 2 || (MODE == 0 && nb < BRK_INLINE)) bdst[nb] = prev; nb++; }
@@ -425,12 +433,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       while (mis) {
         const int bit = 31 - __clz(mis);
         mis &= ~(1u << bit);
-        atomicAdd(err_row + pos0 + ((bit & 3) << 3) + 7 - (bit >> 2), 1);
+        COV_RED(err_row + pos0 + ((bit & 3) << 3) + 7 - (bit >> 2), 1);
       }
       while (dmask) {
         const int bit = 31 - __clz(dmask);
         dmask &= ~(1u << bit);
-        atomicAdd(err_row + dpos + ((28 - bit) >> 2), 1);
+        COV_RED(err_row + dpos + ((28 - bit) >> 2), 1);
       }
     }
   }
@@ -625,7 +633,10 @@ constexpr int CLUSTER_THREADS = 128;
 
 // One thread per read.  Key tokens are functions of the break list, so they are regenerated on the fly for hashing,
 // comparing and storing instead of being held in registers.
-__global__ void __launch_bounds__(CLUSTER_THREADS) cluster_kernel(const DevCfg c, const BatchDev b) {
+#ifndef NPT_CLUSTER_MIN_BLOCKS
+#define NPT_CLUSTER_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) cluster_kernel(const DevCfg c, const BatchDev b) {
   extern __shared__ __align__(16) int s_int[];
   if (ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
   int* s_ostart = s_int;

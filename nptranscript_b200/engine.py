@@ -1,6 +1,7 @@
 """Thin ctypes wrapper over libnpt.so (include/npt.h).  Product path: fails loudly when the CUDA library is missing,
 cannot be loaded, or finds no sm_100 device — there is no CPU fallback and nothing here touches oracle/."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -18,7 +19,7 @@ class NptError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.build_libnpt()
+        path = os.environ.get("NPT_LIBNPT") or _build.build_libnpt()  # NPT_LIBNPT: an experimental build (profiles/NOTES.md)
         _lib = abi.declare(C.CDLL(path))
         if _lib.npt_abi_version() != abi.NPT_ABI_VERSION:
             raise RuntimeError("libnpt.so ABI version mismatch")
