@@ -29,6 +29,13 @@ namespace npt {
 #else
 #define COV_RED(addr, v) atomicAdd((addr), (v))
 #endif
+// the few updates per read that land on a handful of addresses (run boundaries at the leader / junction / 3' end, read
+// start and end): second experiment switch
+#ifdef NPT_EXPERIMENT_NOHOTRED
+#define COV_RED_HOT(addr, v) do { int* a__ = (addr); if (a__ == nullptr) atomicAdd(a__, (v)); } while (0)
+#else
+#define COV_RED_HOT(addr, v) COV_RED(addr, v)
+#endif
 
 constexpr int BRK_INLINE = 6;     // breaks stored in the per-read inline slot
 constexpr int WALK_THREADS = 256;
@@ -137,8 +144,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   auto depth_run = [&](int base, int n) {
     if (MODE != 1 || n <= 0) return;
     if (pendingEnd != base) {
-      if (pendingEnd >= 0) COV_RED(cov + pendingEnd, -1);
-      COV_RED(cov + base, 1);
+      if (pendingEnd >= 0) COV_RED_HOT(cov + pendingEnd, -1);
+      COV_RED_HOT(cov + base, 1);
     }
     pendingEnd = base + n;
   };
@@ -181,12 +188,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
         }
         if (MODE == 1) {
-          if (pendingEnd >= 0) COV_RED(cov + pendingEnd, -1);
+          if (pendingEnd >= 0) COV_RED_HOT(cov + pendingEnd, -1);
           // CigarCluster.setStartEnd :360-365 with the (trimmed) start/end of the read; positions past seqlen+1 only come
           // from alignments that run off the reference and are dropped by the dense rows
           const int sp = b.start_pos[r], ep = b.end_pos[r];
-          if (sp >= 0 && sp < c.stride) COV_RED(cov + 2 * arr_stride + sp, 1);
-          if (ep >= 0 && ep < c.stride) COV_RED(cov + 3 * arr_stride + ep, 1);
+          if (sp >= 0 && sp < c.stride) COV_RED_HOT(cov + 2 * arr_stride + sp, 1);
+          if (ep >= 0 && ep < c.stride) COV_RED_HOT(cov + 3 * arr_stride + ep, 1);
         }
         active = false;
       }
