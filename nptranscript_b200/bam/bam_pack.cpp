@@ -52,6 +52,22 @@ struct Buf {  // grow-only array from the caller's allocator
 
 struct BlockRef { size_t coff; uint32_t csize, usize; size_t uoff; };
 
+// one scanned record: where it is, and what the history-free part of the filter chain says about it
+enum : uint8_t { KEEP, UNMAPPED, EXCLUDED, LOWQ, SHORT, STOP, LOWMAPQ, SECONDARY, MALFORMED };
+struct RecInfo { size_t off; double q1; int32_t refID; uint32_t n_cig, sb, nl; uint8_t what; bool lowmapq, secondary; };
+
+// fn(lo, hi) over [0, count) on up to nthreads threads (inline when the range is small)
+template <typename F>
+void parallel_for(size_t count, int nthreads, F fn) {
+  const size_t nt = std::min<size_t>((size_t)std::max(1, nthreads), count / 2048 + 1);
+  if (nt <= 1) { if (count) fn(0, count); return; }
+  std::vector<std::thread> th;
+  const size_t per = (count + nt - 1) / nt;
+  for (size_t t = 1; t < nt; t++) th.emplace_back([=]() { fn(std::min(count, t * per), std::min(count, (t + 1) * per)); });
+  fn(0, std::min(count, per));
+  for (auto& x : th) x.join();
+}
+
 }  // namespace
 
 struct nptb_reader {
@@ -68,6 +84,8 @@ struct nptb_reader {
   // batch buffers
   Buf<int32_t> pos; Buf<uint16_t> flag, src; Buf<uint32_t> cigar_off, cigar, name_off; Buf<uint64_t> seq_off; Buf<uint8_t> seq4, mapq;
   Buf<double> q1; Buf<char> names;
+  std::vector<RecInfo> scan;
+  std::vector<uint32_t> kept;
   // totals
   int64_t n_records = 0, n_unmapped = 0, n_excluded_ref = 0, n_low_quality = 0, n_short = 0, n_low_mapq = 0, n_secondary = 0;
   int64_t num_reads = 0;  // "numReads" of the reference's loop
@@ -235,74 +253,129 @@ int nptb_next_batch(nptb_reader* r, const nptb_filter* f, int32_t src, int64_t m
   const int32_t nrefs = (int32_t)r->ref_names.size();
   if (!r->cigar_off.reserve(1, 0) || !r->seq_off.reserve(1, 0) || !r->name_off.reserve(1, 0)) return fail(r, "out of memory");
   r->cigar_off.p[0] = 0; r->seq_off.p[0] = 0; r->name_off.p[0] = 0;
-  while (n < max_batch_reads && !r->stopped) {
+  typedef RecInfo Info;
+  std::vector<Info>& recs = r->scan;
+  std::vector<uint32_t>& kept = r->kept;
+  bool batch_closed = false;
+  while (n < max_batch_reads && !r->stopped && !batch_closed) {
+    // ---- 1. the complete records at hand, in file order (one 4-byte hop each)
     bool sh; int rc;
     const uint8_t* p = peek(r, 4, &sh, &rc);
     if (!p) { if (rc) return rc; if (sh) return fail(r, "truncated BAM record"); break; }
-    const uint32_t bs = le32(p);
-    if (bs < 32) return fail(r, "BAM record shorter than its fixed fields");
-    p = peek(r, 4 + (size_t)bs, &sh, &rc);
-    if (!p) return rc ? rc : fail(r, "truncated BAM record");
-    const int32_t refID = (int32_t)le32(p + 4), pos0 = (int32_t)le32(p + 8);
-    const unsigned l_name = p[12], mq = p[13], n_cig = le16(p + 16), flg = le16(p + 18);
-    const uint32_t l_seq = le32(p + 20);
-    const size_t need = 32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
-    if (need > bs) return fail(r, "BAM record fields exceed its block_size");
-    const uint8_t* name = p + 36;
-    const uint8_t* cig = name + l_name;
-    const uint8_t* seq = cig + 4 * (size_t)n_cig;
-    const uint8_t* qual = seq + (l_seq + 1) / 2;
-    // ---- the reference's filter chain, in its order.  Decide first, count afterwards: a record that opens the next
-    // chromosome is left unread (and uncounted) for the next call.
-    enum { KEEP, UNMAPPED, EXCLUDED, LOWQ, SHORT, STOP, LOWMAPQ, SECONDARY } what = KEEP;
-    bool counted = false, pre = false;  // counted: reached numReads++ (:804); pre: reached the chromosome switch (:830)
-    double q1 = 500;
-    if (flg & 0x4) what = UNMAPPED;                                                                          // :716
-    else if (f->ref_include && (refID < 0 || refID >= nrefs || !f->ref_include[refID])) what = EXCLUDED;     // :721-730
-    else {
-      if (l_seq > 0 && qual[0] != 0xFF) {                                                                    // :738-752
-        double sump = 0;
-        for (uint32_t i = 0; i < l_seq; i++) sump += r->err_prob[qual[i]];  // Math.pow(10, -b[i]/10.0), b[i] a signed byte
-        sump = sump / (double)l_seq;
-        q1 = -10.0 * std::log10(sump);
+    const uint32_t bs0 = le32(p);
+    if (bs0 < 32) return fail(r, "BAM record shorter than its fixed fields");
+    if (!peek(r, 4 + (size_t)bs0, &sh, &rc)) return rc ? rc : fail(r, "truncated BAM record");
+    recs.clear();
+    const size_t want = (size_t)(max_batch_reads - n) + 1024;  // a few more than fit: some will be filtered out
+    for (size_t o = r->upos; recs.size() < want && r->uend - o >= 4;) {
+      const uint32_t bs = le32(r->ubuf.data() + o);
+      if (bs < 32) return fail(r, "BAM record shorter than its fixed fields");
+      if (r->uend - o < 4 + (size_t)bs) break;
+      Info in{}; in.off = o;
+      recs.push_back(in);
+      o += 4 + (size_t)bs;
+    }
+    // ---- 2. per record, in parallel: the part of the filter chain that needs no history, and q1
+    auto classify = [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) {
+        Info& in = recs[i];
+        const uint8_t* q = r->ubuf.data() + in.off;
+        const uint32_t bs = le32(q);
+        in.refID = (int32_t)le32(q + 4);
+        const unsigned l_name = q[12], mq = q[13], n_cig = le16(q + 16), flg = le16(q + 18);
+        const uint32_t l_seq = le32(q + 20);
+        const size_t need = 32 + (size_t)l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+        if (need > bs) { in.what = MALFORMED; continue; }
+        const uint8_t* qual = q + 36 + l_name + 4 * (size_t)n_cig + (l_seq + 1) / 2;
+        in.n_cig = n_cig; in.sb = (l_seq + 1) / 2; in.nl = l_name ? l_name - 1 : 0;
+        in.q1 = 500; in.what = KEEP; in.lowmapq = false; in.secondary = false;
+        if (flg & 0x4) { in.what = UNMAPPED; continue; }                                                             // :716
+        if (f->ref_include && (in.refID < 0 || in.refID >= nrefs || !f->ref_include[in.refID])) { in.what = EXCLUDED; continue; }  // :721-730
+        if (l_seq > 0 && qual[0] != 0xFF) {                                                                          // :738-752
+          double sump = 0;
+          for (uint32_t k = 0; k < l_seq; k++) sump += r->err_prob[qual[k]];  // Math.pow(10, -b[i]/10.0), b[i] a signed byte
+          sump = sump / (double)l_seq;
+          in.q1 = -10.0 * std::log10(sump);
+        }
+        if (in.q1 < f->fail_thresh) { in.what = LOWQ; continue; }
+        if (l_seq <= 1) { in.what = SHORT; continue; }                                                               // :797
+        in.lowmapq = (int)mq < f->min_mapq;                                                                          // :813
+        in.secondary = (flg & 0x900) != 0;                                                                           // :938-959
       }
-      if (q1 < f->fail_thresh) what = LOWQ;
-      else if (l_seq <= 1) what = SHORT;                                                                     // :797
-      else {
-        counted = true;                                                                                      // :804-808
+    };
+    parallel_for(recs.size(), r->nthreads, classify);
+    // ---- 3. in file order: the stateful part (numReads / maxReads, chromosome switch, batch capacity) and output offsets.
+    // A record that opens the next chromosome, or does not fit, is left unread (and uncounted) for the next call.
+    kept.clear();
+    size_t consumed_end = r->upos;
+    const int64_t n0 = n;
+    const size_t ncig0 = ncig, nseq0 = nseq, nname0 = nname;
+    for (size_t i = 0; i < recs.size(); i++) {
+      Info& in = recs[i];
+      if (in.what == MALFORMED) return fail(r, "BAM record fields exceed its block_size");
+      uint8_t what = in.what;
+      bool counted = false, pre = false;
+      if (what == KEEP) {
+        counted = true;                                                                                              // :804-808
         if (f->max_reads > 0 && r->num_reads + 1 > f->max_reads) what = STOP;
-        else if ((int)mq < f->min_mapq) what = LOWMAPQ;                                                      // :813
-        else { pre = true; if (flg & 0x900) what = SECONDARY; }                                              // :938-959
+        else if (in.lowmapq) what = LOWMAPQ;
+        else { pre = true; if (in.secondary) what = SECONDARY; }
       }
+      if (pre && n > 0 && in.refID != ref) { batch_closed = true; break; }            // chromosome switch (:830)
+      if (what == KEEP && (n >= max_batch_reads || ncig + in.n_cig >= (1ull << 32))) { batch_closed = true; break; }
+      if (pre && n == 0) ref = in.refID;
+      if (counted) r->num_reads++;
+      if (what == STOP) { r->stopped = true; break; }
+      r->n_records++;
+      const uint8_t* q = r->ubuf.data() + in.off;
+      consumed_end = in.off + 4 + (size_t)le32(q);
+      switch (what) {
+        case UNMAPPED: r->n_unmapped++; break;
+        case EXCLUDED: r->n_excluded_ref++; break;
+        case LOWQ: r->n_low_quality++; break;
+        case SHORT: r->n_short++; break;
+        case LOWMAPQ: r->n_low_mapq++; break;
+        case SECONDARY: r->n_secondary++; break;
+        default: break;
+      }
+      if (what != KEEP) continue;
+      in.what = KEEP;
+      kept.push_back((uint32_t)i);
+      n++; ncig += in.n_cig; nseq += in.sb; nname += in.nl;
     }
-    if (pre && n > 0 && refID != ref) break;                          // chromosome switch (:830)
-    if (what == KEEP && ncig + n_cig >= (1ull << 32)) break;          // cigar_off is 32-bit in npt_batch: next batch
-    if (pre && n == 0) ref = refID;
-    if (counted) r->num_reads++;
-    if (what == STOP) { r->stopped = true; break; }
-    r->n_records++;
-    r->upos += 4 + (size_t)bs;
-    switch (what) {
-      case UNMAPPED: r->n_unmapped++; break;
-      case EXCLUDED: r->n_excluded_ref++; break;
-      case LOWQ: r->n_low_quality++; break;
-      case SHORT: r->n_short++; break;
-      case LOWMAPQ: r->n_low_mapq++; break;
-      case SECONDARY: r->n_secondary++; break;
-      default: break;
+    // ---- 4. copy the kept records, in parallel (every field is a memcpy)
+    if (!kept.empty()) {
+      if (!r->pos.reserve(n, n0) || !r->flag.reserve(n, n0) || !r->src.reserve(n, n0) || !r->mapq.reserve(n, n0) || !r->q1.reserve(n, n0) ||
+          !r->cigar_off.reserve(n + 1, n0 + 1) || !r->seq_off.reserve(n + 1, n0 + 1) || !r->name_off.reserve(n + 1, n0 + 1) ||
+          !r->cigar.reserve(ncig, ncig0) || !r->seq4.reserve(nseq + 16, nseq0) || !r->names.reserve(nname + 1, nname0))
+        return fail(r, "out of memory");
+      // sequential prefix of the three offset arrays (cheap), then the copies
+      {
+        size_t c = ncig0, s2 = nseq0, m = nname0;
+        for (size_t k = 0; k < kept.size(); k++) {
+          const Info& in = recs[kept[k]];
+          c += in.n_cig; s2 += in.sb; m += in.nl;
+          r->cigar_off.p[n0 + k + 1] = (uint32_t)c; r->seq_off.p[n0 + k + 1] = s2; r->name_off.p[n0 + k + 1] = (uint32_t)m;
+        }
+      }
+      auto copy = [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+          const Info& in = recs[kept[k]];
+          const size_t j = (size_t)n0 + k;
+          const uint8_t* q = r->ubuf.data() + in.off;
+          const unsigned l_name = q[12];
+          const uint8_t* name = q + 36;
+          const uint8_t* cig = name + l_name;
+          const uint8_t* seq = cig + 4 * (size_t)in.n_cig;
+          r->pos.p[j] = (int32_t)le32(q + 8) + 1; r->flag.p[j] = le16(q + 18); r->src.p[j] = (uint16_t)src; r->mapq.p[j] = q[13]; r->q1.p[j] = in.q1;
+          memcpy(r->cigar.p + r->cigar_off.p[j], cig, 4 * (size_t)in.n_cig);
+          memcpy(r->seq4.p + r->seq_off.p[j], seq, in.sb);
+          memcpy(r->names.p + r->name_off.p[j], name, in.nl);
+        }
+      };
+      parallel_for(kept.size(), r->nthreads, copy);
     }
-    if (what != KEEP) continue;
-    const size_t sb = (l_seq + 1) / 2, nl = l_name ? l_name - 1 : 0;
-    if (!r->pos.reserve(n + 1, n) || !r->flag.reserve(n + 1, n) || !r->src.reserve(n + 1, n) || !r->mapq.reserve(n + 1, n) || !r->q1.reserve(n + 1, n) ||
-        !r->cigar_off.reserve(n + 2, n + 1) || !r->seq_off.reserve(n + 2, n + 1) || !r->name_off.reserve(n + 2, n + 1) ||
-        !r->cigar.reserve(ncig + n_cig, ncig) || !r->seq4.reserve(nseq + sb + 16, nseq) || !r->names.reserve(nname + nl, nname))
-      return fail(r, "out of memory");
-    r->pos.p[n] = pos0 + 1; r->flag.p[n] = (uint16_t)flg; r->src.p[n] = (uint16_t)src; r->mapq.p[n] = (uint8_t)mq; r->q1.p[n] = q1;
-    memcpy(r->cigar.p + ncig, cig, 4 * (size_t)n_cig); ncig += n_cig;
-    memcpy(r->seq4.p + nseq, seq, sb); nseq += sb;
-    memcpy(r->names.p + nname, name, nl); nname += nl;
-    n++;
-    r->cigar_off.p[n] = (uint32_t)ncig; r->seq_off.p[n] = nseq; r->name_off.p[n] = (uint32_t)nname;
+    r->upos = consumed_end;
   }
   out->ref_id = ref == -2 ? -1 : ref;
   out->n = n;
