@@ -230,3 +230,29 @@ def test_bam_file_to_results(tmp_path):
         eng.close()
     ora = oracle.run(oracle.make_config(**kw), g, w.annotation, parts)
     assert_same(dev, ora)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_fuzz_more_seeds(seed):
+    """More random CIGARs around the step / tile boundaries of the walk: thresholds near the 32-base step, long reads,
+    many mismatches, weird ops, all with coverage on."""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(seed)
+    T = int(rng.choice([16, 31, 32, 33, 64, 100, 500]))
+    kw = dict(bin=int(rng.choice([1, 10, 100])), break_thresh=T, record_depth=1, include_start=int(rng.integers(0, 2)),
+              enforce_strand=int(rng.integers(0, 2)), num_sources=2, max_coverage_clusters=8192)
+    bs = [random_batch(rng, 1200, w.genome_len, g, num_sources=2, weird=float(rng.choice([0.0, 0.3, 0.8])),
+                       mismatch=float(rng.choice([0.02, 0.1, 0.4])), long_reads=bool(i == 0), max_ops=80) for i in range(2)]
+    dev, ora = _both(kw, w, bs)
+    assert_same(dev, ora)
+
+
+def test_229e_eight_sources():
+    """BASELINE config 3 in small: 229E genome + ORF table, eight source BAMs processed one after the other."""
+    w = workloads.HCOV229E
+    bs = [synth.generate(w, 20200310 + k, 5000, num_sources=8, src_fixed=k) for k in range(8)]
+    kw = dict(bin=10, break_thresh=1000, record_depth=1, num_sources=8, max_coverage_clusters=512)
+    dev, ora = _both(kw, w, bs)
+    assert_same(dev, ora)
+    assert (dev["total_counts"] == 5000).all()
