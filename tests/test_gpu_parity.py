@@ -256,3 +256,28 @@ def test_229e_eight_sources():
     dev, ora = _both(kw, w, bs)
     assert_same(dev, ora)
     assert (dev["total_counts"] == 5000).all()
+
+
+@pytest.mark.parametrize("kw,empty", [
+    (dict(bin=10, break_thresh=1000, record_depth=1, max_coverage_clusters=512), False),
+    (dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1]), True),
+])
+def test_reference_too_large_for_shared_memory(kw, empty):
+    """A 200 kb reference does not fit the walk's shared-memory copy (96 KB packed): the kernels read it through L1/L2."""
+    w = workloads.SARS2
+    rng = np.random.default_rng(8)
+    G = 200_003
+    g = np.array([1, 2, 4, 8], np.uint8)[rng.integers(0, 4, G)]
+    bs = [random_batch(rng, 800, G, g, num_sources=2, big_n=3000, long_reads=(i == 0)) for i in range(2)]
+    ann = workloads.Annotation.empty() if empty else w.annotation
+    dev, ora = _both(dict(kw, num_sources=2), w, bs, annotation=ann, genome=g, chrom_index=1)
+    assert_same(dev, ora)
+
+
+def test_reference_forced_out_of_shared_memory(monkeypatch):
+    """Same kernels, template instance without the shared-memory reference, on the benchmark genome."""
+    monkeypatch.setenv("NPT_REF_SMEM", "0")
+    w = workloads.SARS2
+    b = synth.generate(w, 41, 6000)
+    dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1), w, [b])
+    assert_same(dev, ora)
