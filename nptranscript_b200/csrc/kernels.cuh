@@ -1,21 +1,24 @@
 // kernels.cuh — the hot path as three small kernels, one THREAD per read with lane-level dynamic scheduling.
 //
-//   walk_kernel<0>   CIGAR walk + 4-bit base compare, 8 bases per 32-bit word -> break list, read offsets, error sums
+//   walk_kernel<0>   CIGAR walk + 4-bit base compare, 32 bases per loop step (four 8-base XORs) from lane-private tiles the
+//                    owning lane stages with cp.async -> break list, read offsets, error sums
 //                    (IdentityProfile1.processCigar + CigarCluster.add, J/cluster/IdentityProfile1.java:482-585,
 //                    J/cluster/CigarCluster.java:442-498, incl. the D/=/X "advance, then emit" quirk)
 //   cluster_kernel   break list -> key tokens / break-point pairs / ORF counters / type -> cluster and sub-cluster hash
 //                    tables (IdentityProfile1.processRefPositions :149-356, CigarClusters.matchCluster :75-102,
 //                    CigarCluster.merge :633-698).  Records are written before the CAS that publishes them: no waiting.
-//   walk_kernel<1>   second walk (inputs are L2-resident for long reads, re-streamed otherwise) that sends the read's
-//                    depth runs as difference-array events (+1 at run start, -1 after run end) and its error / mapStart /
-//                    mapEnd points straight to the rows of its cluster with RED.ADD; a segmented scan at end of
-//                    chromosome turns difference rows into depth.
+//   walk_kernel<1>   second walk (the cluster must be known before a position can be credited) that sends the read's
+//                    depth runs as difference-array events (+1 at run start, -1 after run end), its short deletions as one
+//                    histogram point each and its error / mapStart / mapEnd points straight to the rows of its cluster with
+//                    RED.ADD; at end of chromosome the histograms are folded in and a segmented scan turns difference rows
+//                    into depth.  Bound by the L2 atomic rate (126 REDs per read), not by the walk (profiles/NOTES.md).
+//   walk_kernel<2>   store-all pass for the few reads whose break list does not fit the inline slot.
 //
 // Why thread-per-read: the first design of this file was warp-per-read (32 ops per step, warp scans for offsets, ballot
 // compaction, shared-memory event staging).  ncu (profiles/r01a..r01c) showed it instruction- and I-cache-bound at 1 % of
 // the HBM roofline: ~7 000 warp-instructions per read, `no_instruction` the top stall, DRAM 1 % busy.  A read is a strictly
 // sequential state machine with ~8-base granularity; giving each lane its own read removes every scan, shuffle and ballot
-// (~25x fewer warp-instructions per read) and lets each kernel fit the instruction cache.  Lanes fetch the next read from
+// (7 000 -> 1 700 warp-instructions per read today) and lets each kernel fit the instruction cache.  Lanes fetch the next read from
 // an atomic cursor as soon as they finish one, so a warp stays busy whatever the read lengths are.
 #pragma once
 #include "npt_device.cuh"
