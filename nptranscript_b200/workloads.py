@@ -54,6 +54,42 @@ class Annotation:
         """Exon rows of one chromosome in file order (GFFAnnotation.java:409-428): gene = the exon's parent attribute."""
         return cls(kind=2, genes=list(genes), start=list(start), end=list(end), strand=list(strand))
 
+    @classmethod
+    def from_gff_lines(cls, lines, chrom, gtf=False, features=("Name", "description", "ID", "biotype", "Parent")):
+        """Exon rows of one chromosome from GFF3 / GTF text, as GFFAnnotation's constructor reads them
+        (J/cluster/GFFAnnotation.java:368-459): feature types ending in "exon", gene = the value of the attribute named by
+        the 5th --GFF_features entry ("Parent" by default) after GFFAnnotation.process (:337-362: GFF values keep the part
+        after the last ':', GTF values lose their quotes).  The reference takes one zip entry per chromosome and tries the
+        name with and without a "chr" prefix (:370-372); here rows are selected by their first column under the same rule."""
+        name, description, id_, biotype, parent = features
+        headers = [id_, name, description, biotype, parent]  # GFFAnnotation.java:387
+        split = " " if gtf else "="
+        seqids = {chrom}
+        seqids.add(chrom[3:] if chrom.startswith("chr") else "chr" + chrom)
+        a = cls(kind=2)
+        for st in lines:
+            st = st.rstrip("\n")
+            if not st or st.startswith("#"):
+                continue
+            t = st.split("\t")
+            typ = t[2]
+            if typ == "chromosome" or typ.endswith("biological_region") or typ.startswith("unknown") or "scaffold" in typ or "contig" in typ:
+                continue
+            if t[0] not in seqids or not typ.endswith("exon"):
+                continue
+            target = [""] * 5
+            for d in t[8].split(";"):
+                dj = d.strip().split(split)
+                if len(dj) < 2:
+                    continue
+                key = dj[0].strip()
+                val = dj[1][1:-1] if gtf else dj[1].split(":")[-1]
+                for k, h in enumerate(headers):
+                    if key == h:
+                        target[k] = dj[1].split("[")[0] if k == 2 else val
+            a.genes.append(target[4]); a.start.append(int(t[3])); a.end.append(int(t[4])); a.strand.append(t[6][0] == "+")
+        return a
+
     @property
     def name_hash(self):
         """h ^ (h >>> 16) of Java's String.hashCode() per row (HashMap.hash): decides HashSet<String> iteration order."""
