@@ -281,3 +281,39 @@ def test_reference_forced_out_of_shared_memory(monkeypatch):
     b = synth.generate(w, 41, 6000)
     dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1), w, [b])
     assert_same(dev, ora)
+
+
+def test_chromosomes_one_after_the_other_on_one_context():
+    """The reference's chromosome switch (ViralTranscriptAnalysisCmd2.java:830-901): one context, several begin/end cycles
+    with different references, annotations and batch sizes; results of each equal a fresh oracle run; fetch twice; a
+    cycle without fetch in between."""
+    rng = np.random.default_rng(21)
+    w1, w2 = workloads.SARS2, workloads.HCOV229E
+    G3 = 250_001
+    g3 = np.array([1, 2, 4, 8], np.uint8)[rng.integers(0, 4, G3)]
+    plan = [
+        (0, w1, synth.genome_codes(w1), w1.annotation, [synth.generate(w1, 3, 5000), synth.generate(w1, 4, 100)]),
+        (1, w2, synth.genome_codes(w2), w2.annotation, [synth.generate(w2, 5, 3000)]),
+        (2, w1, g3, w1.annotation, [random_batch(rng, 700, G3, g3, big_n=3000)]),   # larger reference: reallocation + global-memory reference
+        (3, w1, synth.genome_codes(w1), w1.annotation, []),                          # a chromosome without reads
+        (4, w1, synth.genome_codes(w1), w1.annotation, [synth.generate(w1, 6, 2000)]),
+    ]
+    kw = dict(bin=10, break_thresh=1000, record_depth=1, max_coverage_clusters=256)
+    eng = engine.Engine(engine.make_config(**kw))
+    try:
+        for ci, w, g, ann, bs in plan:
+            eng.begin_chrom(ci, g, ann)
+            for b in bs:
+                eng.submit(b)
+            eng.end_chrom()
+            if ci == 1:
+                eng.release()  # results never fetched
+                continue
+            dev = eng.fetch()
+            again = eng.fetch(abi.NPT_FETCH_TABLES)
+            assert np.array_equal(dev["sub_count"], again["sub_count"]) and np.array_equal(dev["cl_key_tok"], again["cl_key_tok"])
+            ora = oracle.run(oracle.make_config(**kw), g, ann, bs, ci)
+            assert_same(dev, ora)
+            eng.release()
+    finally:
+        eng.close()
