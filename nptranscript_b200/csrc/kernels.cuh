@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
   uint32_t pmat = 0; int ppos0 = 0;
   int mStart0 = 0, mRpos = 0, mN = 0, mOff = 0;  // M op being windowed: windows remain while mOff < mN
   int st_r = 0, maxEnd = 0, eBs = 0, eRs = 0;
+  int nbases = 0;           // MODE 0: bases this record holds (2 per byte: the pad nibble of an odd-length read counts)
   bool stFound = false;
   int pendingEnd = -1;      // MODE 1: exclusive end of the last depth run, not yet written
   int* cov = nullptr;       // MODE 1: row [arr 0][cluster][src][0]
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           ckg = __ldg(b.cigar_off + r); cendg = __ldg(b.cigar_off + r + 1);
           cs = ckg + 64u;               // nothing staged yet (ckg - cs wraps to a huge value)
           const unsigned long long so = __ldg(b.seq_off + r);
+          if (MODE == 0) nbases = (int)min(2ull * (__ldg(b.seq_off + r + 1) - so), 0x7FFFFFFFull);
           rp16 = (long long)(so >> 4) << 2;
           ss = 0x80000000u;             // base tile belongs to another read
           nib0 = (uint32_t)(so & 15) * 2;
@@ -325,8 +327,13 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       if (!stFound && bEnd >= alnStart) { st_r = alnStart < bStart ? 0 : alnStart - bStart + rStart; stFound = true; }
       if (bEnd > maxEnd) { maxEnd = bEnd; eBs = bStart; eRs = rStart; }
       const int nE = max(0, min(len, G - ref0));
+      if (MODE == 0 && nE > 0 && (long long)read0 + nE > nbases) {
+        // the reference's readSeq.getBase runs past the end of the read and throws (IdentityProfile1.java:531-551): not clustered
+        b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu;
+        active = false;
+      }
       maps += nE;
-      mStart0 = ref0; mRpos = read0; mOff = 0; mN = nE;
+      mStart0 = ref0; mRpos = read0; mOff = 0; mN = active ? nE : 0;
       if (MODE == 1 && nE > 0) depth_run(ref0 + 1, nE);
     }
     __syncwarp();

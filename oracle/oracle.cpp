@@ -206,7 +206,7 @@ int read_pos_at_ref_pos(const uint32_t* cig, int nc, int alnStart, int pos) {
 }
 
 // IdentityProfile1.processCigar (J/cluster/IdentityProfile1.java:482-585)
-bool process_cigar(Scratch& s, const Cfg& cfg, int alnStart, const uint32_t* cig, int nc, const uint8_t* seq4,
+bool process_cigar(Scratch& s, const Cfg& cfg, int alnStart, const uint32_t* cig, int nc, const uint8_t* seq4, int64_t nbases,
                    const uint8_t* ref, int64_t refLen, int* alnEndOut) {
   int64_t readPos = 0;
   int64_t refPos = (int64_t)alnStart - 1;
@@ -228,6 +228,9 @@ bool process_cigar(Scratch& s, const Cfg& cfg, int alnStart, const uint32_t* cig
         break;
       case 1: readPos += length; break;  // I
       case 0:  // M :531-550
+        // readSeq.getBase(readPos+i) past the end of the read throws in the reference: record not clustered.  nbases counts
+        // the pad nibble of an odd-length read as a base (npt_batch carries bytes, not l_seq).
+        if (length > 0 && refPos < refLen && readPos + std::min<int64_t>(length, refLen - refPos) > nbases) return false;
         for (int i = 0; i < length && refPos + i < refLen; i++) {
           bool m = ref[refPos + i] == seq4_at(seq4, readPos + i);
           cc_add(s, cfg, (int)(refPos + i + 1), m);
@@ -254,12 +257,12 @@ bool process_cigar(Scratch& s, const Cfg& cfg, int alnStart, const uint32_t* cig
 
 // IdentityProfile1.identity1 :594-643 + processRefPositions :149-356 for one read (the order-free part).
 void per_read(const Cfg& cfg, const Annot& annot, const uint8_t* ref, int64_t refLen, int alnStart, int flag, int src,
-              const uint32_t* cig, int nc, const uint8_t* seq4, Scratch& s, ReadOut& o) {
+              const uint32_t* cig, int nc, const uint8_t* seq4, int64_t nbases, Scratch& s, ReadOut& o) {
   s.clear();
   o = ReadOut();
   int alnEnd = 0;
   if (alnStart <= 0) return;  // unmapped-style record: the caller's filter chain drops these (ViralTranscriptAnalysisCmd2.java:716)
-  if (!process_cigar(s, cfg, alnStart, cig, nc, seq4, ref, refLen, &alnEnd)) return;
+  if (!process_cigar(s, cfg, alnStart, cig, nc, seq4, nbases, ref, refLen, &alnEnd)) return;
   o.ok = true;
   // :634-635
   int st_r = read_pos_at_ref_pos(cig, nc, alnStart, alnStart);
@@ -580,7 +583,7 @@ void npto_submit(void* h, const npt_batch* b, int nthreads) {
       Scratch s; ReadOut o;
       for (int64_t i = base; i < base + m; i++) {
         per_read(R.cfg, R.annot, R.ref.data(), (int64_t)R.ref.size(), b->pos[i], b->flag[i], b->src[i], b->cigar + b->cigar_off[i],
-                 (int)(b->cigar_off[i + 1] - b->cigar_off[i]), b->seq4 + b->seq_off[i], s, o);
+                 (int)(b->cigar_off[i + 1] - b->cigar_off[i]), b->seq4 + b->seq_off[i], 2 * (int64_t)(b->seq_off[i + 1] - b->seq_off[i]), s, o);
         commit(R, o, s, b->src[i]);
       }
     } else {
@@ -593,7 +596,8 @@ void npto_submit(void* h, const npt_batch* b, int nthreads) {
           for (int64_t k = j; k < std::min(j + 64, m); k++) {
             int64_t i = base + k;
             per_read(R.cfg, R.annot, R.ref.data(), (int64_t)R.ref.size(), b->pos[i], b->flag[i], b->src[i],
-                     b->cigar + b->cigar_off[i], (int)(b->cigar_off[i + 1] - b->cigar_off[i]), b->seq4 + b->seq_off[i], scr[k],
+                     b->cigar + b->cigar_off[i], (int)(b->cigar_off[i + 1] - b->cigar_off[i]), b->seq4 + b->seq_off[i],
+                     2 * (int64_t)(b->seq_off[i + 1] - b->seq_off[i]), scr[k],
                      outs[k]);
           }
         }

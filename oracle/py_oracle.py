@@ -226,6 +226,10 @@ class Run:
             elif c == "I":
                 read_pos += ln
             elif c == "M":
+                n_emit = max(0, min(ln, G - ref_pos))
+                if n_emit > 0 and read_pos + n_emit > len(bases):  # getBase past the end of the read throws in the reference
+                    self.rows.append(dict(ok=False))
+                    return
                 i = 0
                 while i < ln and ref_pos + i < G:
                     add(ref_pos + i + 1, self.ref[ref_pos + i] == bases[read_pos + i])
@@ -383,6 +387,5 @@ def unpack_batch(b):
         for byte in sq:
             bases.append(int(byte) >> 4)
             bases.append(int(byte) & 15)
-        bases += [0] * 16
         out.append((int(b.pos[i]), int(b.flag[i]), int(b.src[i]), cig, bases))
     return out

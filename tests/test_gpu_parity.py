@@ -151,6 +151,9 @@ EDGE_READS = [
     (400, 0, 0, "50M1200D50M", None),                  # a deletion longer than the break threshold
     (500, 0, 0, "33M1I31M2D65M1X3=40M", None),         # step boundaries at 32/33 bases
     (600, 16, 0, "5M3N5M3N5M3N5M3N5M3N5M3N5M3N5M", None),
+    (700, 0, 0, "30M", "ACGTACGTAC"),                  # the CIGAR wants more bases than the record holds: the reference throws
+    (710, 0, 0, "10M5S", "ACGTACGTACGT"),              # ... but a clip past the end is never looked at
+    (29890, 0, 0, "10M", "ACGTAC"),                    # the part of the M op inside the reference fits the 6 bases
 ]
 
 
@@ -160,7 +163,10 @@ def _edge_batch(g):
     gs = lut[g].tobytes().decode()
     import re
     reads = []
-    for pos, flag, src, cig, _ in EDGE_READS:
+    for pos, flag, src, cig, given in EDGE_READS:
+        if given is not None:
+            reads.append((pos, flag, src, cig, given))
+            continue
         ref, bases = pos - 1, []
         for ln, op in re.findall(r"(\d+)([MIDNSHP=X])", cig):
             ln = int(ln)
