@@ -83,7 +83,8 @@ extern "C" {
 #define NPT_RF_TYPE_MASK 0x3u  /* Annotation.getTypeInd: 0=5_3 1=5_no3 2=no5_3 3=no5_no3 (J/cluster/Annotation.java:233-236) */
 #define NPT_RF_LEADER 0x4u     /* hasLeaderBreak (J/cluster/IdentityProfile1.java:256, 281) */
 #define NPT_RF_NEG 0x8u        /* read negative strand flag (SAM flag 0x10) */
-#define NPT_RF_BADCIGAR 0x10u  /* CIGAR op > 8: the reference throws (J/cluster/IdentityProfile1.java:577-578); read not clustered */
+#define NPT_RF_BADCIGAR 0x10u  /* pos <= 0, CIGAR op > 8 (J/cluster/IdentityProfile1.java:577-578) or an M element past the end of the read
+                                 (getBase, :531-551): the reference throws; read not clustered */
 #define NPT_RF_SLOWPATH 0x20u  /* diagnostic: read was walked by the exact serial device path */
 
 typedef struct npt_config {
