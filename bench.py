@@ -49,8 +49,10 @@ class ClockSampler:
         self.gpu, self.rows, self.p = gpu, [], None
 
     def start(self):
+        if self.gpu is None:
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -224,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         device_step()
         eng.release()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank if rank == 0 else None)  # one nvidia-smi loop per job: its queries serialise in the driver
     barrier()
     sampler.start()
     step_ms, walk_ms, fin_ms, launches = [], [], [], 0
@@ -358,7 +360,8 @@ def run_ours(args, rank, world, local_rank):
                        "clusters": n_clusters, "sub_clusters": n_subs, "junction_steps": n_slow,
                        "self_check": {"reads": e2e_reads, "passed": sorted(checks)}, "gen_seconds": gen_s,
                        "merge_breakdown_ms": {"key_exchange_ms": float(np.mean(kx_list)), "reduce_ms": float(np.mean(red_list)),
-                                              "note": "key exchange = export + NCCL all-gather + import, inside the step span; reduce = NCCL all-reduces after end_chrom"} if world > 1 else None,
+                                              "last_step": getattr(__import__("nptranscript_b200.multigpu", fromlist=["x"]).exchange_keys, "last", None),
+                                              "note": "key exchange = wait for own kernels + export + NCCL all-gather + import, inside the step span; reduce = NCCL all-reduces after end_chrom"} if world > 1 else None,
                        "timing": "CUDA events inside libnpt on its compute stream (npt_last_step_ms / npt_last_kernel_ms); wall ms/step %.2f" % wall_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": names[dom], "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms, "algorithmic_bytes": alg,

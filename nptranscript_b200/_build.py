@@ -1,5 +1,7 @@
 """In-tree builds: nvcc for the CUDA library (sm_100a), g++ for the synthetic-workload generator.
 The built .so files live next to their sources (git-ignored, shipped to the GPU box by gpurun)."""
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -13,6 +15,18 @@ LIBBAM = os.path.join(HERE, "bam", "libnptbam.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+
+
+@contextlib.contextmanager
+def _locked(target):
+    """One builder at a time per target (ranks of a torchrun job all import this module), and never a half-written .so:
+    callers compile to a temporary name and os.replace() it under this lock."""
+    with open(target + ".lock", "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
 
 
 def _stale(target, sources):
@@ -35,19 +49,24 @@ def build_libnpt(force=False, verbose=False):
     cus = [s for s in srcs if s.endswith((".cu", ".cpp"))]
     if not force and not _stale(LIBNPT, srcs):
         return LIBNPT
-    nvcc = _nvcc()
-    if nvcc is None:
-        if os.path.exists(LIBNPT):
-            return LIBNPT  # GPU box without a toolchain on PATH: use the shipped build
-        raise RuntimeError("nvcc not found and libnpt.so not built")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIBNPT] + cus
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with _locked(LIBNPT):
+        if not force and not _stale(LIBNPT, srcs):
+            return LIBNPT  # another process built it while we waited
+        nvcc = _nvcc()
+        if nvcc is None:
+            if os.path.exists(LIBNPT):
+                return LIBNPT  # GPU box without a toolchain on PATH: use the shipped build
+            raise RuntimeError("nvcc not found and libnpt.so not built")
+        tmp = LIBNPT + f".{os.getpid()}.tmp"
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", tmp] + cus
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIBNPT)
+        if verbose:
+            print(r.stderr)
     return LIBNPT
 
 
@@ -55,24 +74,35 @@ def build_synth(force=False):
     src = os.path.join(HERE, "synth", "synth.cpp")
     if not force and not _stale(LIBSYNTH, [src]):
         return LIBSYNTH
-    cxx = shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", LIBSYNTH, src]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    with _locked(LIBSYNTH):
+        if not force and not _stale(LIBSYNTH, [src]):
+            return LIBSYNTH
+        cxx = shutil.which("g++") or "g++"
+        tmp = LIBSYNTH + f".{os.getpid()}.tmp"
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-pthread", "-shared", "-o", tmp, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIBSYNTH)
     return LIBSYNTH
 
 
 def build_bam(force=False):
     """BAM (BGZF) -> SoA packer: host C++ + zlib, no CUDA."""
     src = os.path.join(HERE, "bam", "bam_pack.cpp")
-    if not force and not _stale(LIBBAM, [src, os.path.join(ROOT, "include", "npt_bam.h")]):
+    deps = [src, os.path.join(ROOT, "include", "npt_bam.h")]
+    if not force and not _stale(LIBBAM, deps):
         return LIBBAM
-    cxx = shutil.which("g++") or "g++"
-    cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-pthread", "-shared", "-Wall", "-Wextra", "-o", LIBBAM, src, "-lz"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    with _locked(LIBBAM):
+        if not force and not _stale(LIBBAM, deps):
+            return LIBBAM
+        cxx = shutil.which("g++") or "g++"
+        tmp = LIBBAM + f".{os.getpid()}.tmp"
+        cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-pthread", "-shared", "-Wall", "-Wextra", "-o", tmp, src, "-lz"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIBBAM)
     return LIBBAM
 
 

@@ -232,21 +232,29 @@ def exchange_keys(eng, rank, world):
     import torch
     import torch.distributed as dist
     t0 = time.perf_counter()
+    eng.wait()  # this rank's kernels
+    t1 = time.perf_counter()
     ptr, n = eng.export_keys()
+    t2 = time.perf_counter()
     sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
     sizes[rank] = n
     dist.all_reduce(sizes)
     sizes = sizes.cpu().tolist()
+    t3 = time.perf_counter()  # includes waiting for the slowest rank
     m = int(max(sizes))
     mine = torch.zeros(m, dtype=torch.int32, device="cuda")
     mine[:n] = torch.as_tensor(_DevPtr(ptr, n, "<i4"), device="cuda")
     allbuf = torch.empty(world * m, dtype=torch.int32, device="cuda")
     dist.all_gather_into_tensor(allbuf, mine)
     torch.cuda.synchronize()
+    t4 = time.perf_counter()
     for r in range(world):
         if r != rank:
             eng.import_keys(allbuf[r * m:].data_ptr(), int(sizes[r]))
-    return 1e3 * (time.perf_counter() - t0)
+    t5 = time.perf_counter()
+    exchange_keys.last = dict(wait_own_kernels_ms=1e3 * (t1 - t0), export_ms=1e3 * (t2 - t1), sizes_allreduce_ms=1e3 * (t3 - t2),
+                              all_gather_ms=1e3 * (t4 - t3), import_ms=1e3 * (t5 - t4), words=int(n))
+    return 1e3 * (t5 - t0)
 
 
 def reduce_aggregates(eng):

@@ -19,10 +19,15 @@ _lib = None
 def build(force=False):
     src = os.path.join(HERE, "oracle.cpp")
     hdr = os.path.join(HERE, "..", "include", "npt.h")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        r = subprocess.run(["make", "-C", HERE, "-B" if force else "-s"], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    stale = lambda: not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or stale():
+        import fcntl
+        with open(LIB + ".lock", "w") as f:  # one builder at a time (parallel test workers, ranks)
+            fcntl.flock(f, fcntl.LOCK_EX)
+            if force or stale():
+                r = subprocess.run(["make", "-C", HERE, "-B" if force else "-s"], capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
     return LIB
 
 
