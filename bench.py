@@ -234,6 +234,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- HBM-resident leg
     for _ in range(args.warmup):
+        if world > 1:
+            dist.barrier()
         device_step()
         eng.release()
     sampler = ClockSampler(local_rank if rank == 0 else None)  # one nvidia-smi loop per job: its queries serialise in the driver
@@ -244,6 +246,8 @@ def run_ours(args, rank, world, local_rank):
     kx_list, red_list = [], []
     wall0 = time.perf_counter()
     for _ in range(args.steps):
+        if world > 1:
+            dist.barrier()  # ranks start a step together: a step's span contains the key exchange, which waits for the slowest rank
         t = device_step()
         step_ms.append(t["step_ms"] + t["merge_ms"]); walk_ms.append(t["walk_ms"]); fin_ms.append(t["finalize_ms"])
         stages.append([t["walk0_ms"], t["walk2_ms"], t["cluster_ms"], t["walk1_ms"]])
