@@ -131,3 +131,25 @@ def test_library_exports_every_declared_symbol():
     L = bam.lib()
     for s in bam.SYMBOLS:
         assert hasattr(L, s)
+
+
+def test_struct_layout_matches_c():
+    import ctypes as C
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "npt_bam.h"\nint main(){\n'
+    probes = []
+    for cname, st in (("nptb_filter", bam.Filter), ("nptb_batch", bam.BatchStruct)):
+        src += f'printf("%zu\\n", sizeof({cname}));\n'
+        probes.append((cname, None, C.sizeof(st)))
+        for fname, _ in st._fields_:
+            src += f'printf("%zu\\n", offsetof({cname}, {fname}));\n'
+            probes.append((cname, fname, getattr(st, fname).offset))
+    src += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", os.path.join(d, "p"), os.path.join(d, "p.c")])
+        out = subprocess.check_output([os.path.join(d, "p")], text=True).split()
+    for (n, f, py), c in zip(probes, out):
+        assert py == int(c), (n, f, py, c)

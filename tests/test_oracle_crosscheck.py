@@ -153,3 +153,32 @@ def test_edge_case_reads():
     for kw in (dict(bin=10, break_thresh=1000, record_depth=1), dict(bin=10, break_thresh=2, record_depth=1)):
         _compare(kw, w.annotation, [b, b.slice(3, 4), b])
     _compare(dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=1), workloads.Annotation.empty(), [b])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_flag_combinations(seed):
+    """Flags drawn at random (both modes, all three annotation kinds): the two restatements must agree on everything."""
+    from tests.fuzz import gff_case
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(1000 + seed)
+    corona = bool(rng.integers(0, 2))
+    S = int(rng.integers(1, 4))
+    kw = dict(bin=int(rng.choice([1, 5, 10, 100])), break_thresh=int(rng.choice([2, 20, 50, 400, 1000])), coronavirus=int(corona),
+              include_start=int(rng.integers(0, 2)), record_depth=int(rng.integers(0, 2)), num_sources=S,
+              start_thresh=int(rng.choice([0, 100, 1000])), end_thresh=int(rng.choice([0, 100, 1000])))
+    if corona:
+        kw["enforce_strand"] = int(rng.integers(0, 2))
+        kw["rna"] = [1] * S
+        ann = w.annotation
+        bs = [random_batch(rng, 150, w.genome_len, g, num_sources=S, max_ops=12 if kw["break_thresh"] < 8 else 40), synth.generate(w, seed, 60, num_sources=S)]
+    else:
+        kw["rna"] = [int(x) for x in rng.integers(0, 2, S)]
+        kw["first_is_transcriptome"] = int(rng.integers(0, 2))
+        if rng.integers(0, 2):
+            ann = workloads.Annotation.empty()
+            bs = [random_batch(rng, 200, w.genome_len, g, num_sources=S, big_n=300)]
+        else:
+            ann, b = gff_case(rng, 200, w.genome_len, _genome_str(g), num_sources=S, hash_collide=bool(rng.integers(0, 2)))
+            bs = [b]
+    _compare(kw, ann, bs, chrom_index=int(rng.integers(0, 5)))
