@@ -323,3 +323,35 @@ def test_chromosomes_one_after_the_other_on_one_context():
             eng.release()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_flag_combinations(seed):
+    """Flags drawn at random (both modes, all three annotation kinds, 1-3 sources): device against oracle."""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    rng = np.random.default_rng(2000 + seed)
+    corona = bool(rng.integers(0, 2))
+    S = int(rng.integers(1, 4))
+    kw = dict(bin=int(rng.choice([1, 5, 10, 100])), break_thresh=int(rng.choice([2, 20, 50, 400, 1000])), coronavirus=int(corona),
+              include_start=int(rng.integers(0, 2)), record_depth=int(rng.integers(0, 2)), num_sources=S,
+              start_thresh=int(rng.choice([0, 100, 1000])), end_thresh=int(rng.choice([0, 100, 1000])), max_coverage_clusters=1024)
+    if corona:
+        kw["enforce_strand"] = int(rng.integers(0, 2))
+        kw["rna"] = [1] * S
+        ann = w.annotation
+        bs = [random_batch(rng, 1500, w.genome_len, g, num_sources=S, max_ops=12 if kw["break_thresh"] < 8 else 40), synth.generate(w, seed, 2000, num_sources=S)]
+    else:
+        kw["rna"] = [int(x) for x in rng.integers(0, 2, S)]
+        kw["first_is_transcriptome"] = int(rng.integers(0, 2))
+        kw["max_coverage_clusters"] = 4096
+        if rng.integers(0, 2):
+            ann = workloads.Annotation.empty()
+            bs = [random_batch(rng, 2000, w.genome_len, g, num_sources=S, big_n=300)]
+        else:
+            lut = np.full(16, ord("N"), np.uint8)
+            lut[[1, 2, 4, 8]] = [ord(ch) for ch in "ACGT"]
+            ann, b = gff_case(rng, 3000, w.genome_len, lut[g].tobytes().decode(), n_genes=50, num_sources=S, hash_collide=bool(rng.integers(0, 2)))
+            bs = [b]
+    dev, ora = _both(kw, w, bs, annotation=ann, chrom_index=int(rng.integers(0, 5)))
+    assert_same(dev, ora)
