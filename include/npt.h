@@ -208,7 +208,10 @@ const char* npt_last_error(const npt_ctx* ctx); /* ctx may be NULL: error of the
 
 /* ref_codes: one BAM 4-bit code per reference base (same code table as seq4), host memory. */
 int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot);
-/* Asynchronous: returns once the batch is enqueued.  Host arrays must stay untouched until npt_wait. */
+/* Asynchronous: returns once the batch is enqueued.  Host arrays (NPT_MEM_HOST) must stay untouched until npt_wait.
+ * Device arrays (NPT_MEM_DEVICE) are read in place and must stay valid and unchanged until npt_end_chrom has returned
+ * (with first_is_transcriptome the end-of-chromosome pass reads src again).  A record whose src is >= num_sources makes
+ * npt_end_chrom fail with NPT_EINVAL. */
 int npt_submit(npt_ctx* ctx, const npt_batch* batch);
 int npt_wait(npt_ctx* ctx);
 /* Drains, assigns first-appearance ids (sort-and-rank), rewrites per-read ids, scans the coverage difference arrays. */
@@ -276,9 +279,11 @@ void npt_free_pinned(void* p);
 int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t* walk_launches, int64_t* total_launches);
 /* CUDA-event span on the compute stream from the first device work of npt_begin_chrom to the last of npt_end_chrom. */
 int npt_last_step_ms(npt_ctx* ctx, float* step_ms);
-/* Per-kernel CUDA-event durations summed over the batches of the last chromosome, in launch order:
- * out4 = { walk_kernel<0> (breaks), walk_kernel<2> (long break lists), cluster_kernel, walk_kernel<1> (coverage) }. */
-int npt_last_stage_ms(npt_ctx* ctx, float* out4);
+/* Per-stage CUDA-event durations summed over the batches of the last chromosome, in launch order:
+ * out6 = { fast_walk_kernel (breaks + coverage entries of the reads it can restate), walk_kernel<0> (serial walker: all
+ * reads when the fast walk is off, else the reads it refused), walk_kernel<2> (long break lists), cluster_kernel,
+ * walk_kernel<1> (coverage of the serial walker's reads), coverage of the fast reads (keys + radix sort + accumulate_kernel) }. */
+int npt_last_stage_ms(npt_ctx* ctx, float* out6);
 
 #ifdef __cplusplus
 }

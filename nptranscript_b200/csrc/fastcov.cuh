@@ -1,0 +1,374 @@
+// fastcov.cuh — device kernels around fastwalk.cuh:
+//
+//   fast_walk_kernel     one thread per read, rounds of [stage tiles -> produce tasks -> consume tasks -> flush entries]
+//   cov_key_kernel       after clustering: sort key (coverage row of the cluster, source) per read + the few
+//                        mapStart/mapEnd points of a read (CigarCluster.setStartEnd :360-365 and the break_p events of
+//                        CigarCluster.add :476-486) credited with REDs
+//   accumulate_kernel    per (cluster, source) group of the key-sorted reads: positional popcount of the reads' entries
+//                        with bit-sliced carry-save adders, one thread per (reference-grid entry, read subset), private
+//                        16-bit counters in shared memory, one RED per touched position per group at the end.
+//
+// Why no atomics per event: ncu of round 1 showed the coverage walk bound by the L2 atomic rate (126 REDs per read,
+// 4.5e10 RED/s), and shared-memory atomics are no way out on this part (ATOMS ~2 cycles per lane).  A read's coverage is a
+// set of per-position flags on the reference grid; summing flags over reads is positional popcount, which plain LOP3
+// does 32 positions at a time (2 LOP3 per plane and word).
+#pragma once
+#include "fastwalk.cuh"
+
+namespace npt {
+
+constexpr int FW_WARPS_MAX = 16;
+constexpr int FW_PW_CIG = 32 * FW_TILE_STRIDE, FW_PW_SEQ = 32 * FW_TILE_STRIDE, FW_PW_TASK = FW_K * 32 * 2, FW_PW_SRC = 32 + 64;
+__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_CIG + FW_PW_SEQ + FW_PW_TASK + (record ? FW_RING * 32 : 0) + FW_PW_SRC; }
+
+__device__ __forceinline__ void fw_cp16z(uint32_t dst, const void* src, int n) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void fw_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool REF_SMEM, bool RECORD>
+__global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const DevCfg c, const BatchDev b) {
+  extern __shared__ __align__(16) uint32_t fw_smem[];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned FULL = 0xffffffffu;
+  const int refw = REF_SMEM ? ((c.refg_nwords + 3) & ~3) : 0;
+  uint32_t* s_ref = fw_smem;
+  uint32_t* wb = fw_smem + refw + warp * fw_warp_words(RECORD);
+  uint32_t* cigT = wb;
+  uint32_t* seqT = cigT + FW_PW_CIG;
+  uint2* taskT = (uint2*)(seqT + FW_PW_SEQ);
+  uint32_t* ringT = (uint32_t*)taskT + FW_PW_TASK;
+  uint32_t* srcC = ringT + (RECORD ? FW_RING * 32 : 0);                 // [32] first CIGAR word to stage + 1, 0 = none
+  unsigned long long* srcS = (unsigned long long*)(srcC + 32);          // [32] first base byte to stage + 1, 0 = none
+  if (REF_SMEM)
+    for (int i = threadIdx.x; i < c.refg_nwords; i += blockDim.x) s_ref[i] = c.refg_words[i];
+  if (RECORD)
+    for (int i = lane; i < FW_RING * 32; i += 32) ringT[i] = 0;
+  __syncthreads();
+  const uint32_t* refg = REF_SMEM ? s_ref : c.refg_words;
+  const uint32_t cigS = (uint32_t)__cvta_generic_to_shared(cigT), seqS = (uint32_t)__cvta_generic_to_shared(seqT);
+  unsigned* cursor = b.bctr + 5;
+  const long long cig_words = b.cigar_words, seq_bytes = b.seq_bytes;
+
+  FwLane L;
+  L.flags = 0; L.nt = 0; L.tb = -1; L.so = 0; L.readPos = 0; L.ck = 0; L.cs = 0; L.r = 0;
+  for (;;) {
+    // ---- (0) lanes without a read take the next ones from the cursor (one atomic per warp and round)
+    const bool want = (L.flags & (FWF_ACTIVE | FWF_DONE)) == 0;
+    const unsigned wm = __ballot_sync(FULL, want);
+    if (wm) {
+      unsigned base = 0;
+      const int leader = __ffs(wm) - 1;
+      if ((int)lane == leader) base = atomicAdd(cursor, (unsigned)__popc(wm));
+      base = __shfl_sync(FULL, base, leader);
+      if (want) {
+        const long long r = (long long)base + __popc(wm & ((1u << lane) - 1u));
+        if (r < b.n) fw_start_read(L, b, r); else L.flags = FWF_DONE;
+      }
+    }
+    if (__all_sync(FULL, (L.flags & (FWF_ACTIVE | FWF_DONE)) == FWF_DONE)) break;
+    // ---- (1) stage this round's CIGAR words and bases: every lane publishes what it needs, the warp copies all tiles
+    // together with 16-byte cp.async (a lane copying only its own tile costs one L1 wavefront per lane and copy)
+    {
+      const bool live = (L.flags & (FWF_ACTIVE | FWF_SLOW)) == FWF_ACTIVE;
+      const unsigned ncs = L.ck & ~3u;
+      const bool needC = live && ncs != L.cs && L.ck < L.cend;
+      if (needC) L.cs = ncs;
+      srcC[lane] = needC ? ncs + 1u : 0u;
+      const long long ntb = (long long)((L.so + (unsigned long long)(L.readPos >> 1)) & ~15ull);
+      const bool needS = live && ntb != L.tb;
+      if (needS) L.tb = ntb;
+      srcS[lane] = needS ? (unsigned long long)ntb + 1ull : 0ull;
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < FW_CIG_TILE / 4; it++) {     // 32 tiles x 4 chunks
+        const unsigned id = it * 32 + lane, owner = id >> 2, ch = id & 3u;
+        const unsigned s1 = srcC[owner];
+        if (s1) {
+          const long long w0 = (long long)(s1 - 1u) + 4 * ch;
+          const long long left = (cig_words - w0) * 4;
+          fw_cp16z(cigS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.cigar + w0) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < FW_SEQ_TILE / 4; it++) {     // 32 tiles x 5 chunks
+        const unsigned id = it * 32 + lane, owner = id / 5u, ch = id - owner * 5u;
+        const unsigned long long s1 = srcS[owner];
+        if (s1) {
+          const long long a0 = (long long)(s1 - 1ull) + 16 * ch;
+          const long long left = seq_bytes - a0;
+          fw_cp16z(seqS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.seq4 + a0) : (const void*)b.seq4, (int)max(0LL, min(16LL, left)));
+        }
+      }
+      fw_cp_wait();
+      __syncwarp();
+    }
+    // ---- (2) CIGAR -> tasks
+    fw_produce<RECORD>(L, c, cigT + lane * FW_TILE_STRIDE, FW_CIG_TILE, taskT + lane, 32);
+    __syncwarp();
+    // ---- (3) tasks -> match masks, breaks, ring (the same straight-line code in every lane)
+    const int ntmax = __reduce_max_sync(FULL, L.nt);
+    for (int i = 0; i < ntmax; i++) {
+      if (i < L.nt) fw_task<RECORD>(L, c, b, taskT[i * 32 + lane], seqT + lane * FW_TILE_STRIDE, refg, ringT + lane, 32);
+      __syncwarp();
+    }
+    // ---- (4) completed entries, closed blocks, finished reads
+    fw_flush<RECORD>(L, c, b, ringT + lane, 32);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ keys + start/end points
+// key = coverage row of the read's cluster * S + source; reads that are not credited by accumulate_kernel (walked by the
+// serial path, bad records, unclustered) get the sentinel cov_cap * S and sort to the end.
+__global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys, unsigned* vals) {
+  if (__ldcg(b.bctr + 1)) return;  // break lists incomplete, nothing was clustered: the host re-runs this batch
+  const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
+    const unsigned rf = b.rflags[r];
+    const int slot = b.cluster[r];
+    unsigned key = (unsigned)c.cov_cap * (unsigned)c.S;
+    if (!(rf & 0x30u) && slot >= 0) {
+      const int prov = __ldcg(c.cl_rec + (unsigned)(__ldcg(&c.cl[slot].word) & 0xffffffffu));
+      const int src = b.src[r];
+      if (prov >= c.cov_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_COV_FULL);
+      else {
+        key = (unsigned)prov * (unsigned)c.S + (unsigned)src;
+        int* cov = c.cov + ((long long)prov * c.S + src) * c.stride;
+        int* mstart = cov + 2 * arr_stride;
+        int* mend = cov + 3 * arr_stride;
+        // CigarCluster.setStartEnd :360-365 with the (trimmed) start / end of the read
+        const int sp = b.start_pos[r], ep = b.end_pos[r];
+        if (sp >= 0 && sp < c.stride) atomicAdd(mstart + sp, 1);
+        if (ep >= 0 && ep < c.stride) atomicAdd(mend + ep, 1);
+        const uint4 h0 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS));
+        const int njunc = (h0.y >> 8) & 0xFF, nextra = (h0.y >> 16) & 0xFF;
+        if (njunc | nextra) {
+          const uint4 h2 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 8));
+          const uint4 h3 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 12));
+          if (njunc > 0) { atomicAdd(mend + h2.x, 1); atomicAdd(mstart + h2.y, 1); }
+          if (njunc > 1) { atomicAdd(mend + h2.z, 1); atomicAdd(mstart + h2.w, 1); }
+          for (int e = 0; e < nextra; e++) {
+            const unsigned a = e == 0 ? h3.x : h3.z, p = e == 0 ? h3.y : h3.w;
+            if (a & 0x80000000u) {          // a position emitted by two D elements
+              const unsigned q = a & 0x7FFFFFFFu;
+              atomicAdd(cov + 8 * arr_stride + q, 1);   // depth
+              atomicAdd(cov + arr_stride + q, 1);       // errors
+            } else {                        // emission more than break_thresh after prev that was not a match
+              atomicAdd(mstart + a, 1); atomicAdd(mend + p, 1);
+            }
+          }
+        }
+      }
+    }
+    keys[r] = key; vals[r] = (unsigned)r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ positional popcount
+constexpr int ACC_THREADS = 1024;
+constexpr int ACC_TILE = 2048;        // key-sorted reads per block tile
+constexpr int ACC_MAX_ENT = 8192;     // reference-grid entries (32 positions each) a chromosome may have on this path
+constexpr int ACC_PLANES = 6;         // bit-sliced counters hold 63 reads before they are expanded
+constexpr int ACC_CNT_WORDS = 48;     // 96 16-bit counters per thread: (COV, QRK, MIS) x 32 positions
+
+struct AccSmem {
+  uint32_t cnt[ACC_CNT_WORDS * ACC_THREADS];   // [word][thread]
+  uint32_t vals[ACC_TILE];
+  uint32_t head[ACC_TILE / 32];
+  uint32_t act[ACC_MAX_ENT / 32];
+  uint32_t actpre[ACC_MAX_ENT / 32 + 1];
+  uint16_t word_of[ACC_MAX_ENT];
+  int nruns_dummy;
+};
+
+__device__ __forceinline__ void acc_add(uint32_t (&p)[ACC_PLANES], uint32_t x) {
+#pragma unroll
+  for (int k = 0; k < ACC_PLANES; k++) { const uint32_t cy = p[k] & x; p[k] ^= x; x = cy; }
+}
+
+// planes of one entry word -> the thread's 16-bit counters.  Byte lane m of ((plane >> j) & 0x01010101) is bit 8m+j of the
+// word = flag (j & 3) of nibble 7 - 2m - (j >> 2) counted from the top.
+__device__ __forceinline__ void acc_expand(uint32_t (&p)[ACC_PLANES], int k, uint32_t* cnt) {
+#pragma unroll
+  for (int f = 0; f < 3; f++) {
+    const int fb = f == 2 ? 3 : f;   // flag bits 0 (COV), 1 (QRK), 3 (MIS)
+    uint32_t A = 0, B = 0;           // A: odd nibbles (j = fb), B: even nibbles (j = fb + 4), four byte counters each
+#pragma unroll
+    for (int q = 0; q < ACC_PLANES; q++) {
+      A += ((p[q] >> fb) & 0x01010101u) << q;
+      B += ((p[q] >> (fb + 4)) & 0x01010101u) << q;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const uint32_t v = ((B >> (8 * m)) & 0xFFu) | (((A >> (8 * m)) & 0xFFu) << 16);
+      // counters of nibbles (6 - 2m, 7 - 2m) of word k: counter pair index f*16 + 4k + 3 - m
+      if (v) cnt[(f * 16 + 4 * k + 3 - m) * ACC_THREADS] += v;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < ACC_PLANES; q++) p[q] = 0;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg c, const BatchDev b, const unsigned* keys, const unsigned* vals,
+                                                                    unsigned* tile_cursor) {
+  extern __shared__ __align__(16) unsigned char acc_raw[];
+  if (__ldcg(b.bctr + 1)) return;  // see cov_key_kernel
+  AccSmem& sm = *reinterpret_cast<AccSmem*>(acc_raw);
+  __shared__ int s_tile, s_wact;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned invalid = (unsigned)c.cov_cap * (unsigned)c.S;
+  const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
+  const int n_ent = (c.stride + 31) / 32 + 1;
+  const int n_actw = (n_ent + 31) / 32;
+  uint32_t* mycnt = sm.cnt + tid;
+  for (;;) {
+    if (tid == 0) s_tile = (int)atomicAdd(tile_cursor, 1u);
+    __syncthreads();
+    const long long t0 = (long long)s_tile * ACC_TILE;
+    __syncthreads();
+    if (t0 >= b.n) break;
+    const int tn = (int)min((long long)ACC_TILE, b.n - t0);
+    if (__ldg(keys + t0) == invalid) break;   // sorted: nothing left to credit in this and all later tiles
+    // ---- the tile: read indices into shared memory, head flags of the runs of equal key
+    for (int i = tid; i < ACC_TILE; i += ACC_THREADS) {
+      bool head = false;
+      if (i < tn) {
+        sm.vals[i] = __ldg(vals + t0 + i);
+        const unsigned k = __ldg(keys + t0 + i);
+        head = (i == 0) || (k != __ldg(keys + t0 + i - 1));
+      }
+      const unsigned hb = __ballot_sync(0xffffffffu, head);
+      if (lane == 0) sm.head[i >> 5] = hb;
+    }
+    __syncthreads();
+    int i0 = 0;
+    while (i0 < tn) {
+      // ---- next run [i0, i1)
+      int i1 = tn;
+      {
+        int w = (i0 + 1) >> 5;
+        unsigned bits = (i0 + 1) < ACC_TILE ? (sm.head[w] & (0xffffffffu << ((i0 + 1) & 31))) : 0u;
+        const int nw = (tn + 31) >> 5;
+        while (!bits && ++w < nw) bits = sm.head[w];
+        if (bits && w < nw) i1 = min(tn, w * 32 + __ffs(bits) - 1);
+      }
+      const unsigned key = __ldg(keys + t0 + i0);
+      if (key == invalid) break;
+      const int rl = i1 - i0;
+      int* row_err = c.cov + arr_stride + (long long)key * c.stride;
+      int* row_dep = c.cov + 8 * arr_stride + (long long)key * c.stride;
+      // ---- (A) reference-grid entries touched by the run
+      for (int i = tid; i < n_actw; i += ACC_THREADS) sm.act[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < rl; i += ACC_THREADS) {
+        const unsigned r = sm.vals[i0 + i];
+        const uint4 h0 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
+        const uint4 h1 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS + 4));
+        const int nblk = h0.y & 0xFF;
+#pragma unroll
+        for (int k = 0; k < FW_MAX_BLOCKS; k++) {
+          if (k < nblk) {
+            const unsigned f = k == 0 ? h0.z : (k == 1 ? h1.x : h1.z), cn = k == 0 ? h0.w : (k == 1 ? h1.y : h1.w);
+            if (cn) {
+              const unsigned lo = f, hi = f + cn - 1;   // entries [lo, hi]
+              for (unsigned w = lo >> 5; w <= (hi >> 5) && w < (unsigned)n_actw; w++) {
+                unsigned m = 0xffffffffu;
+                if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+                if (w == (hi >> 5)) m &= 0xffffffffu >> (31 - (hi & 31));
+                if ((sm.act[w] & m) != m) atomicOr(&sm.act[w], m);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {   // exclusive prefix of the popcounts (n_actw <= 256)
+        int carry = 0;
+        for (int base = 0; base < n_actw; base += 32) {
+          const int w = base + lane;
+          const int pc = w < n_actw ? __popc(sm.act[w]) : 0;
+          int inc = pc;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+          if (w < n_actw) sm.actpre[w] = carry + inc - pc;
+          carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_wact = carry;
+      }
+      __syncthreads();
+      for (int w = tid; w < n_actw; w += ACC_THREADS) {
+        unsigned bits = sm.act[w];
+        int slot = sm.actpre[w];
+        while (bits) { const int bpos = __ffs(bits) - 1; bits &= bits - 1; sm.word_of[slot++] = (uint16_t)(w * 32 + bpos); }
+      }
+      __syncthreads();
+      const int wact = s_wact;
+      // ---- (B) passes of up to ACC_THREADS entries; thread = (entry s, read subset q)
+      for (int slot0 = 0; slot0 < wact; slot0 += ACC_THREADS) {
+        const int W = min(ACC_THREADS, wact - slot0);
+        const int Wpad = (W + 31) & ~31;
+        const int Q = ACC_THREADS / Wpad;
+        const int q = tid / Wpad, s = tid - q * Wpad;
+        const bool live = q < Q && s < W && q < rl;
+        const unsigned myw = (s < W) ? sm.word_of[slot0 + s] : 0u;
+        if (live)
+#pragma unroll
+          for (int k = 0; k < ACC_CNT_WORDS; k++) mycnt[k * ACC_THREADS] = 0;
+        uint32_t P0[ACC_PLANES], P1[ACC_PLANES], P2[ACC_PLANES], P3[ACC_PLANES];
+#pragma unroll
+        for (int k = 0; k < ACC_PLANES; k++) { P0[k] = 0; P1[k] = 0; P2[k] = 0; P3[k] = 0; }
+        int nin = 0;
+        if (q < Q) {
+          for (int i = q; i < rl; i += Q) {
+            const unsigned r = sm.vals[i0 + i];
+            const uint4 h0 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
+            const uint4 h1 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS + 4));
+            const int nblk = h0.y & 0xFF;
+            const unsigned c0 = nblk > 0 ? h0.w : 0u, c1 = nblk > 1 ? h1.y : 0u, c2 = nblk > 2 ? h1.w : 0u;
+            const unsigned d0 = myw - h0.z, d1 = myw - h1.x, d2 = myw - h1.z;
+            unsigned idx = 0xffffffffu;
+            if (d0 < c0) idx = d0;
+            else if (d1 < c1) idx = c0 + d1;
+            else if (d2 < c2) idx = c0 + c1 + d2;
+            if (s < W && idx != 0xffffffffu) {
+              const uint4 e = __ldg(b.fent + (size_t)h0.x + idx);
+              acc_add(P0, e.x); acc_add(P1, e.y); acc_add(P2, e.z); acc_add(P3, e.w);
+            }
+            if (++nin == (1 << ACC_PLANES) - 1) {
+              if (live) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
+              nin = 0;
+            }
+          }
+          if (nin && live) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
+        }
+        __syncthreads();
+        // ---- (C) sum the subsets and credit the rows: depth += COV + QRK, errors += MIS + QRK
+        if (q < Q && s < W) {
+          const int Qu = min(Q, rl);   // subsets that hold counts
+          for (int j = q; j < 32; j += Q) {
+            // position j of the entry = nibble (j & 7) of word (j >> 3): counter pair index f*16 + (j >> 1), half = j & 1
+            int cov = 0, qrk = 0, mis = 0;
+            const int sh = (j & 1) * 16;
+            for (int qq = 0; qq < Qu; qq++) {
+              const uint32_t* oc = sm.cnt + qq * Wpad + s;
+              cov += (oc[(0 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
+              qrk += (oc[(1 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
+              mis += (oc[(2 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
+            }
+            const int pos = (int)myw * 32 + j;
+            if (pos < c.stride) {
+              if (cov + qrk) atomicAdd(row_dep + pos, cov + qrk);
+              if (mis + qrk) atomicAdd(row_err + pos, mis + qrk);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      i0 = i1;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace npt

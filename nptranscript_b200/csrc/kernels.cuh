@@ -48,7 +48,7 @@ constexpr int TILE_W = 20;        // words per lane tile: five 16-byte chunks fe
 constexpr int STEP_WINS = 4;      // 8-base windows compared per loop iteration
 constexpr int STEP_BASES = 8 * STEP_WINS;
 constexpr int DEL_HIST = 4;        // deletion lengths recorded in the per-length histogram rows (coverage arrays 4..7)
-constexpr int COV_ARRAYS = 4 + DEL_HIST;
+constexpr int COV_ARRAYS = 4 + DEL_HIST + 1;  // + absolute depth credited by accumulate_kernel (fastcov.cuh)
 constexpr int TILE_STRIDE = 20;   // 80 bytes: keeps every lane tile 16-byte aligned for cp.async
 
 template <typename T>
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           b.read_en[r] = (alnEnd > 0 && maxEnd == alnEnd) ? (alnEnd < eBs ? 0 : alnEnd - eBs + eRs) : 0;
           b.maps_sum[r] = c.record_depth ? maps : 0;
           b.err_sum[r] = c.record_depth ? errs : 0;
-          b.rflags[r] = 0;
+          b.rflags[r] = b.fast ? 0x20u : 0u;
           if (nb > MAX_BREAKS) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_TOO_MANY_BREAKS);
         }
         if (MODE == 1) {
@@ -204,7 +204,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       {
         bool ok = true;
         r = (long long)atomicAdd(cursor, 1u);
-        if (r >= b.n) { done = true; ok = false; }
+        if (b.fast) {   // only the reads the fast walk handed over (fastwalk.cuh)
+          if (r >= (long long)ldcg(b.bctr + 7)) { done = true; ok = false; r = 0; }
+          else r = (long long)b.slow_list[r];
+        } else if (r >= b.n) { done = true; ok = false; }
         if (ok && MODE == 2 && b.nbreaks[r] <= BRK_INLINE) ok = false;
         if (ok && MODE == 1) {
           const int slot = b.cluster[r];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           }
         }
         if (ok && alnStart <= 0) {  // not a mapped record
-          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+          if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = b.fast ? 0x30u : 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
           ok = false;
         }
         if (ok) {
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       ckg++;
       const int len = (int)(w >> 4), op = (int)(w & 15);
       if (op > 8) {  // the reference throws (IdentityProfile1.java:577-578): record not clustered
-        if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
+        if (MODE == 0) { b.nbreaks[r] = 0; b.rflags[r] = b.fast ? 0x30u : 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu; }
         active = false;
       } else {
         const bool isDX = (op == 2) | (op == 8), isEQ = op == 7;
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       const int nE = max(0, min(len, G - ref0));
       if (MODE == 0 && nE > 0 && (long long)read0 + nE > nbases) {
         // the reference's readSeq.getBase runs past the end of the read and throws (IdentityProfile1.java:531-551): not clustered
-        b.nbreaks[r] = 0; b.rflags[r] = 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu;
+        b.nbreaks[r] = 0; b.rflags[r] = b.fast ? 0x30u : 0x10u; b.read_st[r] = 0; b.read_en[r] = 0; b.maps_sum[r] = 0; b.err_sum[r] = 0; b.break_loc[r] = 0xFFFFFFFFu;
         active = false;
       }
       maps += nE;
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
       }
     }
   }
-  if (MODE == 0 && slow_windows) atomicAdd(c.counters + CN_SLOW, (unsigned)slow_windows);
+  if (MODE == 0 && slow_windows && !b.fast) atomicAdd(c.counters + CN_SLOW, (unsigned)slow_windows);
 }
 
 // ------------------------------------------------------------------------------------------------ firstIsTranscriptome
@@ -666,6 +669,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) clust
   __syncthreads();
 
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
+    const unsigned slowbit = b.rflags[r] & 0x20u;  // diagnostic: walked by the serial path
     if (b.rflags[r] & 0x10u) {  // bad record: not clustered
       b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0;
       continue;
@@ -674,6 +678,11 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) clust
     unsigned loc = b.break_loc[r];
     int* br = (loc == 0xFFFFFFFFu) ? b.break_arena + r * BRK_INLINE : b.break_arena + b.n * BRK_INLINE + loc;
     const int src = b.src[r];
+    if (src >= c.S) {  // a source index outside the configuration: the reference would throw; reported as NPT_EINVAL
+      atomicOr(c.counters + CN_ERROR, (unsigned)ERR_BAD_SRC);
+      b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0; b.rflags[r] = 0x10u | slowbit;
+      continue;
+    }
     const bool neg = (b.flag[r] & 0x10) != 0;
     // ---- small first/last exon removal (IdentityProfile1.java:205-228), host mode only: drops the first and/or last pair
     if (c.min_fl_exon > 0 && nb > 2) {
@@ -726,7 +735,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) clust
         }
       }
       if (tree_bin) {  // a real tree bin (> 10 fully colliding names in one read): iteration order not restated, record dropped
-        b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0; b.rflags[r] = 0x10u;
+        b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0; b.rflags[r] = 0x10u | slowbit;
         continue;
       }
       if (ng > 0) {
@@ -826,7 +835,7 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) clust
       }
     }
     b.cluster[r] = cl_slot; b.sub[r] = sb_slot; b.start_pos[r] = startPos; b.end_pos[r] = endPos;
-    b.rflags[r] = (unsigned)type_ind | (leader ? 4u : 0u) | (neg ? 8u : 0u);
+    b.rflags[r] = (unsigned)type_ind | (leader ? 4u : 0u) | (neg ? 8u : 0u) | slowbit;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x) if (s_cnt[i]) atomicAdd(c.small + i, s_cnt[i]);

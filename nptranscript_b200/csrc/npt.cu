@@ -15,6 +15,7 @@
 #include "../../include/npt.h"
 #include "npt_device.cuh"
 #include "kernels.cuh"
+#include "fastcov.cuh"
 
 using namespace npt;
 
@@ -68,6 +69,14 @@ struct Batch {
   int staging = -1;           // index into ctx->stg, or -1 for caller-owned device memory
   bool retired = false;
   cudaEvent_t done = nullptr;
+  // fast walk scratch (returned to the pool when the batch retires): slow list, headers, entry arena, sort keys / values
+  void* f_slow = nullptr; size_t f_slow_bytes = 0;
+  void* f_hdr = nullptr; size_t f_hdr_bytes = 0;
+  void* f_ent = nullptr; size_t f_ent_bytes = 0;
+  void* f_sort = nullptr; size_t f_sort_bytes = 0;   // keys, vals, sorted keys, sorted vals, cub temp
+  unsigned *k_in = nullptr, *v_in = nullptr, *k_out = nullptr, *v_out = nullptr;
+  void* cub_tmp = nullptr; size_t cub_bytes = 0;
+  int key_bits = 0;
 };
 
 }  // namespace
@@ -97,6 +106,11 @@ struct npt_ctx {
   DBuf<unsigned long long> d_sub_sums, d_sub_min0;
   int walk_blocks[3] = {0, 0, 0};   // grid sizes of walk_kernel<0/1/2>
   size_t walk_smem = 0, cluster_smem = 0;
+  // fast walk (fastwalk.cuh / fastcov.cuh)
+  DBuf<uint32_t> d_refg;
+  bool fast = false, fast_record = false;
+  int fw_blocks = 0, fw_threads = 0, acc_blocks = 0;
+  size_t fw_smem = 0;
   DBuf<PairEntry> d_pr;
   DBuf<int> d_cov, d_cov_out;
   DBuf<int> d_small;
@@ -121,6 +135,7 @@ struct npt_ctx {
   int cov_rows = 0;           // rows of d_cov_out (n_clusters, or n_global after npt_remap_clusters)
   int64_t n_pairs = 0;
   int64_t n_total = 0;
+  int64_t n_slow = 0;            // reads the fast walk handed to the serial walker (this chromosome)
   long long total_breaks = 0;
   DBuf<long long> d_ex_first;
   DBuf<unsigned> d_ex_u[5];
@@ -153,8 +168,8 @@ struct npt_ctx {
   float walk_ms = 0, fin_ms = 0;
   int64_t walk_launches = 0, total_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> walk_events;
-  std::vector<cudaEvent_t> stage_events;  // 5 per batch: before walk<0>, after walk<0>, after walk<2>, after cluster, after walk<1>
-  float stage_ms[4] = {0, 0, 0, 0};
+  std::vector<cudaEvent_t> stage_events;  // 7 per batch: before / after fast walk, walk<0>, walk<2>, cluster, walk<1>, coverage (keys + sort + accumulate)
+  float stage_ms[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -350,14 +365,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
   __syncthreads();
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < stride; base += SCAN_THREADS * SCAN_ITEMS) {
-    int v[SCAN_ITEMS];
+    int v[SCAN_ITEMS], absd[SCAN_ITEMS];   // absd: depth credited as absolute counts by accumulate_kernel (array 8)
     int sum = 0;
     const int i0 = base + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; j++) {
       int x = 0;
+      absd[j] = 0;
       if (i0 + j < stride) {
         x = in[i0 + j];
+        absd[j] = cov[8 * arr_stride + rowoff + i0 + j];
         for (int l = 1; l <= DEL_HIST; l++) x += -dh(l, i0 + j) + 2 * dh(l, i0 + j - l) - dh(l, i0 + j - 2 * l);
       }
       v[j] = x; sum += v[j]; v[j] = sum;
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
     const int carry = carry_s;
     const int excl = carry + woff + incl - sum;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; j++) if (i0 + j < stride) o[i0 + j] = excl + v[j];
+    for (int j = 0; j < SCAN_ITEMS; j++) if (i0 + j < stride) o[i0 + j] = excl + v[j] + absd[j];
     __syncthreads();
     if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + sum;
     __syncthreads();
@@ -381,38 +398,70 @@ __global__ void __launch_bounds__(SCAN_THREADS) coverage_rows_kernel(const int* 
 
 // The per-batch kernel sequence on the compute stream.  from_stage: 0 = everything, 1 = from the store-all pass on
 // (used when the overflow area of a batch had to be enlarged).
-int launch_batch(npt_ctx* ctx, const BatchDev& bd, int from_stage) {
+int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
+  const BatchDev& bd = B.d;
   const DevCfg& dc = ctx->dc;
   const int T = WALK_THREADS;
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[7];
   for (auto& e : ev) { CK(cudaEventCreate(&e)); ctx->stage_events.push_back(e); }
   CK(cudaEventRecord(ev[0], ctx->s_comp));
+  // ---- the fast walk: every read it can restate exactly (breaks, read offsets, coverage entries); the others go to slow_list
+  if (bd.fast && from_stage == 0) {
+    const bool rec = ctx->fast_record;
+    if (ctx->ref_smem) {
+      if (rec) fast_walk_kernel<true, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+      else fast_walk_kernel<true, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+    } else {
+      if (rec) fast_walk_kernel<false, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+      else fast_walk_kernel<false, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+    }
+    ctx->total_launches++;
+  }
+  CK(cudaEventRecord(ev[1], ctx->s_comp));
+  // ---- the exact serial walker (all reads when the fast walk is off, else the reads of slow_list)
   if (ctx->ref_smem) {
     if (from_stage == 0) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    CK(cudaEventRecord(ev[1], ctx->s_comp));
+    CK(cudaEventRecord(ev[2], ctx->s_comp));
     walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   } else {
     if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    CK(cudaEventRecord(ev[1], ctx->s_comp));
+    CK(cudaEventRecord(ev[2], ctx->s_comp));
     walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
   }
-  CK(cudaEventRecord(ev[2], ctx->s_comp));
+  CK(cudaEventRecord(ev[3], ctx->s_comp));
   const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
   cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
-  CK(cudaEventRecord(ev[3], ctx->s_comp));
+  CK(cudaEventRecord(ev[4], ctx->s_comp));
   ctx->total_launches += from_stage == 0 ? 3 : 2;
   if (dc.record_depth) {
     if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     else walk_kernel<1, false><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     ctx->total_launches++;
   }
-  CK(cudaEventRecord(ev[4], ctx->s_comp));
+  CK(cudaEventRecord(ev[5], ctx->s_comp));
+  if (dc.record_depth && bd.fast) {
+    // coverage of the fast reads: key = (coverage row, source) -> radix sort -> positional popcount per group
+    const int kgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + 255) / 256, (long long)ctx->sm_count * 16));
+    cov_key_kernel<<<kgrid, 256, 0, ctx->s_comp>>>(dc, bd, B.k_in, B.v_in);
+    size_t tmp = B.cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(B.cub_tmp, tmp, B.k_in, B.k_out, B.v_in, B.v_out, (int)bd.n, 0, B.key_bits, ctx->s_comp));
+    accumulate_kernel<<<ctx->acc_blocks, ACC_THREADS, sizeof(AccSmem), ctx->s_comp>>>(dc, bd, B.k_out, B.v_out, bd.bctr + 6);
+    ctx->total_launches += 2 + (B.key_bits + 7) / 8 + 1;
+  }
+  CK(cudaEventRecord(ev[6], ctx->s_comp));
   CK(cudaGetLastError());
   return NPT_OK;
 }
 
 cudaError_t pool_get(npt_ctx* ctx, void** out, size_t bytes, size_t* got);
 void pool_put(npt_ctx* ctx, void* p, size_t bytes);
+
+// the fast walk's per-batch scratch is dead once the batch's kernels have run
+void release_scratch(npt_ctx* ctx, Batch& B) {
+  if (B.f_hdr) { pool_put(ctx, B.f_hdr, B.f_hdr_bytes); B.f_hdr = nullptr; }
+  if (B.f_ent) { pool_put(ctx, B.f_ent, B.f_ent_bytes); B.f_ent = nullptr; }
+  if (B.f_sort) { pool_put(ctx, B.f_sort, B.f_sort_bytes); B.f_sort = nullptr; }
+}
 
 int retire_batch(npt_ctx* ctx, size_t bi) {
   Batch& B = ctx->batches[bi];
@@ -429,15 +478,17 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
     size_t bigger_bytes = 0;
     CK(pool_get(ctx, (void**)&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int), &bigger_bytes));
     CK(cudaMemcpyAsync(bigger, B.d.break_arena, (size_t)B.n * BRK_INLINE * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
-    CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
+    CK(cudaMemsetAsync(B.bctr, 0, 7 * sizeof(unsigned), ctx->s_comp));  // [7] = reads in slow_list stays
     CK(cudaStreamSynchronize(ctx->s_comp));
     pool_put(ctx, B.d.break_arena, B.arena_bytes);
     B.d.break_arena = bigger; B.d.break_cap = need; B.arena_bytes = bigger_bytes;
-    int rc = launch_batch(ctx, B.d, 1);
+    int rc = launch_batch(ctx, B, 1);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_comp));
   }
+  release_scratch(ctx, B);
   if (B.staging >= 0) { ctx->stg[B.staging].busy = false; ctx->stg[B.staging].batch_index = -1; }
+  if (B.d.fast) ctx->n_slow += h[7];
   B.retired = true;
   return NPT_OK;
 }
@@ -461,6 +512,8 @@ void free_batches(npt_ctx* ctx) {
     pool_put(ctx, B.out_block, B.out_bytes);
     pool_put(ctx, B.d.break_arena, B.arena_bytes);
     pool_put(ctx, B.bctr, B.bctr_bytes);
+    release_scratch(ctx, B);
+    if (B.f_slow) pool_put(ctx, B.f_slow, B.f_slow_bytes);
     if (B.done) cudaEventDestroy(B.done);
   }
   ctx->batches.clear();
@@ -488,6 +541,7 @@ int npt_create(const npt_config* cfg, npt_ctx** out) {
   if (cfg->num_sources < 1 || cfg->num_sources > NPT_MAX_SOURCES) return fail(nullptr, NPT_EINVAL, "num_sources out of range");
   if (cfg->bin < 1) return fail(nullptr, NPT_EINVAL, "bin must be >= 1");
   if (cfg->break_thresh < 0) return fail(nullptr, NPT_EINVAL, "break_thresh must be >= 0");
+  if (cfg->max_clusters > (1 << 24)) return fail(nullptr, NPT_EINVAL, "max_clusters is limited to 2^24 (cluster rank and first index share one 64-bit sort key)");
   if (cfg->coronavirus)
     for (int s = 0; s < cfg->num_sources; s++)
       if (!cfg->rna[s])
@@ -522,7 +576,7 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();
-  ctx->d_ref.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
+  ctx->d_ref.release(); ctx->d_refg.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
   ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
@@ -565,6 +619,11 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   if (annot->kind == NPT_ANNOT_CSV && cf.coronavirus && annot->n < 2)
     return fail(ctx, NPT_EINVAL, "coronavirus mode needs >= 2 annotation rows (Annotation.isLeader reads start.get(1), Annotation.java:214-216)");
   if (annot->n < 0 || annot->n > (gff ? (1 << 22) : 4096)) return fail(ctx, NPT_EINVAL, "annotation rows out of range");
+  if (!cf.coronavirus && annot->kind == NPT_ANNOT_EMPTY)
+    for (int s = 0; s < cf.num_sources; s++)
+      if (!cf.rna[s])
+        return fail(ctx, NPT_EINVAL, "host mode with EmptyAnnotation needs rna[src]=1: the reference passes a null Boolean to "
+                    "EmptyAnnotation.nextUpstream(int,int,boolean) and throws (IdentityProfile1.java:293-299, EmptyAnnotation.java:22)");
   if (gff) for (int i = 0; i < annot->n; i++) if (annot->name_id[i] < 0 || annot->name_id[i] >= annot->n) return fail(ctx, NPT_EINVAL, "name_id out of range");
   const int n_orf = gff ? 0 : annot->n;  // ORF rows (shared-memory tables, spliced/unspliced counters): CSV only
   const bool calc_breaks1 = cf.calc_breaks && cf.coronavirus && (int64_t)cf.break_thresh < ref_len;  // ViralTranscriptAnalysisCmd2.java:882
@@ -576,7 +635,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   ctx->in_chrom = true; ctx->finalized = false;
   ctx->chrom_index = chrom_index; ctx->G = ref_len; ctx->n_orf = n_orf;
   ctx->idx_base = ctx->idx_user_base;
-  ctx->walk_ms = ctx->fin_ms = 0; ctx->walk_launches = ctx->total_launches = 0;
+  ctx->walk_ms = ctx->fin_ms = 0; ctx->walk_launches = ctx->total_launches = 0; ctx->n_slow = 0;
 
   CK(cudaEventRecord(ctx->ev_c0, ctx->s_comp));
   DevCfg& dc = ctx->dc;
@@ -596,6 +655,15 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(ctx->d_ref.ensure(nwords));
   CK(cudaMemcpy(ctx->d_ref.p, words.data(), (size_t)nwords * 4, cudaMemcpyHostToDevice));
   dc.ref_words = ctx->d_ref.p; dc.ref_nwords = nwords;
+  {
+    // the same bases on the position grid of the fast walk: word W = positions 8W..8W+7 (1-based), first in the top nibble
+    const int gwords = (int)(ref_len >> 3) + 1 + 4;
+    std::vector<uint32_t> gw(gwords, 0);
+    for (int64_t i = 0; i < ref_len; i++) { const int64_t p = i + 1; gw[p >> 3] |= (uint32_t)(ref_codes[i] & 0xF) << (28 - 4 * (p & 7)); }
+    CK(ctx->d_refg.ensure(gwords));
+    CK(cudaMemcpy(ctx->d_refg.p, gw.data(), (size_t)gwords * 4, cudaMemcpyHostToDevice));
+    dc.refg_words = ctx->d_refg.p; dc.refg_nwords = gwords;
+  }
   CK(ctx->d_ostart.ensure(n_orf)); CK(ctx->d_oname.ensure(n_orf)); CK(ctx->d_ostrand.ensure(n_orf));
   if (n_orf) {
     CK(cudaMemcpy(ctx->d_ostart.p, annot->start, (size_t)n_orf * 4, cudaMemcpyHostToDevice));
@@ -693,6 +761,36 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
     }
     ctx->walk_blocks[2] = ctx->sm_count;  // the store-all pass only touches the rare long-break-list reads
   }
+  {
+    // fast walk: tasks are 16 positions, so a break can only hide inside one when break_thresh < 16; with depth recording the
+    // reference-grid entries of a chromosome must fit accumulate_kernel's shared tables.  Otherwise: serial walker for all.
+    ctx->fast_record = cf.record_depth != 0;
+    ctx->fast = cf.break_thresh >= FW_TASK_MAX && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
+    if (const char* e = getenv("NPT_FAST")) if (atoi(e) == 0) ctx->fast = false;   // experiments / A-B runs
+    if (ctx->fast) {
+      const size_t refb = ctx->ref_smem ? (size_t)((dc.refg_nwords + 3) & ~3) * 4 : 0;
+      const size_t per_warp = (size_t)fw_warp_words(ctx->fast_record) * 4;
+      int warps = (int)std::min<size_t>(FW_WARPS_MAX, (ctx->smem_optin - refb - 64) / per_warp);
+      if (warps < 1) ctx->fast = false;
+      else {
+        ctx->fw_threads = warps * 32;
+        ctx->fw_smem = refb + (size_t)warps * per_warp;
+        int occ = 1;
+        if (ctx->ref_smem) {
+          if (ctx->fast_record) { CK(cudaFuncSetAttribute(fast_walk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_walk_kernel<true, true>, ctx->fw_threads, ctx->fw_smem)); }
+          else { CK(cudaFuncSetAttribute(fast_walk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_walk_kernel<true, false>, ctx->fw_threads, ctx->fw_smem)); }
+        } else {
+          if (ctx->fast_record) { CK(cudaFuncSetAttribute(fast_walk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_walk_kernel<false, true>, ctx->fw_threads, ctx->fw_smem)); }
+          else { CK(cudaFuncSetAttribute(fast_walk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_walk_kernel<false, false>, ctx->fw_threads, ctx->fw_smem)); }
+        }
+        ctx->fw_blocks = ctx->sm_count * std::max(1, occ);
+        if (ctx->fast_record) {
+          CK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
+          ctx->acc_blocks = ctx->sm_count;
+        }
+      }
+    }
+  }
   CK(cudaStreamSynchronize(ctx->s_comp));
   return NPT_OK;
 }
@@ -709,6 +807,7 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   B.n = n;
   BatchDev& d = B.d;
   d.n = n; d.idx_base = ctx->idx_base;
+  const uint16_t* host_src = nullptr;
 
   if (b->location == NPT_MEM_HOST) {
     const uint32_t ncig = b->cigar_off[n];
@@ -731,14 +830,15 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     unsigned char* base = S.buf.p;
     CK(cudaMemcpyAsync(base + o_pos, b->pos, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_copy));
     CK(cudaMemcpyAsync(base + o_flag, b->flag, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
-    CK(cudaMemcpyAsync(base + o_src, b->src, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
     CK(cudaMemcpyAsync(base + o_coff, b->cigar_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->s_copy));
     if (ncig) CK(cudaMemcpyAsync(base + o_cig, b->cigar, (size_t)ncig * 4, cudaMemcpyHostToDevice, ctx->s_copy));
     CK(cudaMemcpyAsync(base + o_soff, b->seq_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
     if (nseq) CK(cudaMemcpyAsync(base + o_seq, b->seq4, (size_t)nseq, cudaMemcpyHostToDevice, ctx->s_copy));
     CK(cudaEventRecord(S.done, ctx->s_copy));
     CK(cudaStreamWaitEvent(ctx->s_comp, S.done, 0));
-    d.pos = (const int*)(base + o_pos); d.flag = (const uint16_t*)(base + o_flag); d.src = (const uint16_t*)(base + o_src);
+    d.pos = (const int*)(base + o_pos); d.flag = (const uint16_t*)(base + o_flag);
+    host_src = b->src;   // copied below into the batch's own output block: fit_fixup_kernel reads it at end of chromosome,
+                         // long after this staging buffer has been handed to a later batch
     d.cigar_off = (const uint32_t*)(base + o_coff); d.cigar = (const uint32_t*)(base + o_cig);
     d.seq_off = (const unsigned long long*)(base + o_soff); d.seq4 = base + o_seq; d.seq_bytes = (long long)nseq; d.cigar_words = (long long)ncig;
     S.busy = true; S.batch_index = (int)ctx->batches.size();
@@ -757,9 +857,16 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     return fail(ctx, NPT_EINVAL, "unknown batch location");
   }
 
-  // per-read outputs: 11 int arrays in one block + break arena
-  CK(pool_get(ctx, &B.out_block, (size_t)n * 11 * 4, &B.out_bytes));
+  // per-read outputs: 11 int arrays (+ the source indices of a host batch) in one block + break arena
+  CK(pool_get(ctx, &B.out_block, (size_t)n * 11 * 4 + (size_t)n * 2 + 16, &B.out_bytes));
   int* ob = (int*)B.out_block;
+  if (host_src) {
+    uint16_t* keep = (uint16_t*)(ob + 11 * n);
+    CK(cudaMemcpyAsync(keep, host_src, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaEventRecord(ctx->stg[B.staging].done, ctx->s_copy));
+    CK(cudaStreamWaitEvent(ctx->s_comp, ctx->stg[B.staging].done, 0));
+    d.src = keep;
+  }
   d.cluster = ob; d.sub = ob + n; d.start_pos = ob + 2 * n; d.end_pos = ob + 3 * n; d.read_st = ob + 4 * n; d.read_en = ob + 5 * n;
   d.rflags = (unsigned*)(ob + 6 * n); d.maps_sum = ob + 7 * n; d.err_sum = ob + 8 * n; d.nbreaks = ob + 9 * n; d.break_loc = (unsigned*)(ob + 10 * n);
   d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n / 4, 4096), 1LL << 30);
@@ -767,13 +874,37 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   CK(pool_get(ctx, (void**)&B.bctr, 8 * sizeof(unsigned), &B.bctr_bytes));
   CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
   d.bctr = B.bctr;
+  // fast walk: work list of the serial walker; with depth recording also headers, the entry arena (16 bytes per 32 reference
+  // positions a read covers: its share is (bytes of bases / 16) + 8 entries) and the sort buffers
+  d.fast = ctx->fast ? 1 : 0;
+  if (d.fast && ctx->fast_record && ((uint64_t)d.seq_bytes >> 4) + 8ull * (uint64_t)n + 8 >= (1ull << 32)) d.fast = 0;  // entry index is 32 bits
+  if (d.fast) {
+    CK(pool_get(ctx, &B.f_slow, (size_t)n * 4, &B.f_slow_bytes));
+    d.slow_list = (unsigned*)B.f_slow;
+    if (ctx->fast_record) {
+      const size_t n_ent = ((size_t)d.seq_bytes >> 4) + 8 * (size_t)n + 8;
+      CK(pool_get(ctx, &B.f_hdr, (size_t)n * FW_HDR_WORDS * 4, &B.f_hdr_bytes));
+      CK(pool_get(ctx, &B.f_ent, n_ent * 16, &B.f_ent_bytes));
+      d.fhdr = (unsigned*)B.f_hdr; d.fent = (uint4*)B.f_ent;
+      unsigned maxkey = (unsigned)ctx->dc.cov_cap * (unsigned)ctx->dc.S;
+      B.key_bits = 1;
+      while ((1ull << B.key_bits) <= maxkey) B.key_bits++;
+      size_t tmp = 0;
+      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (int)n, 0, B.key_bits, ctx->s_comp));
+      const size_t an = ((size_t)n * 4 + 255) & ~(size_t)255;
+      CK(pool_get(ctx, &B.f_sort, 4 * an + tmp + 256, &B.f_sort_bytes));
+      unsigned char* sb = (unsigned char*)B.f_sort;
+      B.k_in = (unsigned*)sb; B.v_in = (unsigned*)(sb + an); B.k_out = (unsigned*)(sb + 2 * an); B.v_out = (unsigned*)(sb + 3 * an);
+      B.cub_tmp = sb + 4 * an; B.cub_bytes = tmp;
+    }
+  }
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, ctx->s_comp));
-  int rc = launch_batch(ctx, d, 0);
+  int rc = launch_batch(ctx, B, 0);
   if (rc) return rc;
-  ctx->walk_launches += ctx->dc.record_depth ? 4 : 3;
+  ctx->walk_launches += (ctx->dc.record_depth ? 4 : 3) + (d.fast ? 1 : 0);
   CK(cudaEventRecord(e1, ctx->s_comp));
   ctx->walk_events.emplace_back(e0, e1);
   CK(cudaEventCreateWithFlags(&B.done, cudaEventDisableTiming));
@@ -826,9 +957,9 @@ int npt_end_chrom(npt_ctx* ctx) {
   // walk time = sum over batches of the kernel's event span
   ctx->walk_ms = 0;
   for (auto& e : ctx->walk_events) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); ctx->walk_ms += ms; }
-  for (int k = 0; k < 4; k++) ctx->stage_ms[k] = 0;
-  for (size_t i = 0; i + 5 <= ctx->stage_events.size(); i += 5)
-    for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->stage_events[i + k], ctx->stage_events[i + k + 1])); ctx->stage_ms[k] += ms; }
+  for (int k = 0; k < 6; k++) ctx->stage_ms[k] = 0;
+  for (size_t i = 0; i + 7 <= ctx->stage_events.size(); i += 7)
+    for (int k = 0; k < 6; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->stage_events[i + k], ctx->stage_events[i + k + 1])); ctx->stage_ms[k] += ms; }
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof ctx->h_counters, cudaMemcpyDeviceToHost));
   const unsigned er = ctx->h_counters[CN_ERROR];
   if (er) {
@@ -841,6 +972,7 @@ int npt_end_chrom(npt_ctx* ctx) {
     if (er & ERR_TOO_MANY_BREAKS) m += " a read has more than 2^20 breaks";
     if (er & ERR_GENESET) m += " a read overlaps more than 32 annotated genes";
     ctx->in_chrom = false;
+    if (er & ERR_BAD_SRC) return fail(ctx, NPT_EINVAL, "a record's source index is >= num_sources");
     return fail(ctx, NPT_ECAPACITY, "%s", m.c_str());
   }
   const DevCfg& dc = ctx->dc;
@@ -995,7 +1127,7 @@ int npt_fetch_results(npt_ctx* ctx, int what, npt_results* out) {
   const int64_t n = ctx->n_total;
   R.n_reads = n;
   R.n_clusters = nc; R.n_subs = ns; R.n_orf = dc.n_orf; R.cov_stride = dc.stride;
-  R.n_slow_reads = ctx->h_counters[CN_SLOW];
+  R.n_slow_reads = ctx->fast ? ctx->n_slow : ctx->h_counters[CN_SLOW];
   if (what & NPT_FETCH_READS) {
     const size_t nn = (size_t)std::max<int64_t>(n, 1);
     if (!ctx->r_cluster.ensure(nn) || !ctx->r_sub.ensure(nn) || !ctx->r_start.ensure(nn) || !ctx->r_end.ensure(nn) || !ctx->r_rst.ensure(nn) ||
@@ -1247,9 +1379,9 @@ void* npt_alloc_pinned(size_t bytes) {
 }
 void npt_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
-int npt_last_stage_ms(npt_ctx* ctx, float* out4) {
-  if (!ctx || !out4) return NPT_EINVAL;
-  for (int k = 0; k < 4; k++) out4[k] = ctx->stage_ms[k];
+int npt_last_stage_ms(npt_ctx* ctx, float* out6) {
+  if (!ctx || !out6) return NPT_EINVAL;
+  for (int k = 0; k < 6; k++) out6[k] = ctx->stage_ms[k];
   return NPT_OK;
 }
 

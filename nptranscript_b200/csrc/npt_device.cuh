@@ -17,7 +17,7 @@ enum {
   CN_COUNT
 };
 
-enum { ERR_CL_FULL = 1, ERR_SUB_FULL = 2, ERR_PAIR_FULL = 4, ERR_COV_FULL = 8, ERR_ARENA_FULL = 16, ERR_TOO_MANY_BREAKS = 32, ERR_GENESET = 64 };
+enum { ERR_CL_FULL = 1, ERR_SUB_FULL = 2, ERR_PAIR_FULL = 4, ERR_COV_FULL = 8, ERR_ARENA_FULL = 16, ERR_TOO_MANY_BREAKS = 32, ERR_GENESET = 64, ERR_BAD_SRC = 128 };
 constexpr int GFF_MAX_GENES = 32;  // distinct genes one read may hit (GFF mode)
 
 // Hash-table slot (clusters and sub-clusters): `word` = 0 while empty, else (hash32 << 32) | record offset in the arena.
@@ -47,6 +47,8 @@ struct DevCfg {
   // ---- reference + annotation
   const uint32_t* ref_words;  // 8 bases per word, first base in bits 31..28; padded by 4 words
   int ref_nwords;             // words incl. padding
+  const uint32_t* refg_words; // the same bases on the POSITION grid of the fast walk: word W = positions 8W..8W+7 (1-based,
+  int refg_nwords;            // position 0 is padding), first in the top nibble; padded by 4 words
   const int* orf_start;
   const int* orf_name;
   const uint8_t* orf_strand;
@@ -63,7 +65,8 @@ struct DevCfg {
   unsigned long long* sub_min0;  // [sb slots] firstIsTranscriptome: first global index of a source-0 read of the sub-cluster
   unsigned long long* sub_sums; unsigned sums_cap;
   PairEntry* pr; unsigned pr_mask; int pr_cap;
-  int* cov; int cov_cap;     // [8][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd, deletions of length 1..4 by first deleted position
+  int* cov; int cov_cap;     // [9][cov_cap][S][stride]: depth-diff, errors, mapStart, mapEnd, deletions of length 1..4 by first deleted
+                             // position (serial walker), absolute depth credited by accumulate_kernel (fast walk)
   int* small;                // total_counts[S], spliced[S][n_orf], unspliced[S][n_orf]
   unsigned* counters;
 };
@@ -85,7 +88,14 @@ struct BatchDev {
   int* maps_sum; int* err_sum; int* nbreaks; unsigned* break_loc;
   int* break_arena;     // [n][BRK_INLINE] inline slots, then break_cap ints of overflow area
   unsigned break_cap;
-  unsigned* bctr;       // per batch: [0] overflow-area cursor, [1] overflow-area full flag, [2..4] read cursors of walk_kernel<0/1/2>
+  unsigned* bctr;       // per batch: [0] overflow-area cursor, [1] overflow-area full flag, [2..4] read cursors of walk_kernel<0/1/2>,
+                        // [5] read cursor of fast_walk_kernel, [6] tile cursor of accumulate_kernel, [7] reads in slow_list
+  // fast walk (fastwalk.cuh): when `fast` is set every read is first offered to fast_walk_kernel and only the reads it lists
+  // in slow_list are walked by walk_kernel<0/1/2>
+  int fast;
+  unsigned* slow_list;  // [n] read indices flagged NPT_RF_SLOWPATH
+  unsigned* fhdr;       // [n][16] per-read header of the fast walk (blocks of entries, junction points)
+  uint4* fent;          // entry arena: 32 positions x 4 flag bits per entry
 };
 
 }  // namespace npt

@@ -183,10 +183,10 @@ class Engine:
         self._ck(self.L.npt_last_kernel_ms(self.h, C.byref(w), C.byref(f), C.byref(wl), C.byref(tl)))
         st = C.c_float()
         self._ck(self.L.npt_last_step_ms(self.h, C.byref(st)))
-        stg = (C.c_float * 4)()
+        stg = (C.c_float * 6)()
         self._ck(self.L.npt_last_stage_ms(self.h, stg))
         return dict(walk_ms=w.value, finalize_ms=f.value, walk_launches=wl.value, total_launches=tl.value, step_ms=st.value,
-                    walk0_ms=stg[0], walk2_ms=stg[1], cluster_ms=stg[2], walk1_ms=stg[3])
+                    fastwalk_ms=stg[0], walk0_ms=stg[1], walk2_ms=stg[2], cluster_ms=stg[3], walk1_ms=stg[4], fastcov_ms=stg[5])
 
     def device_view(self):
         v = abi.npt_device_view()

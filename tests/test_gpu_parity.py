@@ -27,6 +27,36 @@ def test_sars2_20k(depth):
     assert dev["n_slow_reads"] < 5 * 20000  # exact per-base windows (junction windows): a diagnostic, ~1 per read
 
 
+def test_config2_flags_200k():
+    """the benchmark's own flag set (bin=100, breakThresh=1000, depth recording) on 200 k reads"""
+    w = workloads.SARS2
+    b = synth.generate(w, 20200302, 200000)
+    dev, ora = _both(dict(bin=100, break_thresh=1000, record_depth=1), w, [b])
+    assert_same(dev, ora)
+    assert 0 < dev["n_slow_reads"] < 0.02 * 200000   # the fast walk took (nearly) all of them
+
+
+def test_first_is_transcriptome_many_host_batches():
+    """firstIsTranscriptome + break sums with four host batches of different sizes: the end-of-chromosome fix-up reads the
+    source index of every read long after the staging buffers were handed to later batches"""
+    w = workloads.SARS2
+    sizes = [3000, 7000, 1500, 5000]
+    bs, first = [], 0
+    for k, n in enumerate(sizes):
+        bs.append(synth.generate(w, 77, n, first_index=first, num_sources=2))
+        first += n
+    dev, ora = _both(dict(bin=10, break_thresh=1000, record_depth=1, num_sources=2, rna=[1, 1], first_is_transcriptome=1), w, bs)
+    assert_same(dev, ora)
+
+
+def test_bad_source_index_is_an_error():
+    w = workloads.SARS2
+    b = synth.generate(w, 3, 500, num_sources=3)   # src in 0..2, configuration says 2 sources
+    with pytest.raises(engine.NptError) as e:
+        engine.run(engine.make_config(bin=10, num_sources=2, record_depth=1), synth.genome_codes(w), w.annotation, [b])
+    assert e.value.code == abi.NPT_EINVAL
+
+
 def test_multi_batch_and_sources():
     w = workloads.HCOV229E
     bs = [synth.generate(w, 20200310 + k, 5000, first_index=0, num_sources=4, src_fixed=k) for k in range(4)]
@@ -76,8 +106,8 @@ def test_fuzz_bad_ops():
     dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1], first_is_transcriptome=1),  # opts_host.txt
     dict(bin=10, break_thresh=1000, coronavirus=1, record_depth=1, rna=[1, 1], first_is_transcriptome=1),
     dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[1, 1]),
-    dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, rna=[0, 1]),
-    dict(bin=10, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, rna=[1, 0]),
+    dict(bin=10, break_thresh=50, coronavirus=0, include_start=1, record_depth=1, rna=[1, 1]),
+    dict(bin=10, break_thresh=16, coronavirus=0, include_start=1, record_depth=1, rna=[1, 1], enforce_strand=1),
 ])
 def test_fuzz_host_mode_empty_annotation(kw):
     """Host mode (opts_host.txt flag set minus firstIsTranscriptome) with EmptyAnnotation: chr.bin keys, exon trimming."""
@@ -109,6 +139,17 @@ def test_fuzz_host_mode_gff_annotation(kw, collide):
     assert_same(dev, ora)
     toks = dev["cl_key_tok"]
     assert (toks == abi.NPT_TOK_GENESET).sum() > 20 and dev["n_clusters"] > (toks == abi.NPT_TOK_GENESET).sum()
+
+
+def test_empty_annotation_needs_rna():
+    """coronavirus=0 + EmptyAnnotation + rna[src]=0: the reference unboxes a null Boolean (IdentityProfile1.java:293-299) and
+    throws; the library rejects the combination instead of inventing semantics"""
+    w = workloads.SARS2
+    for rna in ([0, 1], [1, 0]):
+        with pytest.raises(engine.NptError) as e:
+            engine.run(engine.make_config(coronavirus=0, num_sources=2, rna=rna), synth.genome_codes(w), workloads.Annotation.empty(),
+                       [synth.generate(w, 1, 10)])
+        assert e.value.code == abi.NPT_EINVAL
 
 
 def test_gff_needs_host_mode():
