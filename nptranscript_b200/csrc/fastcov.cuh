@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
       srcC[lane] = needC ? ncs + 1u : 0u;
       const long long ntb = (long long)((L.so + (unsigned long long)(L.readPos >> 1)) & ~15ull);
       const bool needS = live && ntb != L.tb;
-      if (needS) L.tb = ntb;
+      if (needS) { L.tb = ntb; L.tnib0 = (int)(2 * (ntb - (long long)L.so)); }
       srcS[lane] = needS ? (unsigned long long)ntb + 1ull : 0ull;
       __syncwarp();
 #pragma unroll
@@ -141,8 +141,13 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
         const int sp = b.start_pos[r], ep = b.end_pos[r];
         if (sp >= 0 && sp < c.stride) atomicAdd(mstart + sp, 1);
         if (ep >= 0 && ep < c.stride) atomicAdd(mend + ep, 1);
-        const uint4 h0 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS));
-        const int njunc = (h0.y >> 8) & 0xFF, nextra = (h0.y >> 16) & 0xFF;
+        const unsigned meta = __ldg(b.fhdr + r * FW_HDR_WORDS + 4);
+        const int njunc = (meta >> 8) & 0xFF, nextra = (meta >> 16) & 0xFF, ndbl = (meta >> 24) & 0xFF;
+        for (int d = 0; d < ndbl; d++) {   // positions emitted by two D elements
+          const unsigned q = __ldg(b.fhdr + r * FW_HDR_WORDS + 5 + d);
+          atomicAdd(cov + 8 * arr_stride + q, 1);
+          atomicAdd(cov + arr_stride + q, 1);
+        }
         if (njunc | nextra) {
           const uint4 h2 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 8));
           const uint4 h3 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 12));
@@ -187,6 +192,18 @@ __device__ __forceinline__ void acc_add(uint32_t (&p)[ACC_PLANES], uint32_t x) {
   for (int k = 0; k < ACC_PLANES; k++) { const uint32_t cy = p[k] & x; p[k] ^= x; x = cy; }
 }
 
+// four words at once: carry-save adders (xor3 / majority are one LOP3 each), then the carry of weight 4 ripples up
+__device__ __forceinline__ void acc_add4(uint32_t (&p)[ACC_PLANES], uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const uint32_t s1 = p[0] ^ a ^ b, c1 = (p[0] & a) | (p[0] & b) | (a & b);
+  const uint32_t s2 = s1 ^ c ^ d, c2 = (s1 & c) | (s1 & d) | (c & d);
+  p[0] = s2;
+  const uint32_t t = p[1] ^ c1 ^ c2;
+  uint32_t x = (p[1] & c1) | (p[1] & c2) | (c1 & c2);   // weight 4
+  p[1] = t;
+#pragma unroll
+  for (int k = 2; k < ACC_PLANES; k++) { const uint32_t cy = p[k] & x; p[k] ^= x; x = cy; }
+}
+
 // planes of one entry word -> the thread's 16-bit counters.  Byte lane m of ((plane >> j) & 0x01010101) is bit 8m+j of the
 // word = flag (j & 3) of nibble 7 - 2m - (j >> 2) counted from the top.
 __device__ __forceinline__ void acc_expand(uint32_t (&p)[ACC_PLANES], int k, uint32_t* cnt) {
@@ -225,11 +242,13 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
   for (;;) {
     if (tid == 0) s_tile = (int)atomicAdd(tile_cursor, 1u);
     __syncthreads();
-    const long long t0 = (long long)s_tile * ACC_TILE;
+    const long long n_tiles = (b.n + ACC_TILE - 1) / ACC_TILE;
+    // the tiles with many small groups (late-created clusters sort last) cost the most per read: hand them out first
+    const long long t0 = (n_tiles - 1 - (long long)s_tile) * ACC_TILE;
     __syncthreads();
-    if (t0 >= b.n) break;
+    if (t0 < 0) break;
     const int tn = (int)min((long long)ACC_TILE, b.n - t0);
-    if (__ldg(keys + t0) == invalid) break;   // sorted: nothing left to credit in this and all later tiles
+    if (__ldg(keys + t0) == invalid) continue;   // sorted: this tile holds only reads that are not credited here
     // ---- the tile: read indices into shared memory, head flags of the runs of equal key
     for (int i = tid; i < ACC_TILE; i += ACC_THREADS) {
       bool head = false;
@@ -264,20 +283,17 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
       for (int i = tid; i < rl; i += ACC_THREADS) {
         const unsigned r = sm.vals[i0 + i];
         const uint4 h0 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
-        const uint4 h1 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS + 4));
-        const int nblk = h0.y & 0xFF;
 #pragma unroll
         for (int k = 0; k < FW_MAX_BLOCKS; k++) {
-          if (k < nblk) {
-            const unsigned f = k == 0 ? h0.z : (k == 1 ? h1.x : h1.z), cn = k == 0 ? h0.w : (k == 1 ? h1.y : h1.w);
-            if (cn) {
-              const unsigned lo = f, hi = f + cn - 1;   // entries [lo, hi]
-              for (unsigned w = lo >> 5; w <= (hi >> 5) && w < (unsigned)n_actw; w++) {
-                unsigned m = 0xffffffffu;
-                if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
-                if (w == (hi >> 5)) m &= 0xffffffffu >> (31 - (hi & 31));
-                if ((sm.act[w] & m) != m) atomicOr(&sm.act[w], m);
-              }
+          const unsigned bk = k == 0 ? h0.y : (k == 1 ? h0.z : h0.w);
+          const unsigned f = bk & 0xFFFFu, cn = bk >> 16;
+          if (cn) {
+            const unsigned lo = f, hi = f + cn - 1;   // entries [lo, hi]
+            for (unsigned w = lo >> 5; w <= (hi >> 5) && w < (unsigned)n_actw; w++) {
+              unsigned m = 0xffffffffu;
+              if (w == (lo >> 5)) m &= 0xffffffffu << (lo & 31);
+              if (w == (hi >> 5)) m &= 0xffffffffu >> (31 - (hi & 31));
+              if ((sm.act[w] & m) != m) atomicOr(&sm.act[w], m);
             }
           }
         }
@@ -315,27 +331,43 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
         if (live)
 #pragma unroll
           for (int k = 0; k < ACC_CNT_WORDS; k++) mycnt[k * ACC_THREADS] = 0;
-        uint32_t P0[ACC_PLANES], P1[ACC_PLANES], P2[ACC_PLANES], P3[ACC_PLANES];
+        uint32_t P0[ACC_PLANES], P1[ACC_PLANES], P2[ACC_PLANES], P3[ACC_PLANES];   // [0] ones, [1] twos, [2..] 4s 8s 16s 32s
 #pragma unroll
         for (int k = 0; k < ACC_PLANES; k++) { P0[k] = 0; P1[k] = 0; P2[k] = 0; P3[k] = 0; }
         int nin = 0;
         if (q < Q) {
-          for (int i = q; i < rl; i += Q) {
-            const unsigned r = sm.vals[i0 + i];
-            const uint4 h0 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
-            const uint4 h1 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS + 4));
-            const int nblk = h0.y & 0xFF;
-            const unsigned c0 = nblk > 0 ? h0.w : 0u, c1 = nblk > 1 ? h1.y : 0u, c2 = nblk > 2 ? h1.w : 0u;
-            const unsigned d0 = myw - h0.z, d1 = myw - h1.x, d2 = myw - h1.z;
-            unsigned idx = 0xffffffffu;
-            if (d0 < c0) idx = d0;
-            else if (d1 < c1) idx = c0 + d1;
-            else if (d2 < c2) idx = c0 + c1 + d2;
-            if (s < W && idx != 0xffffffffu) {
-              const uint4 e = __ldg(b.fent + (size_t)h0.x + idx);
-              acc_add(P0, e.x); acc_add(P1, e.y); acc_add(P2, e.z); acc_add(P3, e.w);
+          // four reads per step: their entries for this thread's reference-grid entry go through one carry-save tree
+          // (3 inputs -> sum + carry is two LOP3), and the four header / entry loads are in flight together
+          for (int i = q; i < rl; i += 4 * Q) {
+            uint4 e[4];
+            bool extra = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              e[j] = make_uint4(0u, 0u, 0u, 0u);
+              const int ii = i + j * Q;
+              if (ii < rl && s < W) {
+                const unsigned r = sm.vals[i0 + ii];
+                const uint4 h = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
+                const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
+                const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
+                const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
+                const unsigned idx = in0 ? d0 : (in1 ? c0 + d1 : c0 + c1 + d2);
+                if (in0 || in1 || in2) e[j] = __ldg(b.fent + (size_t)h.x + idx);
+                // blocks of one read can share an entry (an N element shorter than 32 positions): the later blocks' entries
+                // for the same grid entry are added below, one at a time
+                if ((in0 && (in1 || in2)) || (in1 && in2)) {
+                  extra = true;
+                  if (in0 && in1) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + d1); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); }
+                  if ((in0 || in1) && in2) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + c1 + d2); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); }
+                }
+              }
             }
-            if (++nin == (1 << ACC_PLANES) - 1) {
+            acc_add4(P0, e[0].x, e[1].x, e[2].x, e[3].x);
+            acc_add4(P1, e[0].y, e[1].y, e[2].y, e[3].y);
+            acc_add4(P2, e[0].z, e[1].z, e[2].z, e[3].z);
+            acc_add4(P3, e[0].w, e[1].w, e[2].w, e[3].w);
+            nin += __any_sync(0xffffffffu, extra) ? 12 : 4;
+            if (nin + 12 > (1 << ACC_PLANES) - 1) {
               if (live) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
               nin = 0;
             }

@@ -62,8 +62,10 @@ constexpr unsigned FW_MIS = 0x88888888u;   // M position whose base differs from
 
 // per-read header written by the fast walk, read by accumulate_kernel and fast_events_kernel:
 //   [0] index of the read's first entry in the batch's entry arena
-//   [1] nblk | njunc << 8 | nextra << 16
-//   [2+2k], [3+2k]   block k: first entry index on the reference grid (position >> 5), number of entries
+//   [1+k]            block k < 3: first entry index on the reference grid (position >> 5) | number of entries << 16; 0 = no block
+//   [4] nblk | njunc << 8 | nextra << 16 | ndbl << 24
+//   [5+d]            d < 3: a position emitted by two D elements (depth[pos]++, errors[pos]++ on top of the entry's single flag);
+//                    a read's 4th and 5th such position go to the extras as kind 1
 //   [8+2j], [9+2j]   junction j: (prev, pos) = mapEnd[prev]++, mapStart[pos]++
 //   [12+2e],[13+2e]  extra e: kind 0 (bit 31 clear) = emission `pos` more than break_thresh after `prev` that was not a
 //                    match (mapStart[pos]++, mapEnd[prev]++); kind 1 (bit 31 set) = a position emitted by two D elements
@@ -76,11 +78,13 @@ struct FwLane {
   int alnStart, refPos, readPos, mRem, nbases;
   unsigned long long so;        // byte offset of the read's bases in b.seq4
   long long tb;                 // byte offset in b.seq4 of the base tile (16-byte aligned), -1 = nothing staged
+  int tnib0;                    // read base index of the tile's first base (2 * (tb - so), may be negative)
   int st_r, lmRead0, lmLen;     // read offset of the first aligned base; last M element (for the read offset of the alignment end)
   unsigned flags;
-  int nb, nblk, nent, njunc, nextra, errs, maps, nt;
+  int nb, nblk, nent, njunc, nextra, ndbl, errs, maps, nt;
   unsigned pmh, pml; int pp0;   // last match: the last set flag of (pmh:pml), a task's match mask, counted from position pp0
   int maxPos, flushE, blkFirstE;
+  unsigned blk0, blk1, blk2;    // closed blocks: first entry | entries << 16
   unsigned entBase, entCap;
 };
 
@@ -120,14 +124,14 @@ FW_HD void fw_start_read(FwLane& L, const BatchDev& b, long long r) {
   const unsigned long long se = b.seq_off[r + 1];
   const unsigned long long nb2 = 2ull * (se - L.so);
   L.nbases = (int)(nb2 < 0x7FFFFFFFull ? nb2 : 0x7FFFFFFFull);
-  L.tb = -1;
+  L.tb = -1; L.tnib0 = 0;
   L.entBase = (unsigned)((L.so >> 4) + 8ull * (unsigned long long)r);
   L.entCap = (unsigned)(((se >> 4) + 8ull * (unsigned long long)(r + 1)) - ((L.so >> 4) + 8ull * (unsigned long long)r));
   L.refPos = L.alnStart - 1; L.readPos = 0; L.mRem = 0;
   L.st_r = 0; L.lmRead0 = 0; L.lmLen = 0;
-  L.nb = 1; L.nblk = 0; L.nent = 0; L.njunc = 0; L.nextra = 0; L.errs = 0; L.maps = 0; L.nt = 0;
+  L.nb = 1; L.nblk = 0; L.nent = 0; L.njunc = 0; L.nextra = 0; L.ndbl = 0; L.errs = 0; L.maps = 0; L.nt = 0;
   L.pmh = 0x80000000u; L.pml = 0; L.pp0 = L.alnStart;   // CigarCluster.addStart :442-446: prev = alignment start
-  L.maxPos = 0; L.flushE = 0; L.blkFirstE = 0;
+  L.maxPos = 0; L.flushE = 0; L.blkFirstE = 0; L.blk0 = L.blk1 = L.blk2 = 0;
   if (L.alnStart <= 0) L.flags |= FWF_SLOW;             // not a mapped record: the serial walker flags it
   else b.break_arena[r * FW_BRK_INLINE] = L.alnStart;
 }
@@ -135,67 +139,79 @@ FW_HD void fw_start_read(FwLane& L, const BatchDev& b, long long r) {
 // ---- phase 1: CIGAR -> tasks ---------------------------------------------------------------------------------------
 // cig[i] = CIGAR word (L.cs + i), i < cigWords.  tasks[i * TS] receives task i: x = read base index | D flag | (n-1) << 28,
 // y = refPos before the first emitted position (the task emits positions y+1 .. y+n).
+// One iteration = [take one CIGAR element if the current M element is used up] + [emit at most one task], written as
+// straight-line arithmetic: lanes sit on different element types all the time, and a branch per type serialises the warp
+// (ncu r02b: 3-12 of 32 lanes active in the branchy version, half of the kernel's instructions).  Everything the fast walk
+// does not restate only sets a sticky word that is looked at once per round; a round that ran on such an element produced
+// tasks nobody uses (fw_task clamps its reference index, the read goes to the serial walker).
 template <bool RECORD>
 FW_HD void fw_produce(FwLane& L, const DevCfg& c, const uint32_t* cig, int cigWords, uint2* tasks, int TS) {
   L.nt = 0;
   if ((L.flags & (FWF_ACTIVE | FWF_SLOW)) != FWF_ACTIVE) return;
-  const int tnibEnd = (int)(2 * (L.tb - (long long)L.so)) + FW_SEQ_TILE * 8;
-  const int G = c.G;
-  for (;;) {
-    if (L.mRem > 0) {
-      if (L.readPos + FW_TASK_MAX + 8 > tnibEnd) break;   // bases not staged: next round
-      const int n = fw_min(L.mRem, FW_TASK_MAX);
-      uint2 t; t.x = (unsigned)L.readPos | ((unsigned)(n - 1) << 28); t.y = (unsigned)L.refPos;
-      tasks[L.nt * TS] = t;
-      L.refPos += n; L.readPos += n; L.mRem -= n; L.nt++;
-      if (L.nt == FW_K) break;
-      continue;
+  const int tnibLast = L.tnib0 + FW_SEQ_TILE * 8 - (FW_TASK_MAX + 8);   // last read base a task may start at with this tile
+  bool open = (L.flags & FWF_BLOCKOPEN) != 0, firstref = (L.flags & FWF_FIRSTREF) != 0, lastM = (L.flags & FWF_LASTREFM) != 0;
+  unsigned viol = 0, orRef = 0, orRead = 0;
+  unsigned endf = 0;
+  int nt = 0, refPos = L.refPos, readPos = L.readPos, mRem = L.mRem;
+  unsigned ck = L.ck;
+  bool go = true;
+  while (go) {
+    // ---- (a) one CIGAR element; lanes that do not take one see a no-op (P of length 0)
+    const bool need = mRem == 0;
+    const bool atEnd = need && ck == L.cend;
+    const bool fetch = need && !atEnd && (ck - L.cs < (unsigned)cigWords);
+    unsigned w = cig[fetch ? (ck - L.cs) : 0u];
+    w = fetch ? w : 6u;
+    const unsigned op = w & 15u, len = w >> 4;
+    const unsigned pr = (0x00084281u >> ((op & 7u) << 2)) & 15u;   // 1 = M, 2 = D, 4 = N, 8 = I / S, 0 = H / P
+    const bool isM = (pr & 1u) != 0, isD = (pr & 2u) != 0, isN = (pr & 4u) != 0;
+    const bool nStop = isN && open;                 // N ends the aligned block: the round that closed it takes the element next time
+    const unsigned lenT = nStop ? 0u : len;
+    viol |= (op + 9u) >> 4;                         // = X and invalid ops
+    viol |= (pr != 0u && len == 0u) ? 1u : 0u;      // zero-length elements
+    viol |= (isD && len > (unsigned)FW_TASK_MAX) ? 1u : 0u;
+    viol |= ((pr & 6u) && !firstref) ? 1u : 0u;     // D / N before the first M
+    viol |= ((pr & 3u) && !open && L.nblk == FW_MAX_BLOCKS) ? 1u : 0u;
+    ck += (fetch && !nStop) ? 1u : 0u;
+    refPos += (pr & 6u) ? (int)lenT : 0;            // D, N advance first; D then emits len mismatching positions (:513-522)
+    if (isM) {                                      // M: emits from its own start (:531-551)
+      L.st_r = firstref ? L.st_r : readPos + 1;
+      L.lmRead0 = readPos; L.lmLen = (int)len; mRem = (int)len;
     }
-    if (L.ck == L.cend) { L.flags |= FWF_ENDREAD; break; }
-    if (L.ck - L.cs >= (unsigned)cigWords) break;
-    const unsigned w = cig[L.ck - L.cs];
-    const int op = (int)(w & 15u), len = (int)(w >> 4);
-    if (op == 0) {          // M: emits from its own start (:531-551)
-      if (len == 0 || L.readPos + len > L.nbases || L.refPos + len > G || (unsigned)(L.readPos + len) >= FW_NIB_MAX) { L.flags |= FWF_SLOW; break; }
-      if (!(L.flags & FWF_FIRSTREF)) { L.flags |= FWF_FIRSTREF; L.st_r = L.readPos + 1; }
-      if (!(L.flags & FWF_BLOCKOPEN)) {
-        if (L.nblk == FW_MAX_BLOCKS) { L.flags |= FWF_SLOW; break; }
-        L.flags |= FWF_BLOCKOPEN; L.flushE = L.blkFirstE = (L.refPos + 1) >> 5; L.maxPos = L.refPos + 1;
-      }
-      L.lmRead0 = L.readPos; L.lmLen = len; L.flags |= FWF_LASTREFM;
-      L.mRem = len; L.maps += len; L.ck++;
-      L.maxPos = fw_max(L.maxPos, L.refPos + len);
-      continue;
+    firstref = firstref || isM;
+    lastM = isM || (lastM && !(pr & 6u));
+    L.maps += (pr & 3u) ? (int)lenT : 0;
+    L.errs += isD ? (int)lenT : 0;
+    readPos += (pr & 8u) ? (int)lenT : 0;
+    if (pr & 3u) {
+      if (!open) { open = true; L.flushE = L.blkFirstE = (refPos + 1) >> 5; L.maxPos = refPos + 1; }
+      L.maxPos = fw_max(L.maxPos, refPos + (int)len);
     }
-    if (op == 2) {          // D: advance, then emit len mismatching positions (:513-522)
-      if (len == 0 || len > FW_TASK_MAX || !(L.flags & FWF_FIRSTREF) || L.refPos + 2 * len > G) { L.flags |= FWF_SLOW; break; }
-      L.ck++; L.refPos += len; L.flags &= ~FWF_LASTREFM;
-      if (!(L.flags & FWF_BLOCKOPEN)) {
-        if (L.nblk == FW_MAX_BLOCKS) { L.flags |= FWF_SLOW; break; }
-        L.flags |= FWF_BLOCKOPEN; L.flushE = L.blkFirstE = (L.refPos + 1) >> 5; L.maxPos = L.refPos + 1;
-      }
-      uint2 t; t.x = FW_TASK_D | ((unsigned)(len - 1) << 28); t.y = (unsigned)L.refPos;
-      tasks[L.nt * TS] = t;
-      L.maxPos = fw_max(L.maxPos, L.refPos + len);
-      L.maps += len; L.errs += len; L.nt++;
-      if (L.nt == FW_K) break;
-      continue;
+    orRef |= (unsigned)refPos | len; orRead |= (unsigned)readPos;
+    // ---- (b) at most one task: the positions of the D element just taken, or the next piece of the current M element
+    const bool haveM = mRem > 0;
+    const bool staged = readPos <= tnibLast;
+    const bool emitM = haveM && staged;
+    const int n = isD ? (int)len : fw_min(mRem, FW_TASK_MAX);
+    if (isD || emitM) {
+      uint2 t;
+      t.x = (isD ? FW_TASK_D : (unsigned)readPos) | ((unsigned)(n - 1) << 28);
+      t.y = (unsigned)refPos;
+      tasks[nt * TS] = t;
+      nt++;
     }
-    if (op == 3) {          // N: ends the aligned block; the round that closed the block consumes the element next time
-      if (L.flags & FWF_BLOCKOPEN) { L.flags |= FWF_ENDBLOCK; break; }
-      if (len == 0 || !(L.flags & FWF_FIRSTREF) || (long long)L.refPos + len > (long long)G) { L.flags |= FWF_SLOW; break; }
-      L.ck++; L.refPos += len; L.flags &= ~FWF_LASTREFM;
-      continue;
-    }
-    if (op == 1 || op == 4) {  // I, S consume read bases only
-      if (len == 0 || (unsigned)L.readPos + (unsigned)len >= FW_NIB_MAX) { L.flags |= FWF_SLOW; break; }
-      L.readPos += len; L.ck++;
-      continue;
-    }
-    if (op == 5 || op == 6) { L.ck++; continue; }  // H, P
-    L.flags |= FWF_SLOW;    // = X and invalid ops: the serial walker restates them literally
-    break;
+    const int adv = emitM ? n : 0;
+    refPos += adv; readPos += adv; mRem -= adv;
+    // ---- (c) the round ends at the end of the read / block / staged data, or when the task buffer is full
+    endf |= (atEnd ? FWF_ENDREAD : 0u) | (nStop ? FWF_ENDBLOCK : 0u);
+    go = !(atEnd || nStop || (need && !atEnd && !fetch) || (haveM && !staged) || nt == FW_K || viol != 0u);
   }
+  L.nt = nt; L.refPos = refPos; L.readPos = readPos; L.mRem = mRem; L.ck = ck;
+  // ranges: positions <= G (a round adds < 2^28 per element to positions < 2^29, so the sticky OR sees every excursion before
+  // an int can wrap), read bases < 2^27 (the task encoding)
+  const bool slow = viol != 0u || (orRef >> 29) != 0u || (orRead >> 27) != 0u || L.maxPos > c.G || refPos > c.G;
+  L.flags = (L.flags & ~(FWF_BLOCKOPEN | FWF_FIRSTREF | FWF_LASTREFM)) | (open ? FWF_BLOCKOPEN : 0u) | (firstref ? FWF_FIRSTREF : 0u) |
+            (lastM ? FWF_LASTREFM : 0u) | endf | (slow ? FWF_SLOW : 0u);
 }
 
 // ---- phase 2: tasks -> match masks, breaks, ring ---------------------------------------------------------------------
@@ -208,14 +224,15 @@ FW_HD void fw_task(FwLane& L, const DevCfg& c, const BatchDev& b, const uint2 tk
   const int p0 = (int)tk.y + 1;              // first emitted position
   const unsigned t4 = ((unsigned)p0 & 7u) << 2;
   const unsigned W0 = (unsigned)p0 >> 3;
+  const unsigned Wr = W0 < (unsigned)(c.refg_nwords - 3) ? W0 : (unsigned)(c.refg_nwords - 3);   // memory safety only
   // 16 read bases from the task's first base, normalised to the top of (hi:lo)
-  const int rel = isD ? 0 : (int)(tk.x & (FW_NIB_MAX - 1)) - (int)(2 * (L.tb - (long long)L.so));
+  const int rel = isD ? 0 : (int)(tk.x & (FW_NIB_MAX - 1)) - L.tnib0;
   const int k0 = rel >> 3;
   const unsigned o4 = ((unsigned)rel & 7u) << 2;
   const unsigned w0 = fw_bswap(seq[k0]), w1 = fw_bswap(seq[k0 + 1]), w2 = fw_bswap(seq[k0 + 2]);
   const unsigned hi = fw_fl(w1, w0, o4), lo = fw_fl(w2, w1, o4);
   // 16 reference bases from position p0
-  const unsigned R0 = refg[W0], R1 = refg[W0 + 1], R2 = refg[W0 + 2];
+  const unsigned R0 = refg[Wr], R1 = refg[Wr + 1], R2 = refg[Wr + 2];
   const unsigned rhi = fw_fl(R1, R0, t4), rlo = fw_fl(R2, R1, t4);
   const unsigned xh = hi ^ rhi, xl = lo ^ rlo;
   const unsigned nzh = ((xh & 0x77777777u) + 0x77777777u) | xh, nzl = ((xl & 0x77777777u) + 0x77777777u) | xl;  // bit 3 of a nibble: bases differ
@@ -263,8 +280,10 @@ FW_HD void fw_task(FwLane& L, const DevCfg& c, const BatchDev& b, const uint2 tk
         while (v) {
           const int bit = 31 - fw_clz(v);
           v &= ~(1u << bit);
+          const unsigned q = (unsigned)((W0 + j) * 8 + ((31 - bit) >> 2));
+          if (L.ndbl < 3) { b.fhdr[L.r * FW_HDR_WORDS + 5 + L.ndbl] = q; L.ndbl++; continue; }
           if (L.nextra == FW_MAX_EXTRA) { L.flags |= FWF_SLOW; break; }
-          b.fhdr[L.r * FW_HDR_WORDS + 12 + 2 * L.nextra] = 0x80000000u | (unsigned)((W0 + j) * 8 + ((31 - bit) >> 2));
+          b.fhdr[L.r * FW_HDR_WORDS + 12 + 2 * L.nextra] = 0x80000000u | q;
           b.fhdr[L.r * FW_HDR_WORDS + 13 + 2 * L.nextra] = 0;
           L.nextra++;
         }
@@ -278,29 +297,33 @@ template <bool RECORD>
 FW_HD void fw_flush(FwLane& L, const DevCfg& c, const BatchDev& b, uint32_t* ring, int RS) {
   if (!(L.flags & FWF_ACTIVE)) return;
   const bool fin = (L.flags & (FWF_ENDREAD | FWF_ENDBLOCK | FWF_SLOW)) != 0;
-  if (RECORD && (L.flags & FWF_BLOCKOPEN)) {
+  if (RECORD && (L.flags & FWF_SLOW)) {
+    for (int j = 0; j < FW_RING; j++) ring[j * RS] = 0;   // whatever the read left behind; its entries are never looked at
+  } else if (RECORD && (L.flags & FWF_BLOCKOPEN)) {
     // an entry (32 positions) is complete when every position of it lies before the next position an M element can emit
-    int endE = fin ? (L.maxPos >> 5) + 1 : (L.refPos + 1) >> 5;
+    const int endE = fin ? (L.maxPos >> 5) + 1 : (L.refPos + 1) >> 5;
     while (L.flushE < endE) {
       const int j = (L.flushE & (FW_RING / 4 - 1)) * 4;
       uint4 e;
       e.x = ring[(j + 0) * RS]; e.y = ring[(j + 1) * RS]; e.z = ring[(j + 2) * RS]; e.w = ring[(j + 3) * RS];
       ring[(j + 0) * RS] = 0; ring[(j + 1) * RS] = 0; ring[(j + 2) * RS] = 0; ring[(j + 3) * RS] = 0;
       if ((unsigned)L.nent < L.entCap) b.fent[(size_t)L.entBase + (unsigned)L.nent] = e;
-      else { L.flags |= FWF_SLOW; endE = (L.maxPos >> 5) + 1; }   // does not fit the read's share of the arena: empty the ring, serial path
+      else L.flags |= FWF_SLOW;   // does not fit the read's share of the arena (the ring is emptied all the same): serial path
       L.errs += fw_popc((e.x & FW_MIS) | ((e.y & FW_MIS) >> 1) | ((e.z & FW_MIS) >> 2) | ((e.w & FW_MIS) >> 3));
       L.nent++; L.flushE++;
     }
     if (fin && L.nblk < FW_MAX_BLOCKS) {
-      b.fhdr[L.r * FW_HDR_WORDS + 2 + 2 * L.nblk] = (unsigned)L.blkFirstE;
-      b.fhdr[L.r * FW_HDR_WORDS + 3 + 2 * L.nblk] = (unsigned)(L.flushE - L.blkFirstE);
+      const unsigned cnt = (unsigned)(L.flushE - L.blkFirstE);
+      const unsigned v = (unsigned)L.blkFirstE | (cnt << 16);
+      if (cnt >= 0x10000u || (unsigned)L.blkFirstE >= 0x10000u) L.flags |= FWF_SLOW;
+      if (L.nblk == 0) L.blk0 = v; else if (L.nblk == 1) L.blk1 = v; else L.blk2 = v;
       L.nblk++;
     }
   }
   if (fin || (L.flags & FWF_SLOW)) L.flags &= ~(FWF_BLOCKOPEN | FWF_ENDBLOCK);
   if (L.flags & (FWF_ENDREAD | FWF_SLOW)) {
     const long long r = L.r;
-    if (!(L.flags & FWF_SLOW) && L.nb + 1 > FW_BRK_INLINE) L.flags |= FWF_SLOW;
+    if (!(L.flags & FWF_SLOW) && (L.nb + 1 > FW_BRK_INLINE || L.lmRead0 + L.lmLen > L.nbases)) L.flags |= FWF_SLOW;
     if (L.flags & FWF_SLOW) {
       b.rflags[r] = 0x20u;    // NPT_RF_SLOWPATH: walked again by the exact serial device path
 #if defined(__CUDA_ARCH__)
@@ -320,8 +343,9 @@ FW_HD void fw_flush(FwLane& L, const DevCfg& c, const BatchDev& b, uint32_t* rin
       b.err_sum[r] = c.record_depth ? L.errs : 0;
       b.rflags[r] = 0;
       if (RECORD) {
-        b.fhdr[r * FW_HDR_WORDS + 0] = L.entBase;
-        b.fhdr[r * FW_HDR_WORDS + 1] = (unsigned)L.nblk | ((unsigned)L.njunc << 8) | ((unsigned)L.nextra << 16);
+        uint4 h; h.x = L.entBase; h.y = L.blk0; h.z = L.blk1; h.w = L.blk2;
+        *reinterpret_cast<uint4*>(b.fhdr + r * FW_HDR_WORDS) = h;
+        b.fhdr[r * FW_HDR_WORDS + 4] = (unsigned)L.nblk | ((unsigned)L.njunc << 8) | ((unsigned)L.nextra << 16) | ((unsigned)L.ndbl << 24);
       }
     }
     L.flags &= FWF_DONE;

@@ -765,7 +765,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
     // fast walk: tasks are 16 positions, so a break can only hide inside one when break_thresh < 16; with depth recording the
     // reference-grid entries of a chromosome must fit accumulate_kernel's shared tables.  Otherwise: serial walker for all.
     ctx->fast_record = cf.record_depth != 0;
-    ctx->fast = cf.break_thresh >= FW_TASK_MAX && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
+    ctx->fast = cf.break_thresh >= FW_TASK_MAX && ref_len < (1LL << 29) && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
     if (const char* e = getenv("NPT_FAST")) if (atoi(e) == 0) ctx->fast = false;   // experiments / A-B runs
     if (ctx->fast) {
       const size_t refb = ctx->ref_smem ? (size_t)((dc.refg_nwords + 3) & ~3) * 4 : 0;

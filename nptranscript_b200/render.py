@@ -183,8 +183,13 @@ def start_end_matrix(res, cluster, which="map_start"):
     return np.concatenate([pos[:, None].astype(np.int32), a[:, pos].T.astype(np.int32)], axis=1)
 
 
-def annot_rows(res, annotation):
-    """0.annot.txt.gz (Annotation.print, J/cluster/Annotation.java:40-58)."""
+def annot_rows(res, annotation, seqlen=None, polya=0, coronavirus=True):
+    """0.annot.txt.gz (Annotation.print, J/cluster/Annotation.java:40-58).  In coronavirus mode the first processed read
+    moves the last row's end to seqlen - polyA (adjust3UTR, Annotation.java:205-212 via IdentityProfile1.java:179-183):
+    pass the reference length and its polyA tail (workloads.polya_len) to get the End column the reference prints."""
+    if coronavirus and seqlen is not None and polya > 0 and res["n_reads"] > 0:
+        import copy
+        annotation = copy.deepcopy(annotation).adjust3utr(seqlen - polya)
     S = res["spliced"].shape[0]
     head = "Gene\tStart\tEnd" + "".join(f"\tSpliced_5_{j}\tUnspliced_5_{j}" for j in range(S))
     rows = [head]

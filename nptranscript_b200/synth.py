@@ -38,6 +38,9 @@ def lib():
 
 
 def genome_codes(w: Workload) -> np.ndarray:
+    if w.genome_file:   # the real reference (BAM 4-bit codes of its letters)
+        from .workloads import read_fasta, ref_char_to_code
+        return ref_char_to_code(read_fasta(w.genome_file)[2])
     out = np.empty(w.genome_len, dtype=np.uint8)
     lib().npts_genome(w.genome_seed, w.genome_len, w.polya_len, out.ctypes.data)
     return out

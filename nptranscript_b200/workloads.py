@@ -49,6 +49,14 @@ class Annotation:
     def empty(cls):
         return cls(kind=1)
 
+    def adjust3utr(self, seqlen2):
+        """Annotation.adjust3UTR (J/cluster/Annotation.java:205-212): the last row's end is pulled back to seqlen2 =
+        reference length - polyA tail when it lies beyond it.  The reference does this on the first read it processes in
+        coronavirus mode (IdentityProfile1.java:179-183 with polyAlen from :649); only the End column of 0.annot changes."""
+        if self.kind == 0 and self.end and self.end[-1] > seqlen2 and self.start[-1] < seqlen2:
+            self.end[-1] = seqlen2
+        return self
+
     @classmethod
     def gff(cls, genes, start, end, strand):
         """Exon rows of one chromosome in file order (GFFAnnotation.java:409-428): gene = the exon's parent attribute."""
@@ -117,6 +125,36 @@ COV_229E = _csv([
     ("E", 24750, 24983), ("M", 24995, 25672), ("N", 25686, 26855), ("3UTR", 26856, 27317)])
 
 
+def read_fasta(path):
+    """First record of a (gzipped) FASTA file: (name, description, sequence).  The reference reads its --reference with
+    japsa SequenceReader.readAll (ViralTranscriptAnalysisCmd2.java:594); name = header up to the first blank."""
+    import gzip
+    op = gzip.open if str(path).endswith(".gz") else open
+    name, desc, seq = None, "", []
+    with op(path, "rt") as f:
+        for line in f:
+            line = line.strip()
+            if line.startswith(">"):
+                if name is not None:
+                    break
+                head = line[1:].split(None, 1)
+                name, desc = head[0], (head[1] if len(head) > 1 else "")
+            elif name is not None:
+                seq.append(line)
+    return name, desc, "".join(seq)
+
+
+def polya_len(seq: str) -> int:
+    """TranscriptUtils.polyAlen (J/cluster/TranscriptUtils.java:116-132): 0 unless the last 10 bases are all 'A', else the
+    length of the trailing run of 'A'."""
+    if len(seq) < 10 or any(ch != "A" for ch in seq[-10:]):
+        return 0
+    i = 1
+    while i <= len(seq) and seq[len(seq) - i] == "A":
+        i += 1
+    return i - 1
+
+
 @dataclass
 class Workload:
     name: str
@@ -126,6 +164,7 @@ class Workload:
     donor: int
     acceptors: List[int]
     acceptor_w: List[float]
+    genome_file: str = ""          # FASTA of the real reference; empty = seeded random genome + polyA tail
     genome_seed: int = 20200101
     w_mix: tuple = (0.60, 0.25, 0.10, 0.05)  # canonical, leaderless, genomic, double-junction
     p_mismatch: float = 0.04
@@ -148,6 +187,32 @@ HCOV229E = Workload(
     name="hcov229e_drna", genome_len=27317, polya_len=20, annotation=COV_229E, donor=65,
     acceptors=[25672, 24983, 24740, 24480, 24080, 20560],
     acceptor_w=[0.40, 0.20, 0.10, 0.10, 0.10, 0.10])
+
+
+def from_files(name, fasta_path, csv_path, donor, acceptors, acceptor_w, enforce_strand=False, **kw) -> Workload:
+    """A workload on a real reference + Coordinates.csv (BASELINE.json configs[0]: run_example.sh's VIC01 files): genome
+    length and polyA tail from the FASTA, ORF table through the reference's own parser rules (Annotation.from_csv)."""
+    _n, _d, seq = read_fasta(fasta_path)
+    return Workload(name=name, genome_len=len(seq), polya_len=polya_len(seq), annotation=Annotation.from_csv(csv_path, enforce_strand),
+                    donor=donor, acceptors=list(acceptors), acceptor_w=list(acceptor_w), genome_file=str(fasta_path), **kw)
+
+
+def golden_path(*parts):
+    """tests/golden/<...>: copies of the reference's own data files (tests/golden/make_reference_fixtures.py)."""
+    import os
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", *parts)
+
+
+def sars2_vic01_real() -> Workload:
+    """configs[0] as specified: MT007544.1 (29 893 bp, 33-A tail) + data/SARS-Cov2/VIC01/Coordinates.csv."""
+    return from_files("sars2_vic01_real", golden_path("vic01", "wuhan_coronavirus_australia.fasta.gz"), golden_path("vic01", "Coordinates.csv"),
+                      donor=SARS2.donor, acceptors=SARS2.acceptors, acceptor_w=SARS2.acceptor_w)
+
+
+def cov229e_real() -> Workload:
+    """configs[2]: data/229E_CoV/WT_229_reference.fasta.gz (27 317 bp) + its Coordinates.csv."""
+    return from_files("hcov229e_real", golden_path("cov229e", "WT_229_reference.fasta.gz"), golden_path("cov229e", "Coordinates.csv"),
+                      donor=HCOV229E.donor, acceptors=HCOV229E.acceptors, acceptor_w=HCOV229E.acceptor_w)
 
 
 def ref_char_to_code(seq: str) -> np.ndarray:

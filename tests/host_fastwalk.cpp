@@ -27,7 +27,7 @@ static void run_all(const DevCfg& c, const BatchDev& b) {
       }
       const long long ntb = (long long)((L.so + (unsigned long long)(L.readPos >> 1)) & ~15ull);
       if (live && ntb != L.tb) {
-        L.tb = ntb;
+        L.tb = ntb; L.tnib0 = (int)(2 * (ntb - (long long)L.so));
         unsigned char* dst = (unsigned char*)seqT.data();
         for (int i = 0; i < FW_SEQ_TILE * 4; i++) dst[i] = (ntb + i < b.seq_bytes) ? b.seq4[ntb + i] : 0;
       }

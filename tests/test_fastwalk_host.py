@@ -84,10 +84,11 @@ def coverage_from_entries(out, b, ora, G, S):
         if c < 0:
             continue
         h = fhdr[r]
-        nblk, njunc, nextra = int(h[1]) & 0xFF, (int(h[1]) >> 8) & 0xFF, (int(h[1]) >> 16) & 0xFF
+        nblk, njunc, nextra = int(h[4]) & 0xFF, (int(h[4]) >> 8) & 0xFF, (int(h[4]) >> 16) & 0xFF
         e0 = int(h[0])
+        assert all(int(h[1 + k]) == 0 for k in range(nblk, 3))
         for k in range(nblk):
-            first, cnt = int(h[2 + 2 * k]), int(h[3 + 2 * k])
+            first, cnt = int(h[1 + k]) & 0xFFFF, int(h[1 + k]) >> 16
             words = fent[e0:e0 + cnt].reshape(-1)               # 8 positions per word
             nib = (words[:, None] >> sh[None, :]) & 0xF          # [word][nibble from the top]
             flags = nib.reshape(-1)
@@ -103,6 +104,9 @@ def coverage_from_entries(out, b, ora, G, S):
         for j in range(njunc):
             cov["map_end"][c, s, int(h[8 + 2 * j])] += 1
             cov["map_start"][c, s, int(h[9 + 2 * j])] += 1
+        for d in range((int(h[4]) >> 24) & 0xFF):
+            cov["depth"][c, s, int(h[5 + d])] += 1
+            cov["errors"][c, s, int(h[5 + d])] += 1
         for e in range(nextra):
             a, p = int(h[12 + 2 * e]), int(h[13 + 2 * e])
             if a & 0x80000000:

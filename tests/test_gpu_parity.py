@@ -27,6 +27,23 @@ def test_sars2_20k(depth):
     assert dev["n_slow_reads"] < 5 * 20000  # exact per-base windows (junction windows): a diagnostic, ~1 per read
 
 
+def test_config1_as_specified_from_the_reference_files():
+    """BASELINE.json configs[0]: VIC01 reference FASTA + Coordinates.csv (copies of the reference's own data files under
+    tests/golden/), 100 000 synthetic direct-RNA reads, seed 20200301, run_example.sh flags (--bin 10 --breakThresh 1000)
+    + --RNA=true --writeGFF=true --maxThreads=1; then the 0.annot rows against the reference-held sample"""
+    from nptranscript_b200 import render
+    w = workloads.sars2_vic01_real()
+    g = synth.genome_codes(w)
+    b = synth.generate(w, 20200301, 100000)
+    kw = dict(bin=10, break_thresh=1000, track_break_sums=1)
+    dev = engine.run(engine.make_config(**kw), g, w.annotation, [b])
+    ora = oracle.run(oracle.make_config(**kw), g, w.annotation, [b])
+    assert_same(dev, ora)
+    rows = render.annot_rows(dev, w.annotation, seqlen=w.genome_len, polya=w.polya_len)
+    want = open(workloads.golden_path("vic01", "0.annot.tsv")).read().splitlines()
+    assert [x.split("\t")[:3] for x in rows[1:]] == [x.split("\t")[:3] for x in want[1:]]
+
+
 def test_config2_flags_200k():
     """the benchmark's own flag set (bin=100, breakThresh=1000, depth recording) on 200 k reads"""
     w = workloads.SARS2
@@ -388,6 +405,7 @@ def test_random_flag_combinations(seed):
         kw["max_coverage_clusters"] = 4096
         if rng.integers(0, 2):
             ann = workloads.Annotation.empty()
+            kw["rna"] = [1] * S   # EmptyAnnotation + rna=0 throws in the reference and is rejected by the library
             bs = [random_batch(rng, 2000, w.genome_len, g, num_sources=S, big_n=300)]
         else:
             lut = np.full(16, ord("N"), np.uint8)

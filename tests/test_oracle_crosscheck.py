@@ -9,8 +9,8 @@ from oracle import oracle, py_oracle
 from tests.fuzz import random_batch
 
 
-def _compare(kw, annotation, batches, chrom_index=0):
-    w = workloads.SARS2
+def _compare(kw, annotation, batches, chrom_index=0, w=None):
+    w = w or workloads.SARS2
     g = synth.genome_codes(w)
     ora = oracle.run(oracle.make_config(**kw), g, annotation, batches, chrom_index)
     fl = py_oracle.Flags(bin=kw.get("bin", 1), break_thresh=kw.get("break_thresh", 1000), include_start=bool(kw.get("include_start", 1)),
