@@ -18,8 +18,8 @@
 namespace npt {
 
 constexpr int FW_WARPS_MAX = 16;
-constexpr int FW_PW_CIG = 32 * FW_TILE_STRIDE, FW_PW_SEQ = 32 * FW_TILE_STRIDE, FW_PW_TASK = FW_K * 32 * 2, FW_PW_SRC = 32 + 64;
-__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_CIG + FW_PW_SEQ + FW_PW_TASK + (record ? FW_RING * 32 : 0) + FW_PW_SRC; }
+constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE, FW_PW_SRC = 32 + 64;
+__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? FW_RING * 32 : 0) + FW_PW_SRC; }
 
 __device__ __forceinline__ void fw_cp16z(uint32_t dst, const void* src, int n) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
@@ -34,10 +34,8 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
   const int refw = REF_SMEM ? ((c.refg_nwords + 3) & ~3) : 0;
   uint32_t* s_ref = fw_smem;
   uint32_t* wb = fw_smem + refw + warp * fw_warp_words(RECORD);
-  uint32_t* cigT = wb;
-  uint32_t* seqT = cigT + FW_PW_CIG;
-  uint2* taskT = (uint2*)(seqT + FW_PW_SEQ);
-  uint32_t* ringT = (uint32_t*)taskT + FW_PW_TASK;
+  uint32_t* tileT = wb;                                                 // [32 lanes][CIGAR tile | base tile]
+  uint32_t* ringT = tileT + FW_PW_TILE;
   uint32_t* srcC = ringT + (RECORD ? FW_RING * 32 : 0);                 // [32] first CIGAR word to stage + 1, 0 = none
   unsigned long long* srcS = (unsigned long long*)(srcC + 32);          // [32] first base byte to stage + 1, 0 = none
   if (REF_SMEM)
@@ -46,12 +44,14 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
     for (int i = lane; i < FW_RING * 32; i += 32) ringT[i] = 0;
   __syncthreads();
   const uint32_t* refg = REF_SMEM ? s_ref : c.refg_words;
-  const uint32_t cigS = (uint32_t)__cvta_generic_to_shared(cigT), seqS = (uint32_t)__cvta_generic_to_shared(seqT);
+  const uint32_t tileS = (uint32_t)__cvta_generic_to_shared(tileT);
+  const uint32_t* cigL = tileT + lane * FW_TILE_STRIDE;
+  const uint32_t* seqL = cigL + FW_CIG_TILE;
   unsigned* cursor = b.bctr + 5;
   const long long cig_words = b.cigar_words, seq_bytes = b.seq_bytes;
 
   FwLane L;
-  L.flags = 0; L.nt = 0; L.tb = -1; L.so = 0; L.readPos = 0; L.ck = 0; L.cs = 0; L.r = 0;
+  L.flags = 0; L.tb = -1; L.so = 0; L.readPos = 0; L.ck = 0; L.cs = 0; L.r = 0; L.cend = 0; L.mRem = 0; L.refPos = 0; L.flushE = 0; L.tnib0 = 0;
   for (;;) {
     // ---- (0) lanes without a read take the next ones from the cursor (one atomic per warp and round)
     const bool want = (L.flags & (FWF_ACTIVE | FWF_DONE)) == 0;
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
     if (__all_sync(FULL, (L.flags & (FWF_ACTIVE | FWF_DONE)) == FWF_DONE)) break;
     // ---- (1) stage this round's CIGAR words and bases: every lane publishes what it needs, the warp copies all tiles
     // together with 16-byte cp.async (a lane copying only its own tile costs one L1 wavefront per lane and copy)
+    const bool live = (L.flags & (FWF_ACTIVE | FWF_SLOW)) == FWF_ACTIVE;
     {
-      const bool live = (L.flags & (FWF_ACTIVE | FWF_SLOW)) == FWF_ACTIVE;
       const unsigned ncs = L.ck & ~3u;
       const bool needC = live && ncs != L.cs && L.ck < L.cend;
       if (needC) L.cs = ncs;
@@ -81,39 +81,35 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
       srcS[lane] = needS ? (unsigned long long)ntb + 1ull : 0ull;
       __syncwarp();
 #pragma unroll
-      for (int it = 0; it < FW_CIG_TILE / 4; it++) {     // 32 tiles x 4 chunks
-        const unsigned id = it * 32 + lane, owner = id >> 2, ch = id & 3u;
+      for (int it = 0; it < FW_CIG_TILE / 4; it++) {     // 32 tiles x 5 chunks
+        const unsigned id = it * 32 + lane, owner = id / (FW_CIG_TILE / 4), ch = id - owner * (FW_CIG_TILE / 4);
         const unsigned s1 = srcC[owner];
         if (s1) {
           const long long w0 = (long long)(s1 - 1u) + 4 * ch;
           const long long left = (cig_words - w0) * 4;
-          fw_cp16z(cigS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.cigar + w0) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
+          fw_cp16z(tileS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.cigar + w0) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
         }
       }
 #pragma unroll
-      for (int it = 0; it < FW_SEQ_TILE / 4; it++) {     // 32 tiles x 5 chunks
-        const unsigned id = it * 32 + lane, owner = id / 5u, ch = id - owner * 5u;
+      for (int it = 0; it < FW_SEQ_TILE / 4; it++) {     // 32 tiles x 6 chunks
+        const unsigned id = it * 32 + lane, owner = id / (FW_SEQ_TILE / 4), ch = id - owner * (FW_SEQ_TILE / 4);
         const unsigned long long s1 = srcS[owner];
         if (s1) {
           const long long a0 = (long long)(s1 - 1ull) + 16 * ch;
           const long long left = seq_bytes - a0;
-          fw_cp16z(seqS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.seq4 + a0) : (const void*)b.seq4, (int)max(0LL, min(16LL, left)));
+          fw_cp16z(tileS + (owner * FW_TILE_STRIDE + FW_CIG_TILE + 4 * ch) * 4, left > 0 ? (const void*)(b.seq4 + a0) : (const void*)b.seq4, (int)max(0LL, min(16LL, left)));
         }
       }
       fw_cp_wait();
       __syncwarp();
     }
-    // ---- (2) CIGAR -> tasks
-    fw_produce<RECORD>(L, c, cigT + lane * FW_TILE_STRIDE, FW_CIG_TILE, taskT + lane, 32);
+    // ---- (2) FW_R steps: [one element that is not M] + [start of the M behind it] + [<= 16 positions of the current M]
+    bool run = live;
+#pragma unroll 1
+    for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigL, seqL, refg, ringT + lane, 32, run);
     __syncwarp();
-    // ---- (3) tasks -> match masks, breaks, ring (the same straight-line code in every lane)
-    const int ntmax = __reduce_max_sync(FULL, L.nt);
-    for (int i = 0; i < ntmax; i++) {
-      if (i < L.nt) fw_task<RECORD>(L, c, b, taskT[i * 32 + lane], seqT + lane * FW_TILE_STRIDE, refg, ringT + lane, 32);
-      __syncwarp();
-    }
-    // ---- (4) completed entries, closed blocks, finished reads
-    fw_flush<RECORD>(L, c, b, ringT + lane, 32);
+    // ---- (3) N elements, completed entries, closed blocks, finished reads
+    fw_round_end<RECORD>(L, c, b, cigL, ringT + lane, 32);
     __syncwarp();
   }
 }
@@ -141,16 +137,16 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
         const int sp = b.start_pos[r], ep = b.end_pos[r];
         if (sp >= 0 && sp < c.stride) atomicAdd(mstart + sp, 1);
         if (ep >= 0 && ep < c.stride) atomicAdd(mend + ep, 1);
-        const unsigned meta = __ldg(b.fhdr + r * FW_HDR_WORDS + 4);
+        const unsigned meta = __ldg(b.fmeta + r);
         const int njunc = (meta >> 8) & 0xFF, nextra = (meta >> 16) & 0xFF, ndbl = (meta >> 24) & 0xFF;
         for (int d = 0; d < ndbl; d++) {   // positions emitted by two D elements
-          const unsigned q = __ldg(b.fhdr + r * FW_HDR_WORDS + 5 + d);
+          const unsigned q = __ldg(b.frare + r * FW_RARE_WORDS + d);
           atomicAdd(cov + 8 * arr_stride + q, 1);
           atomicAdd(cov + arr_stride + q, 1);
         }
         if (njunc | nextra) {
-          const uint4 h2 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 8));
-          const uint4 h3 = __ldg((const uint4*)(b.fhdr + r * FW_HDR_WORDS + 12));
+          const uint4 h2 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 4));
+          const uint4 h3 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 8));
           if (njunc > 0) { atomicAdd(mend + h2.x, 1); atomicAdd(mstart + h2.y, 1); }
           if (njunc > 1) { atomicAdd(mend + h2.z, 1); atomicAdd(mstart + h2.w, 1); }
           for (int e = 0; e < nextra; e++) {
@@ -171,7 +167,7 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
 }
 
 // ------------------------------------------------------------------------------------------------ positional popcount
-constexpr int ACC_THREADS = 1024;
+constexpr int ACC_THREADS = 768;
 constexpr int ACC_TILE = 2048;        // key-sorted reads per block tile
 constexpr int ACC_MAX_ENT = 8192;     // reference-grid entries (32 positions each) a chromosome may have on this path
 constexpr int ACC_PLANES = 6;         // bit-sliced counters hold 63 reads before they are expanded
@@ -179,12 +175,11 @@ constexpr int ACC_CNT_WORDS = 48;     // 96 16-bit counters per thread: (COV, QR
 
 struct AccSmem {
   uint32_t cnt[ACC_CNT_WORDS * ACC_THREADS];   // [word][thread]
-  uint32_t vals[ACC_TILE];
+  uint4 hdr[ACC_TILE];                         // the tile's read headers {first entry, block 0, 1, 2}
   uint32_t head[ACC_TILE / 32];
   uint32_t act[ACC_MAX_ENT / 32];
   uint32_t actpre[ACC_MAX_ENT / 32 + 1];
   uint16_t word_of[ACC_MAX_ENT];
-  int nruns_dummy;
 };
 
 __device__ __forceinline__ void acc_add(uint32_t (&p)[ACC_PLANES], uint32_t x) {
@@ -227,6 +222,16 @@ __device__ __forceinline__ void acc_expand(uint32_t (&p)[ACC_PLANES], int k, uin
   for (int q = 0; q < ACC_PLANES; q++) p[q] = 0;
 }
 
+// which of a read's entries lies on reference-grid entry `myw`: index into the read's entries, or -1.  `more` = a later block of
+// the read holds an entry for the same grid entry too (an N element shorter than 32 positions): the caller adds those one by one
+__device__ __forceinline__ int acc_entry_index(const uint4 h, unsigned myw, bool& more) {
+  const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
+  const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
+  const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
+  more = (in0 && (in1 || in2)) || (in1 && in2);
+  return in0 ? (int)d0 : (in1 ? (int)(c0 + d1) : (in2 ? (int)(c0 + c1 + d2) : -1));
+}
+
 __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg c, const BatchDev b, const unsigned* keys, const unsigned* vals,
                                                                     unsigned* tile_cursor) {
   extern __shared__ __align__(16) unsigned char acc_raw[];
@@ -239,6 +244,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
   const int n_ent = (c.stride + 31) / 32 + 1;
   const int n_actw = (n_ent + 31) / 32;
   uint32_t* mycnt = sm.cnt + tid;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   for (;;) {
     if (tid == 0) s_tile = (int)atomicAdd(tile_cursor, 1u);
     __syncthreads();
@@ -249,12 +255,12 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
     if (t0 < 0) break;
     const int tn = (int)min((long long)ACC_TILE, b.n - t0);
     if (__ldg(keys + t0) == invalid) continue;   // sorted: this tile holds only reads that are not credited here
-    // ---- the tile: read indices into shared memory, head flags of the runs of equal key
+    // ---- the tile: read headers into shared memory, head flags of the runs of equal key
     for (int i = tid; i < ACC_TILE; i += ACC_THREADS) {
       bool head = false;
       if (i < tn) {
-        sm.vals[i] = __ldg(vals + t0 + i);
         const unsigned k = __ldg(keys + t0 + i);
+        sm.hdr[i] = k == invalid ? zero4 : __ldg(b.fhdrA + __ldg(vals + t0 + i));
         head = (i == 0) || (k != __ldg(keys + t0 + i - 1));
       }
       const unsigned hb = __ballot_sync(0xffffffffu, head);
@@ -275,14 +281,14 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
       const unsigned key = __ldg(keys + t0 + i0);
       if (key == invalid) break;
       const int rl = i1 - i0;
+      const uint4* hdr = sm.hdr + i0;
       int* row_err = c.cov + arr_stride + (long long)key * c.stride;
       int* row_dep = c.cov + 8 * arr_stride + (long long)key * c.stride;
       // ---- (A) reference-grid entries touched by the run
       for (int i = tid; i < n_actw; i += ACC_THREADS) sm.act[i] = 0;
       __syncthreads();
       for (int i = tid; i < rl; i += ACC_THREADS) {
-        const unsigned r = sm.vals[i0 + i];
-        const uint4 h0 = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
+        const uint4 h0 = hdr[i];
 #pragma unroll
         for (int k = 0; k < FW_MAX_BLOCKS; k++) {
           const unsigned bk = k == 0 ? h0.y : (k == 1 ? h0.z : h0.w);
@@ -324,9 +330,9 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
       for (int slot0 = 0; slot0 < wact; slot0 += ACC_THREADS) {
         const int W = min(ACC_THREADS, wact - slot0);
         const int Wpad = (W + 31) & ~31;
-        const int Q = ACC_THREADS / Wpad;
+        const int Q = min(ACC_THREADS / Wpad, (rl + 3) >> 2);   // no more subsets than groups of four reads
         const int q = tid / Wpad, s = tid - q * Wpad;
-        const bool live = q < Q && s < W && q < rl;
+        const bool live = q < Q && s < W;
         const unsigned myw = (s < W) ? sm.word_of[slot0 + s] : 0u;
         if (live)
 #pragma unroll
@@ -335,54 +341,57 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
 #pragma unroll
         for (int k = 0; k < ACC_PLANES; k++) { P0[k] = 0; P1[k] = 0; P2[k] = 0; P3[k] = 0; }
         int nin = 0;
-        if (q < Q) {
-          // four reads per step: their entries for this thread's reference-grid entry go through one carry-save tree
-          // (3 inputs -> sum + carry is two LOP3), and the four header / entry loads are in flight together
+        if (live) {
+          // four reads per step: headers come from shared memory (one broadcast load each), so the four entry loads are in
+          // flight together; their words go through one carry-save tree (3 inputs -> sum + carry is two LOP3)
           for (int i = q; i < rl; i += 4 * Q) {
             uint4 e[4];
             bool extra = false;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-              e[j] = make_uint4(0u, 0u, 0u, 0u);
+              e[j] = zero4;
               const int ii = i + j * Q;
-              if (ii < rl && s < W) {
-                const unsigned r = sm.vals[i0 + ii];
-                const uint4 h = __ldg((const uint4*)(b.fhdr + (size_t)r * FW_HDR_WORDS));
-                const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
-                const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
-                const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
-                const unsigned idx = in0 ? d0 : (in1 ? c0 + d1 : c0 + c1 + d2);
-                if (in0 || in1 || in2) e[j] = __ldg(b.fent + (size_t)h.x + idx);
-                // blocks of one read can share an entry (an N element shorter than 32 positions): the later blocks' entries
-                // for the same grid entry are added below, one at a time
-                if ((in0 && (in1 || in2)) || (in1 && in2)) {
-                  extra = true;
-                  if (in0 && in1) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + d1); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); }
-                  if ((in0 || in1) && in2) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + c1 + d2); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); }
-                }
+              if (ii < rl) {
+                const uint4 h = hdr[ii];
+                bool more;
+                const int idx = acc_entry_index(h, myw, more);
+                if (idx >= 0) e[j] = __ldg(b.fent + (size_t)h.x + idx);
+                extra |= more;
               }
             }
             acc_add4(P0, e[0].x, e[1].x, e[2].x, e[3].x);
             acc_add4(P1, e[0].y, e[1].y, e[2].y, e[3].y);
             acc_add4(P2, e[0].z, e[1].z, e[2].z, e[3].z);
             acc_add4(P3, e[0].w, e[1].w, e[2].w, e[3].w);
-            nin += __any_sync(0xffffffffu, extra) ? 12 : 4;
+            nin += 4;
+            if (extra) {   // rare: the later blocks' entries for the same grid entry
+#pragma unroll 1
+              for (int j = 0; j < 4; j++) {
+                const int ii = i + j * Q;
+                if (ii >= rl) break;
+                const uint4 h = hdr[ii];
+                const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
+                const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
+                const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
+                if (in0 && in1) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + d1); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); nin++; }
+                if ((in0 || in1) && in2) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + c1 + d2); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); nin++; }
+              }
+            }
             if (nin + 12 > (1 << ACC_PLANES) - 1) {
-              if (live) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
+              acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt);
               nin = 0;
             }
           }
-          if (nin && live) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
+          if (nin) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
         }
         __syncthreads();
         // ---- (C) sum the subsets and credit the rows: depth += COV + QRK, errors += MIS + QRK
-        if (q < Q && s < W) {
-          const int Qu = min(Q, rl);   // subsets that hold counts
+        if (live) {
           for (int j = q; j < 32; j += Q) {
             // position j of the entry = nibble (j & 7) of word (j >> 3): counter pair index f*16 + (j >> 1), half = j & 1
             int cov = 0, qrk = 0, mis = 0;
             const int sh = (j & 1) * 16;
-            for (int qq = 0; qq < Qu; qq++) {
+            for (int qq = 0; qq < Q; qq++) {
               const uint32_t* oc = sm.cnt + qq * Wpad + s;
               cov += (oc[(0 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
               qrk += (oc[(1 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;

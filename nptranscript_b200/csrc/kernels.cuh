@@ -80,6 +80,9 @@ template <int MODE, bool REF_SMEM>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, const BatchDev b) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   if (MODE == 1 && ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  // behind the fast walk only the handed-over reads are walked here: blocks that would find the list empty leave at once
+  // (the grid is sized for a whole batch; loading the reference into shared memory costs more than walking a few reads)
+  if (b.fast && (unsigned long long)blockIdx.x * WALK_THREADS >= (unsigned long long)ldcg(b.bctr + 7)) return;
   // shared memory: [packed reference (if it fits), padded to 16 bytes] [per-warp CIGAR tiles 32 x 20] [per-warp base tiles 32 x 20]
   uint32_t* s_ref = s_dyn;
   const int ref_words = REF_SMEM ? ((c.ref_nwords + 3) & ~3) : 0;

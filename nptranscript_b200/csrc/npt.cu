@@ -765,7 +765,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
     // fast walk: tasks are 16 positions, so a break can only hide inside one when break_thresh < 16; with depth recording the
     // reference-grid entries of a chromosome must fit accumulate_kernel's shared tables.  Otherwise: serial walker for all.
     ctx->fast_record = cf.record_depth != 0;
-    ctx->fast = cf.break_thresh >= FW_TASK_MAX && ref_len < (1LL << 29) && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
+    ctx->fast = cf.break_thresh >= FW_PIECE && ref_len < (1LL << 29) && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
     if (const char* e = getenv("NPT_FAST")) if (atoi(e) == 0) ctx->fast = false;   // experiments / A-B runs
     if (ctx->fast) {
       const size_t refb = ctx->ref_smem ? (size_t)((dc.refg_nwords + 3) & ~3) * 4 : 0;
@@ -883,9 +883,12 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     d.slow_list = (unsigned*)B.f_slow;
     if (ctx->fast_record) {
       const size_t n_ent = ((size_t)d.seq_bytes >> 4) + 8 * (size_t)n + 8;
-      CK(pool_get(ctx, &B.f_hdr, (size_t)n * FW_HDR_WORDS * 4, &B.f_hdr_bytes));
+      // headers: uint4[n] + meta u32[n] + rare records u32[n][12], in one block (16-byte aligned sections)
+      const size_t hA = (size_t)n * 16, hM = (((size_t)n * 4) + 15) & ~(size_t)15, hR = (size_t)n * FW_RARE_WORDS * 4;
+      CK(pool_get(ctx, &B.f_hdr, hA + hM + hR, &B.f_hdr_bytes));
       CK(pool_get(ctx, &B.f_ent, n_ent * 16, &B.f_ent_bytes));
-      d.fhdr = (unsigned*)B.f_hdr; d.fent = (uint4*)B.f_ent;
+      d.fhdrA = (uint4*)B.f_hdr; d.fmeta = (unsigned*)((unsigned char*)B.f_hdr + hA); d.frare = (unsigned*)((unsigned char*)B.f_hdr + hA + hM);
+      d.fent = (uint4*)B.f_ent;
       unsigned maxkey = (unsigned)ctx->dc.cov_cap * (unsigned)ctx->dc.S;
       B.key_bits = 1;
       while ((1ull << B.key_bits) <= maxkey) B.key_bits++;

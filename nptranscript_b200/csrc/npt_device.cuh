@@ -94,7 +94,9 @@ struct BatchDev {
   // in slow_list are walked by walk_kernel<0/1/2>
   int fast;
   unsigned* slow_list;  // [n] read indices flagged NPT_RF_SLOWPATH
-  unsigned* fhdr;       // [n][16] per-read header of the fast walk (blocks of entries, junction points)
+  uint4* fhdrA;         // [n] first entry of the read in the arena + its (up to three) blocks of entries
+  unsigned* fmeta;      // [n] nblk | njunc << 8 | nextra << 16 | ndbl << 24
+  unsigned* frare;      // [n][12] rare per-read events (junction points, extras; fastwalk.cuh), valid where fmeta says so
   uint4* fent;          // entry arena: 32 positions x 4 flag bits per entry
 };
 

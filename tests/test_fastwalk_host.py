@@ -17,7 +17,7 @@ from tests.fuzz import random_batch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libhostfastwalk.so")
-HDR_WORDS, BRK_INLINE = 16, 6
+RARE_WORDS, BRK_INLINE = 12, 6
 
 
 def _lib():
@@ -29,7 +29,7 @@ def _lib():
         assert r.returncode == 0, r.stderr
         os.replace(tmp, SO)
     L = C.CDLL(SO)
-    L.hfw_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong] + [C.c_void_p] * 17
+    L.hfw_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong] + [C.c_void_p] * 19
     return L
 
 
@@ -49,14 +49,16 @@ def run_host(b, g, T, record):
     refg = ref_grid(g)
     out = dict(nbreaks=np.zeros(n, np.int32), arena=np.zeros(n * BRK_INLINE, np.int32), read_st=np.zeros(n, np.int32),
                read_en=np.zeros(n, np.int32), maps=np.zeros(n, np.int32), errs=np.zeros(n, np.int32), rflags=np.zeros(n, np.uint32),
-               bloc=np.zeros(n, np.uint32), fhdr=np.zeros(n * HDR_WORDS, np.uint32),
+               bloc=np.zeros(n, np.uint32), fhdrA=np.zeros(n * 4, np.uint32), fmeta=np.zeros(n, np.uint32),
+               frare=np.zeros(n * RARE_WORDS, np.uint32),
                fent=np.zeros(((int(b.seq_off[-1]) >> 4) + 8 * n + 8) * 4, np.uint32), slow=np.zeros(n + 1, np.uint32), bctr=np.zeros(8, np.uint32))
     seq4 = np.ascontiguousarray(b.seq4)
     cig = np.ascontiguousarray(b.cigar)
     nslow = L.hfw_run(T, len(g), record, refg.ctypes.data, len(refg), n, b.pos.ctypes.data, b.cigar_off.ctypes.data,
                       cig.ctypes.data, b.seq_off.ctypes.data, seq4.ctypes.data, out["nbreaks"].ctypes.data, out["arena"].ctypes.data,
                       out["read_st"].ctypes.data, out["read_en"].ctypes.data, out["maps"].ctypes.data, out["errs"].ctypes.data,
-                      out["rflags"].ctypes.data, out["bloc"].ctypes.data, out["fhdr"].ctypes.data, out["fent"].ctypes.data,
+                      out["rflags"].ctypes.data, out["bloc"].ctypes.data, out["fhdrA"].ctypes.data, out["fmeta"].ctypes.data, out["frare"].ctypes.data,
+                      out["fent"].ctypes.data,
                       out["slow"].ctypes.data, out["bctr"].ctypes.data)
     out["nslow"] = nslow
     return out
@@ -76,15 +78,15 @@ def coverage_from_entries(out, b, ora, G, S):
     """what cov_key_kernel + accumulate_kernel compute, in numpy"""
     nc, stride = ora["n_clusters"], G + 2
     cov = {k: np.zeros((nc, S, stride), np.int64) for k in ("depth", "errors", "map_start", "map_end")}
-    fhdr = out["fhdr"].reshape(-1, HDR_WORDS)
+    fhdrA, fmeta, frare = out["fhdrA"].reshape(-1, 4), out["fmeta"], out["frare"].reshape(-1, RARE_WORDS)
     fent = out["fent"].reshape(-1, 4)
     sh = (28 - 4 * np.arange(8)).astype(np.uint32)
     for r in range(b.n):
         c, s = int(ora["cluster_id"][r]), int(b.src[r])
         if c < 0:
             continue
-        h = fhdr[r]
-        nblk, njunc, nextra = int(h[4]) & 0xFF, (int(h[4]) >> 8) & 0xFF, (int(h[4]) >> 16) & 0xFF
+        h, meta, rare = fhdrA[r], int(fmeta[r]), frare[r]
+        nblk, njunc, nextra = meta & 0xFF, (meta >> 8) & 0xFF, (meta >> 16) & 0xFF
         e0 = int(h[0])
         assert all(int(h[1 + k]) == 0 for k in range(nblk, 3))
         for k in range(nblk):
@@ -102,13 +104,13 @@ def coverage_from_entries(out, b, ora, G, S):
         cov["map_start"][c, s, ora["start_pos"][r]] += 1
         cov["map_end"][c, s, ora["end_pos"][r]] += 1
         for j in range(njunc):
-            cov["map_end"][c, s, int(h[8 + 2 * j])] += 1
-            cov["map_start"][c, s, int(h[9 + 2 * j])] += 1
-        for d in range((int(h[4]) >> 24) & 0xFF):
-            cov["depth"][c, s, int(h[5 + d])] += 1
-            cov["errors"][c, s, int(h[5 + d])] += 1
+            cov["map_end"][c, s, int(rare[4 + 2 * j])] += 1
+            cov["map_start"][c, s, int(rare[5 + 2 * j])] += 1
+        for d in range((meta >> 24) & 0xFF):
+            cov["depth"][c, s, int(rare[d])] += 1
+            cov["errors"][c, s, int(rare[d])] += 1
         for e in range(nextra):
-            a, p = int(h[12 + 2 * e]), int(h[13 + 2 * e])
+            a, p = int(rare[8 + 2 * e]), int(rare[9 + 2 * e])
             if a & 0x80000000:
                 cov["depth"][c, s, a & 0x7FFFFFFF] += 1
                 cov["errors"][c, s, a & 0x7FFFFFFF] += 1
