@@ -58,7 +58,7 @@ def build_libnpt(force=False, verbose=False):
                 return LIBNPT  # GPU box without a toolchain on PATH: use the shipped build
             raise RuntimeError("nvcc not found and libnpt.so not built")
         tmp = LIBNPT + f".{os.getpid()}.tmp"
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", tmp] + cus
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NPT_NVCC_EXTRA", "").split() + ["-I", os.path.join(ROOT, "include"), "-o", tmp] + cus
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -18,9 +18,12 @@
 namespace npt {
 
 constexpr int FW_WARPS_MAX = 16;
-constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE, FW_PW_SRC = 32 + 64;
-__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? FW_RING * 32 : 0) + FW_PW_SRC; }
+constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE;
+__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : 0); }
 
+__device__ __forceinline__ void fw_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void fw_cp16z(uint32_t dst, const void* src, int n) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
 }
@@ -36,22 +39,21 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
   uint32_t* wb = fw_smem + refw + warp * fw_warp_words(RECORD);
   uint32_t* tileT = wb;                                                 // [32 lanes][CIGAR tile | base tile]
   uint32_t* ringT = tileT + FW_PW_TILE;
-  uint32_t* srcC = ringT + (RECORD ? FW_RING * 32 : 0);                 // [32] first CIGAR word to stage + 1, 0 = none
-  unsigned long long* srcS = (unsigned long long*)(srcC + 32);          // [32] first base byte to stage + 1, 0 = none
   if (REF_SMEM)
     for (int i = threadIdx.x; i < c.refg_nwords; i += blockDim.x) s_ref[i] = c.refg_words[i];
   if (RECORD)
-    for (int i = lane; i < FW_RING * 32; i += 32) ringT[i] = 0;
+    for (int i = lane; i < (FW_RING + FW_RING_PAD) * 32; i += 32) ringT[i] = 0;
   __syncthreads();
   const uint32_t* refg = REF_SMEM ? s_ref : c.refg_words;
   const uint32_t tileS = (uint32_t)__cvta_generic_to_shared(tileT);
   const uint32_t* cigL = tileT + lane * FW_TILE_STRIDE;
   const uint32_t* seqL = cigL + FW_CIG_TILE;
   unsigned* cursor = b.bctr + 5;
-  const long long cig_words = b.cigar_words, seq_bytes = b.seq_bytes;
+  const unsigned cig_words = (unsigned)b.cigar_words;                   // cigar_off is 32 bits
+  const unsigned long long seq_bytes = (unsigned long long)b.seq_bytes;
 
   FwLane L;
-  L.flags = 0; L.tb = -1; L.so = 0; L.readPos = 0; L.ck = 0; L.cs = 0; L.r = 0; L.cend = 0; L.mRem = 0; L.refPos = 0; L.flushE = 0; L.tnib0 = 0;
+  L.flags = 0; L.tb = -1; L.so = 0; L.readPos = 0; L.ck = 0; L.cs = 0; L.r = 0; L.cend = 0; L.mRem = 0; L.refPos = 0; L.flushE = 0; L.tnib0 = 0; L.st_r = 0;
   for (;;) {
     // ---- (0) lanes without a read take the next ones from the cursor (one atomic per warp and round)
     const bool want = (L.flags & (FWF_ACTIVE | FWF_DONE)) == 0;
@@ -67,46 +69,48 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
       }
     }
     if (__all_sync(FULL, (L.flags & (FWF_ACTIVE | FWF_DONE)) == FWF_DONE)) break;
-    // ---- (1) stage this round's CIGAR words and bases: every lane publishes what it needs, the warp copies all tiles
-    // together with 16-byte cp.async (a lane copying only its own tile costs one L1 wavefront per lane and copy)
+    // ---- (1) stage this round's CIGAR words and bases.  Every lane says what it needs (a shuffle away), the warp copies all
+    // tiles together with 16-byte cp.async so that neighbouring lanes fetch neighbouring chunks of one tile (a lane copying only
+    // its own tile costs one L1 wavefront per lane and copy)
     const bool live = (L.flags & (FWF_ACTIVE | FWF_SLOW)) == FWF_ACTIVE;
     {
       const unsigned ncs = L.ck & ~3u;
       const bool needC = live && ncs != L.cs && L.ck < L.cend;
       if (needC) L.cs = ncs;
-      srcC[lane] = needC ? ncs + 1u : 0u;
+      const unsigned myC = needC ? ncs + 1u : 0u;                        // first CIGAR word to stage + 1, 0 = none
       const long long ntb = (long long)((L.so + (unsigned long long)(L.readPos >> 1)) & ~15ull);
       const bool needS = live && ntb != L.tb;
       if (needS) { L.tb = ntb; L.tnib0 = (int)(2 * (ntb - (long long)L.so)); }
-      srcS[lane] = needS ? (unsigned long long)ntb + 1ull : 0ull;
-      __syncwarp();
+      const unsigned myS = needS ? (unsigned)((unsigned long long)ntb >> 4) + 1u : 0u;   // first 16-byte chunk to stage + 1, 0 = none
 #pragma unroll
-      for (int it = 0; it < FW_CIG_TILE / 4; it++) {     // 32 tiles x 5 chunks
+      for (int it = 0; it < FW_CIG_TILE / 4; it++) {
         const unsigned id = it * 32 + lane, owner = id / (FW_CIG_TILE / 4), ch = id - owner * (FW_CIG_TILE / 4);
-        const unsigned s1 = srcC[owner];
+        const unsigned s1 = __shfl_sync(FULL, myC, owner);
         if (s1) {
-          const long long w0 = (long long)(s1 - 1u) + 4 * ch;
-          const long long left = (cig_words - w0) * 4;
-          fw_cp16z(tileS + (owner * FW_TILE_STRIDE + 4 * ch) * 4, left > 0 ? (const void*)(b.cigar + w0) : (const void*)b.cigar, (int)max(0LL, min(16LL, left)));
+          const unsigned w0 = s1 - 1u + 4u * ch;
+          const uint32_t dst = tileS + (owner * FW_TILE_STRIDE + 4 * ch) * 4;
+          if (w0 + 4u <= cig_words) fw_cp16(dst, b.cigar + w0);
+          else fw_cp16z(dst, w0 < cig_words ? (const void*)(b.cigar + w0) : (const void*)b.cigar, w0 < cig_words ? (int)(cig_words - w0) * 4 : 0);
         }
       }
 #pragma unroll
-      for (int it = 0; it < FW_SEQ_TILE / 4; it++) {     // 32 tiles x 6 chunks
+      for (int it = 0; it < FW_SEQ_TILE / 4; it++) {
         const unsigned id = it * 32 + lane, owner = id / (FW_SEQ_TILE / 4), ch = id - owner * (FW_SEQ_TILE / 4);
-        const unsigned long long s1 = srcS[owner];
+        const unsigned s1 = __shfl_sync(FULL, myS, owner);
         if (s1) {
-          const long long a0 = (long long)(s1 - 1ull) + 16 * ch;
-          const long long left = seq_bytes - a0;
-          fw_cp16z(tileS + (owner * FW_TILE_STRIDE + FW_CIG_TILE + 4 * ch) * 4, left > 0 ? (const void*)(b.seq4 + a0) : (const void*)b.seq4, (int)max(0LL, min(16LL, left)));
+          const unsigned long long a0 = ((unsigned long long)(s1 - 1u) + ch) << 4;
+          const uint32_t dst = tileS + (owner * FW_TILE_STRIDE + FW_CIG_TILE + 4 * ch) * 4;
+          if (a0 + 16ull <= seq_bytes) fw_cp16(dst, b.seq4 + a0);
+          else fw_cp16z(dst, a0 < seq_bytes ? (const void*)(b.seq4 + a0) : (const void*)b.seq4, a0 < seq_bytes ? (int)(seq_bytes - a0) : 0);
         }
       }
       fw_cp_wait();
       __syncwarp();
     }
     // ---- (2) FW_R steps: [one element that is not M] + [start of the M behind it] + [<= 16 positions of the current M]
-    bool run = live;
+    const int ringLimit = (L.flushE << 5) + FW_RING * 8 - 2 * FW_PIECE - 2;
 #pragma unroll 1
-    for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigL, seqL, refg, ringT + lane, 32, run);
+    for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigL, seqL, refg, ringT + lane, 32, live, ringLimit);
     __syncwarp();
     // ---- (3) N elements, completed entries, closed blocks, finished reads
     fw_round_end<RECORD>(L, c, b, cigL, ringT + lane, 32);
@@ -147,10 +151,11 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
         if (njunc | nextra) {
           const uint4 h2 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 4));
           const uint4 h3 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 8));
+          const uint4 h4 = nextra > 2 ? __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 12)) : make_uint4(0u, 0u, 0u, 0u);
           if (njunc > 0) { atomicAdd(mend + h2.x, 1); atomicAdd(mstart + h2.y, 1); }
           if (njunc > 1) { atomicAdd(mend + h2.z, 1); atomicAdd(mstart + h2.w, 1); }
           for (int e = 0; e < nextra; e++) {
-            const unsigned a = e == 0 ? h3.x : h3.z, p = e == 0 ? h3.y : h3.w;
+            const unsigned a = e == 0 ? h3.x : (e == 1 ? h3.z : (e == 2 ? h4.x : h4.z)), p = e == 0 ? h3.y : (e == 1 ? h3.w : (e == 2 ? h4.y : h4.w));
             if (a & 0x80000000u) {          // a position emitted by two D elements
               const unsigned q = a & 0x7FFFFFFFu;
               atomicAdd(cov + 8 * arr_stride + q, 1);   // depth

@@ -877,13 +877,14 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   // fast walk: work list of the serial walker; with depth recording also headers, the entry arena (16 bytes per 32 reference
   // positions a read covers: its share is (bytes of bases / 16) + 8 entries) and the sort buffers
   d.fast = ctx->fast ? 1 : 0;
+  if (d.fast && ((uint64_t)d.seq_bytes >> 4) + 2 >= (1ull << 32)) d.fast = 0;  // the walk names 16-byte chunks of the bases with 32 bits
   if (d.fast && ctx->fast_record && ((uint64_t)d.seq_bytes >> 4) + 8ull * (uint64_t)n + 8 >= (1ull << 32)) d.fast = 0;  // entry index is 32 bits
   if (d.fast) {
     CK(pool_get(ctx, &B.f_slow, (size_t)n * 4, &B.f_slow_bytes));
     d.slow_list = (unsigned*)B.f_slow;
     if (ctx->fast_record) {
       const size_t n_ent = ((size_t)d.seq_bytes >> 4) + 8 * (size_t)n + 8;
-      // headers: uint4[n] + meta u32[n] + rare records u32[n][12], in one block (16-byte aligned sections)
+      // headers: uint4[n] + meta u32[n] + rare records u32[n][16], in one block (16-byte aligned sections)
       const size_t hA = (size_t)n * 16, hM = (((size_t)n * 4) + 15) & ~(size_t)15, hR = (size_t)n * FW_RARE_WORDS * 4;
       CK(pool_get(ctx, &B.f_hdr, hA + hM + hR, &B.f_hdr_bytes));
       CK(pool_get(ctx, &B.f_ent, n_ent * 16, &B.f_ent_bytes));

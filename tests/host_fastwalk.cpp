@@ -12,7 +12,7 @@ using namespace npt;
 
 template <bool RECORD>
 static void run_all(const DevCfg& c, const BatchDev& b) {
-  std::vector<uint32_t> tile(FW_TILE_STRIDE + 4), ring(FW_RING, 0);
+  std::vector<uint32_t> tile(FW_TILE_STRIDE + 4), ring(FW_RING + FW_RING_PAD, 0);
   uint32_t* cigT = tile.data();
   uint32_t* seqT = tile.data() + FW_CIG_TILE;
   for (long long r = 0; r < b.n; r++) {
@@ -32,8 +32,8 @@ static void run_all(const DevCfg& c, const BatchDev& b) {
         unsigned char* dst = (unsigned char*)seqT;
         for (int i = 0; i < FW_SEQ_TILE * 4; i++) dst[i] = (ntb + i < b.seq_bytes) ? b.seq4[ntb + i] : 0;
       }
-      bool run = live;
-      for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigT, seqT, c.refg_words, ring.data(), 1, run);
+      const int ringLimit = (L.flushE << 5) + FW_RING * 8 - 2 * FW_PIECE - 2;
+      for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigT, seqT, c.refg_words, ring.data(), 1, live, ringLimit);
       fw_round_end<RECORD>(L, c, b, cigT, ring.data(), 1);
     }
   }

@@ -17,7 +17,7 @@ from tests.fuzz import random_batch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libhostfastwalk.so")
-RARE_WORDS, BRK_INLINE = 12, 6
+RARE_WORDS, BRK_INLINE = 16, 6
 
 
 def _lib():
@@ -207,6 +207,10 @@ def test_known_answers():
     assert arena[1, :4].tolist() == [5, 67, 28262, 29859]
     assert arena[2, :2].tolist() == [100, 111]
     assert arena[3, :4].tolist() == [100, 109, 2112, 2119]
-    # KAT2 proper has three mismatching emissions right after the junction: more than the two a header holds -> serial path
-    assert run_host(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67)))]), g, 1000, 1)["nslow"] == 1
+    # KAT2 proper: three mismatching emissions right after the junction (three of the four extras a header holds)
+    k2 = run_host(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67)))]), g, 1000, 1)
+    assert k2["nslow"] == 0 and k2["arena"][:4].tolist() == [5, 67, 28263, 29859] and (int(k2["fmeta"][0]) >> 16) & 0xFF == 3
+    # five of them are more than a header holds -> serial path
+    assert run_host(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67, 68, 69)))]), g, 1000, 1)["nslow"] == 1
+    check(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67)))]), g, w, 1000, min_fast=1.0)
     check(b, g, w, 1000, min_fast=1.0)
