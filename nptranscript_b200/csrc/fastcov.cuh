@@ -119,21 +119,25 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
 }
 
 // ------------------------------------------------------------------------------------------------ keys + start/end points
-// key = coverage row of the read's cluster * S + source; reads that are not credited by accumulate_kernel (walked by the
-// serial path, bad records, unclustered) get the sentinel cov_cap * S and sort to the end.
-__global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys, unsigned* vals) {
+// key = (coverage row of the read's cluster * S + source) << ACC_POS_BITS | coarse start position; reads that are not credited
+// by accumulate_kernel (walked by the serial path, bad records, unclustered) get the sentinel row cov_cap * S and sort to the
+// end.  The position bits make neighbours in the sorted order cover neighbouring parts of the reference, so that the reads of
+// one tile of a wide cluster (genomic fragments anywhere in 20 kb) touch few reference-grid entries.
+constexpr int ACC_POS_BITS = 10;
+__global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys, unsigned* vals, int pos_shift) {
   if (__ldcg(b.bctr + 1)) return;  // break lists incomplete, nothing was clustered: the host re-runs this batch
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
     const unsigned rf = b.rflags[r];
     const int slot = b.cluster[r];
-    unsigned key = (unsigned)c.cov_cap * (unsigned)c.S;
+    unsigned key = ((unsigned)c.cov_cap * (unsigned)c.S) << ACC_POS_BITS;
     if (!(rf & 0x30u) && slot >= 0) {
       const int prov = __ldcg(c.cl_rec + (unsigned)(__ldcg(&c.cl[slot].word) & 0xffffffffu));
       const int src = b.src[r];
       if (prov >= c.cov_cap) atomicOr(c.counters + CN_ERROR, (unsigned)ERR_COV_FULL);
       else {
-        key = (unsigned)prov * (unsigned)c.S + (unsigned)src;
+        const unsigned first = __ldg(&b.fhdrA[r].y) & 0xFFFFu;   // first reference-grid entry of the read's first block
+        key = (((unsigned)prov * (unsigned)c.S + (unsigned)src) << ACC_POS_BITS) | min(first >> pos_shift, (1u << ACC_POS_BITS) - 1u);
         int* cov = c.cov + ((long long)prov * c.S + src) * c.stride;
         int* mstart = cov + 2 * arr_stride;
         int* mend = cov + 3 * arr_stride;
@@ -172,27 +176,28 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
 }
 
 // ------------------------------------------------------------------------------------------------ positional popcount
+// Per (cluster, source) run of the sorted reads: thread = (reference-grid entry s, read subset q).  A thread adds the entries
+// of its reads into 8 bit planes per entry word (carry-save adders: a 3:2 compressor is two LOP3), 252 reads before the planes
+// could overflow.  The subsets are then summed plane-wise (bit-sliced ripple adders, still no per-position work) by four
+// threads per entry, and only that one total per entry word is expanded into per-position counts and credited with one RED
+// per touched position and row.
 constexpr int ACC_THREADS = 768;
 constexpr int ACC_TILE = 2048;        // key-sorted reads per block tile
 constexpr int ACC_MAX_ENT = 8192;     // reference-grid entries (32 positions each) a chromosome may have on this path
-constexpr int ACC_PLANES = 6;         // bit-sliced counters hold 63 reads before they are expanded
-constexpr int ACC_CNT_WORDS = 48;     // 96 16-bit counters per thread: (COV, QRK, MIS) x 32 positions
+constexpr int ACC_PLANES = 8;         // per-thread planes: 255 reads
+constexpr int ACC_SUM_PLANES = 12;    // per-entry total of a tile: 2048 reads
+constexpr int ACC_EPOCH = 252;        // reads per thread between two reductions (63 steps of four)
 
 struct AccSmem {
-  uint32_t cnt[ACC_CNT_WORDS * ACC_THREADS];   // [word][thread]
-  uint4 hdr[ACC_TILE];                         // the tile's read headers {first entry, block 0, 1, 2}
+  uint32_t planes[ACC_PLANES * 4 * ACC_THREADS];   // [plane][word][thread]
+  uint4 hdr[ACC_TILE];                             // the tile's read headers {first entry, block 0, 1, 2}
   uint32_t head[ACC_TILE / 32];
   uint32_t act[ACC_MAX_ENT / 32];
   uint32_t actpre[ACC_MAX_ENT / 32 + 1];
   uint16_t word_of[ACC_MAX_ENT];
 };
 
-__device__ __forceinline__ void acc_add(uint32_t (&p)[ACC_PLANES], uint32_t x) {
-#pragma unroll
-  for (int k = 0; k < ACC_PLANES; k++) { const uint32_t cy = p[k] & x; p[k] ^= x; x = cy; }
-}
-
-// four words at once: carry-save adders (xor3 / majority are one LOP3 each), then the carry of weight 4 ripples up
+// four words into the planes at once
 __device__ __forceinline__ void acc_add4(uint32_t (&p)[ACC_PLANES], uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   const uint32_t s1 = p[0] ^ a ^ b, c1 = (p[0] & a) | (p[0] & b) | (a & b);
   const uint32_t s2 = s1 ^ c ^ d, c2 = (s1 & c) | (s1 & d) | (c & d);
@@ -203,28 +208,20 @@ __device__ __forceinline__ void acc_add4(uint32_t (&p)[ACC_PLANES], uint32_t a, 
 #pragma unroll
   for (int k = 2; k < ACC_PLANES; k++) { const uint32_t cy = p[k] & x; p[k] ^= x; x = cy; }
 }
-
-// planes of one entry word -> the thread's 16-bit counters.  Byte lane m of ((plane >> j) & 0x01010101) is bit 8m+j of the
-// word = flag (j & 3) of nibble 7 - 2m - (j >> 2) counted from the top.
-__device__ __forceinline__ void acc_expand(uint32_t (&p)[ACC_PLANES], int k, uint32_t* cnt) {
-#pragma unroll
-  for (int f = 0; f < 3; f++) {
-    const int fb = f == 2 ? 3 : f;   // flag bits 0 (COV), 1 (QRK), 3 (MIS)
-    uint32_t A = 0, B = 0;           // A: odd nibbles (j = fb), B: even nibbles (j = fb + 4), four byte counters each
-#pragma unroll
-    for (int q = 0; q < ACC_PLANES; q++) {
-      A += ((p[q] >> fb) & 0x01010101u) << q;
-      B += ((p[q] >> (fb + 4)) & 0x01010101u) << q;
-    }
-#pragma unroll
-    for (int m = 0; m < 4; m++) {
-      const uint32_t v = ((B >> (8 * m)) & 0xFFu) | (((A >> (8 * m)) & 0xFFu) << 16);
-      // counters of nibbles (6 - 2m, 7 - 2m) of word k: counter pair index f*16 + 4k + 3 - m
-      if (v) cnt[(f * 16 + 4 * k + 3 - m) * ACC_THREADS] += v;
+// one entry credited directly, position by position (the rare second entry of a read on the same reference-grid entry)
+__device__ __noinline__ void acc_credit_entry(const uint4 x, unsigned myw, int* row_dep, int* row_err, int stride) {
+  for (int w = 0; w < 4; w++) {
+    const uint32_t v = w == 0 ? x.x : (w == 1 ? x.y : (w == 2 ? x.z : x.w));
+    for (int i = 0; i < 8; i++) {
+      const uint32_t nib = (v >> (28 - 4 * i)) & 0xFu;
+      const int pos = (int)myw * 32 + 8 * w + i;
+      if (nib && pos < stride) {
+        const int cov = nib & 1u, qrk = (nib >> 1) & 1u, mis = (nib >> 3) & 1u;
+        if (cov + qrk) atomicAdd(row_dep + pos, cov + qrk);
+        if (mis + qrk) atomicAdd(row_err + pos, mis + qrk);
+      }
     }
   }
-#pragma unroll
-  for (int q = 0; q < ACC_PLANES; q++) p[q] = 0;
 }
 
 // which of a read's entries lies on reference-grid entry `myw`: index into the read's entries, or -1.  `more` = a later block of
@@ -233,8 +230,9 @@ __device__ __forceinline__ int acc_entry_index(const uint4 h, unsigned myw, bool
   const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
   const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
   const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
-  more = (in0 && (in1 || in2)) || (in1 && in2);
-  return in0 ? (int)d0 : (in1 ? (int)(c0 + d1) : (in2 ? (int)(c0 + c1 + d2) : -1));
+  more = (in0 & (in1 | in2)) | (in1 & in2);
+  const unsigned i12 = in1 ? c0 + d1 : c0 + c1 + d2;
+  return (in0 | in1 | in2) ? (int)(in0 ? d0 : i12) : -1;
 }
 
 __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg c, const BatchDev b, const unsigned* keys, const unsigned* vals,
@@ -244,11 +242,10 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
   AccSmem& sm = *reinterpret_cast<AccSmem*>(acc_raw);
   __shared__ int s_tile, s_wact;
   const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned invalid = (unsigned)c.cov_cap * (unsigned)c.S;
+  const unsigned invalid = (unsigned)c.cov_cap * (unsigned)c.S;   // row part of the key of reads that are not credited here
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
   const int n_ent = (c.stride + 31) / 32 + 1;
   const int n_actw = (n_ent + 31) / 32;
-  uint32_t* mycnt = sm.cnt + tid;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   for (;;) {
     if (tid == 0) s_tile = (int)atomicAdd(tile_cursor, 1u);
@@ -259,14 +256,14 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
     __syncthreads();
     if (t0 < 0) break;
     const int tn = (int)min((long long)ACC_TILE, b.n - t0);
-    if (__ldg(keys + t0) == invalid) continue;   // sorted: this tile holds only reads that are not credited here
-    // ---- the tile: read headers into shared memory, head flags of the runs of equal key
+    if ((__ldg(keys + t0) >> ACC_POS_BITS) == invalid) continue;   // sorted: this tile holds only reads that are not credited here
+    // ---- the tile: read headers into shared memory, head flags of the runs of equal (row, source)
     for (int i = tid; i < ACC_TILE; i += ACC_THREADS) {
       bool head = false;
       if (i < tn) {
-        const unsigned k = __ldg(keys + t0 + i);
+        const unsigned k = __ldg(keys + t0 + i) >> ACC_POS_BITS;
         sm.hdr[i] = k == invalid ? zero4 : __ldg(b.fhdrA + __ldg(vals + t0 + i));
-        head = (i == 0) || (k != __ldg(keys + t0 + i - 1));
+        head = (i == 0) || (k != (__ldg(keys + t0 + i - 1) >> ACC_POS_BITS));
       }
       const unsigned hb = __ballot_sync(0xffffffffu, head);
       if (lane == 0) sm.head[i >> 5] = hb;
@@ -283,7 +280,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
         while (!bits && ++w < nw) bits = sm.head[w];
         if (bits && w < nw) i1 = min(tn, w * 32 + __ffs(bits) - 1);
       }
-      const unsigned key = __ldg(keys + t0 + i0);
+      const unsigned key = __ldg(keys + t0 + i0) >> ACC_POS_BITS;
       if (key == invalid) break;
       const int rl = i1 - i0;
       const uint4* hdr = sm.hdr + i0;
@@ -335,81 +332,95 @@ __global__ void __launch_bounds__(ACC_THREADS, 1) accumulate_kernel(const DevCfg
       for (int slot0 = 0; slot0 < wact; slot0 += ACC_THREADS) {
         const int W = min(ACC_THREADS, wact - slot0);
         const int Wpad = (W + 31) & ~31;
-        const int Q = min(ACC_THREADS / Wpad, (rl + 3) >> 2);   // no more subsets than groups of four reads
+        // subsets: the main loop costs ~ rl / Q per thread, the reduction ~ Q per entry word: balanced near sqrt(rl)
+        int Q = 1;
+        while (Q * Q * 2 < rl && (Q + 1) * Wpad <= ACC_THREADS) Q++;
         const int q = tid / Wpad, s = tid - q * Wpad;
         const bool live = q < Q && s < W;
         const unsigned myw = (s < W) ? sm.word_of[slot0 + s] : 0u;
-        if (live)
+        for (int e0 = 0; e0 < rl; e0 += ACC_EPOCH * Q) {
+          const int e1 = min(rl, e0 + ACC_EPOCH * Q);
+          uint32_t P0[ACC_PLANES], P1[ACC_PLANES], P2[ACC_PLANES], P3[ACC_PLANES];
 #pragma unroll
-          for (int k = 0; k < ACC_CNT_WORDS; k++) mycnt[k * ACC_THREADS] = 0;
-        uint32_t P0[ACC_PLANES], P1[ACC_PLANES], P2[ACC_PLANES], P3[ACC_PLANES];   // [0] ones, [1] twos, [2..] 4s 8s 16s 32s
+          for (int k = 0; k < ACC_PLANES; k++) { P0[k] = 0; P1[k] = 0; P2[k] = 0; P3[k] = 0; }
+          if (live) {
+            // four reads per step: headers come from shared memory (one broadcast load each), so the four entry loads are in flight together
+            for (int i = e0 + q; i < e1; i += 4 * Q) {
+              uint4 e[4];
+              bool extra = false;
 #pragma unroll
-        for (int k = 0; k < ACC_PLANES; k++) { P0[k] = 0; P1[k] = 0; P2[k] = 0; P3[k] = 0; }
-        int nin = 0;
-        if (live) {
-          // four reads per step: headers come from shared memory (one broadcast load each), so the four entry loads are in
-          // flight together; their words go through one carry-save tree (3 inputs -> sum + carry is two LOP3)
-          for (int i = q; i < rl; i += 4 * Q) {
-            uint4 e[4];
-            bool extra = false;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              e[j] = zero4;
-              const int ii = i + j * Q;
-              if (ii < rl) {
+              for (int j = 0; j < 4; j++) {
+                e[j] = zero4;
+                const int ii = min(i + j * Q, e1 - 1);
+                const bool ok = i + j * Q < e1;
                 const uint4 h = hdr[ii];
                 bool more;
                 const int idx = acc_entry_index(h, myw, more);
-                if (idx >= 0) e[j] = __ldg(b.fent + (size_t)h.x + idx);
-                extra |= more;
+                if (ok & (idx >= 0)) e[j] = __ldg(b.fent + (size_t)h.x + idx);
+                extra |= ok & more;
               }
-            }
-            acc_add4(P0, e[0].x, e[1].x, e[2].x, e[3].x);
-            acc_add4(P1, e[0].y, e[1].y, e[2].y, e[3].y);
-            acc_add4(P2, e[0].z, e[1].z, e[2].z, e[3].z);
-            acc_add4(P3, e[0].w, e[1].w, e[2].w, e[3].w);
-            nin += 4;
-            if (extra) {   // rare: the later blocks' entries for the same grid entry
+              acc_add4(P0, e[0].x, e[1].x, e[2].x, e[3].x);
+              acc_add4(P1, e[0].y, e[1].y, e[2].y, e[3].y);
+              acc_add4(P2, e[0].z, e[1].z, e[2].z, e[3].z);
+              acc_add4(P3, e[0].w, e[1].w, e[2].w, e[3].w);
+              if (extra) {   // rare: the later blocks' entries for the same grid entry are credited directly
 #pragma unroll 1
-              for (int j = 0; j < 4; j++) {
-                const int ii = i + j * Q;
-                if (ii >= rl) break;
-                const uint4 h = hdr[ii];
-                const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
-                const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
-                const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
-                if (in0 && in1) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + d1); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); nin++; }
-                if ((in0 || in1) && in2) { const uint4 x = __ldg(b.fent + (size_t)h.x + c0 + c1 + d2); acc_add(P0, x.x); acc_add(P1, x.y); acc_add(P2, x.z); acc_add(P3, x.w); nin++; }
+                for (int j = 0; j < 4; j++) {
+                  const int ii = i + j * Q;
+                  if (ii >= e1) break;
+                  const uint4 h = hdr[ii];
+                  const unsigned c0 = h.y >> 16, c1 = h.z >> 16, c2 = h.w >> 16;
+                  const unsigned d0 = myw - (h.y & 0xFFFFu), d1 = myw - (h.z & 0xFFFFu), d2 = myw - (h.w & 0xFFFFu);
+                  const bool in0 = d0 < c0, in1 = d1 < c1, in2 = d2 < c2;
+                  if (in0 && in1) acc_credit_entry(__ldg(b.fent + (size_t)h.x + c0 + d1), myw, row_dep, row_err, c.stride);
+                  if ((in0 || in1) && in2) acc_credit_entry(__ldg(b.fent + (size_t)h.x + c0 + c1 + d2), myw, row_dep, row_err, c.stride);
+                }
               }
             }
-            if (nin + 12 > (1 << ACC_PLANES) - 1) {
-              acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt);
-              nin = 0;
+#pragma unroll
+            for (int k = 0; k < ACC_PLANES; k++) {
+              sm.planes[(k * 4 + 0) * ACC_THREADS + tid] = P0[k]; sm.planes[(k * 4 + 1) * ACC_THREADS + tid] = P1[k];
+              sm.planes[(k * 4 + 2) * ACC_THREADS + tid] = P2[k]; sm.planes[(k * 4 + 3) * ACC_THREADS + tid] = P3[k];
             }
           }
-          if (nin) { acc_expand(P0, 0, mycnt); acc_expand(P1, 1, mycnt); acc_expand(P2, 2, mycnt); acc_expand(P3, 3, mycnt); }
-        }
-        __syncthreads();
-        // ---- (C) sum the subsets and credit the rows: depth += COV + QRK, errors += MIS + QRK
-        if (live) {
-          for (int j = q; j < 32; j += Q) {
-            // position j of the entry = nibble (j & 7) of word (j >> 3): counter pair index f*16 + (j >> 1), half = j & 1
-            int cov = 0, qrk = 0, mis = 0;
-            const int sh = (j & 1) * 16;
+          __syncthreads();
+          // ---- (C) per entry word: plane-wise sum of the subsets, then per-position counts and the REDs.
+          // Thread (s, w = q) for q < 4; with fewer than four subsets the remaining words are taken in further rounds.
+          for (int w = q; w < 4; w += Q) {
+            if (!live) break;
+            uint32_t T[ACC_SUM_PLANES];
+#pragma unroll
+            for (int k = 0; k < ACC_SUM_PLANES; k++) T[k] = 0;
             for (int qq = 0; qq < Q; qq++) {
-              const uint32_t* oc = sm.cnt + qq * Wpad + s;
-              cov += (oc[(0 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
-              qrk += (oc[(1 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
-              mis += (oc[(2 * 16 + (j >> 1)) * ACC_THREADS] >> sh) & 0xFFFF;
+              uint32_t cy = 0;
+#pragma unroll
+              for (int k = 0; k < ACC_PLANES; k++) {   // full adders: T[k] + plane k of subset qq + carry
+                const uint32_t x = sm.planes[(k * 4 + w) * ACC_THREADS + qq * Wpad + s];
+                const uint32_t sum = T[k] ^ x ^ cy;
+                cy = (T[k] & x) | (T[k] & cy) | (x & cy);
+                T[k] = sum;
+              }
+#pragma unroll
+              for (int k = ACC_PLANES; k < ACC_SUM_PLANES; k++) { const uint32_t t2 = T[k] & cy; T[k] ^= cy; cy = t2; }
             }
-            const int pos = (int)myw * 32 + j;
-            if (pos < c.stride) {
-              if (cov + qrk) atomicAdd(row_dep + pos, cov + qrk);
-              if (mis + qrk) atomicAdd(row_err + pos, mis + qrk);
+            // position 8w + i of the entry = nibble i of the word counted from the top: flag bit fb of it is bit 28 - 4i + fb
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              int cov = 0, qrk = 0, mis = 0;
+#pragma unroll
+              for (int k = 0; k < ACC_SUM_PLANES; k++) {
+                const uint32_t nib = (T[k] >> (28 - 4 * i)) & 0xFu;
+                cov += (int)(nib & 1u) << k; qrk += (int)((nib >> 1) & 1u) << k; mis += (int)((nib >> 3) & 1u) << k;
+              }
+              const int pos = (int)myw * 32 + 8 * w + i;
+              if (pos < c.stride) {
+                if (cov + qrk) atomicAdd(row_dep + pos, cov + qrk);
+                if (mis + qrk) atomicAdd(row_err + pos, mis + qrk);
+              }
             }
           }
+          __syncthreads();
         }
-        __syncthreads();
       }
       i0 = i1;
     }

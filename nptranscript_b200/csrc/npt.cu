@@ -109,7 +109,7 @@ struct npt_ctx {
   // fast walk (fastwalk.cuh / fastcov.cuh)
   DBuf<uint32_t> d_refg;
   bool fast = false, fast_record = false;
-  int fw_blocks = 0, fw_threads = 0, acc_blocks = 0;
+  int fw_blocks = 0, fw_threads = 0, acc_blocks = 0, acc_pos_shift = 0;
   size_t fw_smem = 0;
   DBuf<PairEntry> d_pr;
   DBuf<int> d_cov, d_cov_out;
@@ -442,7 +442,7 @@ int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
   if (dc.record_depth && bd.fast) {
     // coverage of the fast reads: key = (coverage row, source) -> radix sort -> positional popcount per group
     const int kgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + 255) / 256, (long long)ctx->sm_count * 16));
-    cov_key_kernel<<<kgrid, 256, 0, ctx->s_comp>>>(dc, bd, B.k_in, B.v_in);
+    cov_key_kernel<<<kgrid, 256, 0, ctx->s_comp>>>(dc, bd, B.k_in, B.v_in, ctx->acc_pos_shift);
     size_t tmp = B.cub_bytes;
     CK(cub::DeviceRadixSort::SortPairs(B.cub_tmp, tmp, B.k_in, B.k_out, B.v_in, B.v_out, (int)bd.n, 0, B.key_bits, ctx->s_comp));
     accumulate_kernel<<<ctx->acc_blocks, ACC_THREADS, sizeof(AccSmem), ctx->s_comp>>>(dc, bd, B.k_out, B.v_out, bd.bctr + 6);
@@ -765,7 +765,8 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
     // fast walk: tasks are 16 positions, so a break can only hide inside one when break_thresh < 16; with depth recording the
     // reference-grid entries of a chromosome must fit accumulate_kernel's shared tables.  Otherwise: serial walker for all.
     ctx->fast_record = cf.record_depth != 0;
-    ctx->fast = cf.break_thresh >= FW_PIECE && ref_len < (1LL << 29) && (!ctx->fast_record || (dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT);
+    ctx->fast = cf.break_thresh >= FW_PIECE && ref_len < (1LL << 29) &&
+                (!ctx->fast_record || ((dc.stride + 31) / 32 + 1 <= ACC_MAX_ENT && (((unsigned long long)dc.cov_cap * dc.S + 1) << ACC_POS_BITS) < (1ull << 32)));
     if (const char* e = getenv("NPT_FAST")) if (atoi(e) == 0) ctx->fast = false;   // experiments / A-B runs
     if (ctx->fast) {
       const size_t refb = ctx->ref_smem ? (size_t)((dc.refg_nwords + 3) & ~3) * 4 : 0;
@@ -787,6 +788,8 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
         if (ctx->fast_record) {
           CK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
           ctx->acc_blocks = ctx->sm_count;
+          ctx->acc_pos_shift = 0;   // coarse start position of a read in the sort key: reference-grid entry >> shift < 2^ACC_POS_BITS
+          while ((((dc.stride + 31) / 32 + 1) >> ctx->acc_pos_shift) >= (1 << ACC_POS_BITS)) ctx->acc_pos_shift++;
         }
       }
     }
@@ -890,7 +893,7 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
       CK(pool_get(ctx, &B.f_ent, n_ent * 16, &B.f_ent_bytes));
       d.fhdrA = (uint4*)B.f_hdr; d.fmeta = (unsigned*)((unsigned char*)B.f_hdr + hA); d.frare = (unsigned*)((unsigned char*)B.f_hdr + hA + hM);
       d.fent = (uint4*)B.f_ent;
-      unsigned maxkey = (unsigned)ctx->dc.cov_cap * (unsigned)ctx->dc.S;
+      unsigned long long maxkey = (((unsigned long long)ctx->dc.cov_cap * (unsigned)ctx->dc.S + 1) << ACC_POS_BITS) - 1;
       B.key_bits = 1;
       while ((1ull << B.key_bits) <= maxkey) B.key_bits++;
       size_t tmp = 0;
