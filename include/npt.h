@@ -146,6 +146,34 @@ typedef struct npt_batch {
   const uint8_t* seq4;
 } npt_batch;
 
+/* The same records in the compact transfer format (host memory only).  The end-to-end path is bound by the host-to-device
+ * link (1 681 B per SARS-CoV-2 dRNA read as npt_batch); this form moves 852 B per read and is expanded into the npt_batch
+ * layout by two copy kernels on the device (unpack.cuh), bit-identical to submitting the expanded arrays:
+ *   cigar16   one 16-bit word per CIGAR element: (len<<4)|op for len < 4095, else 0xFFF0|op and the element appears in the
+ *             wide list (wide_idx = element index in the batch, ascending; wide_word = its full 32-bit BAM word)
+ *   seq2      two bits per base, A C G T = 0 1 2 3, four bases per byte, first base in the top bits; position-aligned with
+ *             seq4 (nibble k of the seq4 stream = base k of the seq2 stream, so seq2 has ceil(seq_off[n] / 2) bytes)
+ *   exc_byte / exc_val   seq4 bytes that hold any code other than A C G T (N, IUPAC, '=', the pad nibble of an odd-length
+ *             read when it is not one of 1 2 4 8): index into the seq4 stream and the byte to put there
+ * cigar_off / seq_off are those of the equivalent npt_batch (elements / seq4 bytes).  The packer for BAM records is
+ * nptbam (include/npt_bam.h); nptranscript_b200/packed.py is the numpy one the tests and bench use. */
+typedef struct npt_packed_batch {
+  int64_t n;
+  const int32_t* pos;
+  const uint16_t* flag;
+  const uint16_t* src;
+  const uint32_t* cigar_off;
+  const uint16_t* cigar16;
+  int64_t n_wide;
+  const uint32_t* wide_idx;
+  const uint32_t* wide_word;
+  const uint64_t* seq_off;
+  const uint8_t* seq2;
+  int64_t n_exc;
+  const uint64_t* exc_byte;
+  const uint8_t* exc_val;
+} npt_packed_batch;
+
 /* Everything the reference's writers need, in host memory owned by the context
  * (valid until npt_release_results / npt_begin_chrom / npt_destroy). */
 typedef struct npt_results {
@@ -213,6 +241,8 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
  * (with first_is_transcriptome the end-of-chromosome pass reads src again).  A record whose src is >= num_sources makes
  * npt_end_chrom fail with NPT_EINVAL. */
 int npt_submit(npt_ctx* ctx, const npt_batch* batch);
+/* npt_submit for a batch in the compact transfer format (host arrays, untouched until npt_wait). */
+int npt_submit_packed(npt_ctx* ctx, const npt_packed_batch* batch);
 int npt_wait(npt_ctx* ctx);
 /* Drains, assigns first-appearance ids (sort-and-rank), rewrites per-read ids, scans the coverage difference arrays. */
 int npt_end_chrom(npt_ctx* ctx);

@@ -38,6 +38,14 @@ class npt_batch(C.Structure):
     ]
 
 
+class npt_packed_batch(C.Structure):
+    _fields_ = [
+        ("n", i64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("src", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar16", C.c_void_p),
+        ("n_wide", i64), ("wide_idx", C.c_void_p), ("wide_word", C.c_void_p), ("seq_off", C.c_void_p), ("seq2", C.c_void_p),
+        ("n_exc", i64), ("exc_byte", C.c_void_p), ("exc_val", C.c_void_p),
+    ]
+
+
 class npt_results(C.Structure):
     _fields_ = [
         ("n_reads", i64), ("cluster_id", P(i32)), ("sub_id", P(i32)), ("start_pos", P(i32)), ("end_pos", P(i32)),
@@ -64,7 +72,7 @@ class npt_device_view(C.Structure):
 
 # every symbol include/npt.h declares (checked by tests/test_abi.py against the header text and the built .so)
 SYMBOLS = [
-    "npt_abi_version", "npt_create", "npt_destroy", "npt_last_error", "npt_begin_chrom", "npt_submit", "npt_wait",
+    "npt_abi_version", "npt_create", "npt_destroy", "npt_last_error", "npt_begin_chrom", "npt_submit", "npt_submit_packed", "npt_wait",
     "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_remap_clusters", "npt_device_view_get",
     "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
     "npt_merge_tables", "npt_merged_results", "npt_merged_cluster_map", "npt_merged_sub_map", "npt_merge_free",
@@ -83,6 +91,7 @@ def declare(lib):
     lib.npt_last_error.restype = C.c_char_p
     lib.npt_begin_chrom.argtypes = [vp, i32, vp, i64, P(npt_annotation)]
     lib.npt_submit.argtypes = [vp, P(npt_batch)]
+    lib.npt_submit_packed.argtypes = [vp, P(npt_packed_batch)]
     lib.npt_wait.argtypes = [vp]
     lib.npt_end_chrom.argtypes = [vp]
     lib.npt_fetch_results.argtypes = [vp, C.c_int, P(npt_results)]
@@ -110,7 +119,7 @@ def declare(lib):
     lib.npt_merge_free.restype = None
     lib.npt_export_keys.argtypes = [vp, P(vp), P(i64)]
     lib.npt_import_keys.argtypes = [vp, vp, i64]
-    for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_wait", "npt_end_chrom", "npt_fetch_results",
+    for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_submit_packed", "npt_wait", "npt_end_chrom", "npt_fetch_results",
               "npt_release_results", "npt_remap_clusters", "npt_device_view_get", "npt_set_read_index_base",
               "npt_last_kernel_ms", "npt_last_step_ms", "npt_export_keys", "npt_import_keys"):
         getattr(lib, s).restype = C.c_int

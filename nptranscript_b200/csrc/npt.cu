@@ -16,6 +16,7 @@
 #include "npt_device.cuh"
 #include "kernels.cuh"
 #include "fastcov.cuh"
+#include "unpack.cuh"
 
 using namespace npt;
 
@@ -151,6 +152,11 @@ struct npt_ctx {
   // multi-rank key exchange
   DBuf<int> d_kx, d_kx_slotmap;
   DBuf<unsigned> d_kx_ctr;
+  int kx_hdr[16] = {0};          // header of the last npt_export_keys (KX_HDR ints; [13] = words of the buffer)
+  struct NptComm* comm = nullptr;   // collectives of this rank (comm.inl); null = single rank
+  int comm_rank = 0, comm_world = 1;
+  DBuf<int> d_kx_all, d_kx_hdrs;
+  float kx_ms = 0, reduce_ms = 0;
   npt_results res{};
   // host results (pinned for the large per-read arrays)
   HBuf<int> r_cluster, r_sub, r_start, r_end, r_rst, r_ren, r_maps, r_err, r_breaks;
@@ -798,28 +804,41 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   return NPT_OK;
 }
 
-int npt_submit(npt_ctx* ctx, const npt_batch* b) {
-  if (!ctx || !b) return fail(ctx, NPT_EINVAL, "null argument");
+}  // extern "C"
+
+// npt_submit / npt_submit_packed: exactly one of b, pb is set
+static int submit_impl(npt_ctx* ctx, const npt_batch* b, const npt_packed_batch* pb) {
+  if (!ctx || (!b && !pb)) return fail(ctx, NPT_EINVAL, "null argument");
   if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_submit outside npt_begin_chrom..npt_end_chrom");
-  if (b->n < 0 || b->n > (1LL << 31) - 1) return fail(ctx, NPT_EINVAL, "batch size out of range");
-  if (b->n == 0) return NPT_OK;
-  if (ctx->idx_base + b->n >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "more than 2^40 reads");
+  const int64_t n = b ? b->n : pb->n;
+  if (n < 0 || n > (1LL << 31) - 1) return fail(ctx, NPT_EINVAL, "batch size out of range");
+  if (n == 0) return NPT_OK;
+  if (ctx->idx_base + n >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "more than 2^40 reads");
   CK(cudaSetDevice(ctx->device));
-  const int64_t n = b->n;
   Batch B;
   B.n = n;
   BatchDev& d = B.d;
   d.n = n; d.idx_base = ctx->idx_base;
   const uint16_t* host_src = nullptr;
+  const int location = b ? b->location : NPT_MEM_HOST;
 
-  if (b->location == NPT_MEM_HOST) {
-    const uint32_t ncig = b->cigar_off[n];
-    const uint64_t nseq = b->seq_off[n];
+  if (location == NPT_MEM_HOST) {
+    const uint32_t* h_coff = b ? b->cigar_off : pb->cigar_off;
+    const uint64_t* h_soff = b ? b->seq_off : pb->seq_off;
+    const uint32_t ncig = h_coff[n];
+    const uint64_t nseq = h_soff[n];
+    if (pb && (pb->n_wide < 0 || pb->n_exc < 0 || (pb->n_wide && (!pb->wide_idx || !pb->wide_word)) || (pb->n_exc && (!pb->exc_byte || !pb->exc_val))))
+      return fail(ctx, NPT_EINVAL, "packed batch: wide / exception lists inconsistent");
     // staging layout (256-byte aligned sections)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t o_pos = 0, o_flag = al(o_pos + (size_t)n * 4), o_src = al(o_flag + (size_t)n * 2), o_coff = al(o_src + (size_t)n * 2);
     const size_t o_cig = al(o_coff + (size_t)(n + 1) * 4), o_soff = al(o_cig + (size_t)ncig * 4), o_seq = al(o_soff + (size_t)(n + 1) * 8);
-    const size_t total = al(o_seq + nseq + 16);
+    const size_t unpacked = al(o_seq + nseq + 16);
+    // compact transfer format: the packed arrays land behind the expanded layout and two copy kernels fill it
+    const size_t p_cig = unpacked, p_seq = al(p_cig + (size_t)ncig * 2 + 16), p_widx = al(p_seq + (size_t)((nseq + 1) / 2) + 16);
+    const size_t p_wword = pb ? al(p_widx + (size_t)pb->n_wide * 4) : p_widx, p_eidx = pb ? al(p_wword + (size_t)pb->n_wide * 4) : p_widx;
+    const size_t p_eval = pb ? al(p_eidx + (size_t)pb->n_exc * 8) : p_widx;
+    const size_t total = pb ? al(p_eval + (size_t)pb->n_exc + 16) : unpacked;
     int si = -1;
     for (int k = 0; k < 2; k++) if (!ctx->stg[k].busy) { si = k; break; }
     if (si < 0) {  // both in flight: retire the older one
@@ -831,22 +850,46 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
     Staging& S = ctx->stg[si];
     CK(S.buf.ensure(total));
     unsigned char* base = S.buf.p;
-    CK(cudaMemcpyAsync(base + o_pos, b->pos, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_copy));
-    CK(cudaMemcpyAsync(base + o_flag, b->flag, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
-    CK(cudaMemcpyAsync(base + o_coff, b->cigar_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->s_copy));
-    if (ncig) CK(cudaMemcpyAsync(base + o_cig, b->cigar, (size_t)ncig * 4, cudaMemcpyHostToDevice, ctx->s_copy));
-    CK(cudaMemcpyAsync(base + o_soff, b->seq_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
-    if (nseq) CK(cudaMemcpyAsync(base + o_seq, b->seq4, (size_t)nseq, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_pos, b ? b->pos : pb->pos, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_flag, b ? b->flag : pb->flag, (size_t)n * 2, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_coff, h_coff, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+    CK(cudaMemcpyAsync(base + o_soff, h_soff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+    if (b) {
+      if (ncig) CK(cudaMemcpyAsync(base + o_cig, b->cigar, (size_t)ncig * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+      if (nseq) CK(cudaMemcpyAsync(base + o_seq, b->seq4, (size_t)nseq, cudaMemcpyHostToDevice, ctx->s_copy));
+    } else {
+      if (ncig) CK(cudaMemcpyAsync(base + p_cig, pb->cigar16, (size_t)ncig * 2, cudaMemcpyHostToDevice, ctx->s_copy));
+      if (nseq) CK(cudaMemcpyAsync(base + p_seq, pb->seq2, (size_t)((nseq + 1) / 2), cudaMemcpyHostToDevice, ctx->s_copy));
+      if (pb->n_wide) {
+        CK(cudaMemcpyAsync(base + p_widx, pb->wide_idx, (size_t)pb->n_wide * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+        CK(cudaMemcpyAsync(base + p_wword, pb->wide_word, (size_t)pb->n_wide * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+      }
+      if (pb->n_exc) {
+        CK(cudaMemcpyAsync(base + p_eidx, pb->exc_byte, (size_t)pb->n_exc * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+        CK(cudaMemcpyAsync(base + p_eval, pb->exc_val, (size_t)pb->n_exc, cudaMemcpyHostToDevice, ctx->s_copy));
+      }
+    }
     CK(cudaEventRecord(S.done, ctx->s_copy));
     CK(cudaStreamWaitEvent(ctx->s_comp, S.done, 0));
+    if (pb) {   // expand on the compute stream, so that the copy stream is free for the next batch
+      const int ug = ctx->sm_count * 8;
+      if (ncig) unpack_cigar_kernel<<<ug, 256, 0, ctx->s_comp>>>((const uint16_t*)(base + p_cig), (uint32_t*)(base + o_cig), (long long)ncig);
+      if (pb->n_wide) patch_wide_kernel<<<std::max(1, (int)std::min<int64_t>((pb->n_wide + 255) / 256, ug)), 256, 0, ctx->s_comp>>>(
+          (const uint32_t*)(base + p_widx), (const uint32_t*)(base + p_wword), (long long)pb->n_wide, (uint32_t*)(base + o_cig), (long long)ncig);
+      if (nseq) unpack_seq_kernel<<<ug, 256, 0, ctx->s_comp>>>(base + p_seq, base + o_seq, (long long)nseq);
+      if (pb->n_exc) patch_exceptions_kernel<<<std::max(1, (int)std::min<int64_t>((pb->n_exc + 255) / 256, ug)), 256, 0, ctx->s_comp>>>(
+          (const unsigned long long*)(base + p_eidx), base + p_eval, (long long)pb->n_exc, base + o_seq, (long long)nseq);
+      CK(cudaGetLastError());
+      ctx->total_launches += (ncig ? 1 : 0) + (pb->n_wide ? 1 : 0) + (nseq ? 1 : 0) + (pb->n_exc ? 1 : 0);
+    }
     d.pos = (const int*)(base + o_pos); d.flag = (const uint16_t*)(base + o_flag);
-    host_src = b->src;   // copied below into the batch's own output block: fit_fixup_kernel reads it at end of chromosome,
+    host_src = b ? b->src : pb->src;   // copied below into the batch's own output block: fit_fixup_kernel reads it at end of chromosome,
                          // long after this staging buffer has been handed to a later batch
     d.cigar_off = (const uint32_t*)(base + o_coff); d.cigar = (const uint32_t*)(base + o_cig);
     d.seq_off = (const unsigned long long*)(base + o_soff); d.seq4 = base + o_seq; d.seq_bytes = (long long)nseq; d.cigar_words = (long long)ncig;
     S.busy = true; S.batch_index = (int)ctx->batches.size();
     B.staging = si;
-  } else if (b->location == NPT_MEM_DEVICE) {
+  } else if (location == NPT_MEM_DEVICE) {
     if (((uintptr_t)b->seq4 & 15) != 0 || ((uintptr_t)b->cigar & 15) != 0)
       return fail(ctx, NPT_EINVAL, "device seq4 and cigar must be 16-byte aligned (the walk stages them with 16-byte cp.async copies)");
     uint64_t nseq = 0;
@@ -920,6 +963,11 @@ int npt_submit(npt_ctx* ctx, const npt_batch* b) {
   ctx->batches.push_back(B);
   return NPT_OK;
 }
+
+extern "C" {
+
+int npt_submit(npt_ctx* ctx, const npt_batch* b) { return submit_impl(ctx, b, nullptr); }
+int npt_submit_packed(npt_ctx* ctx, const npt_packed_batch* pb) { return submit_impl(ctx, nullptr, pb); }
 
 int npt_wait(npt_ctx* ctx) {
   if (!ctx) return NPT_EINVAL;
@@ -1338,6 +1386,8 @@ int npt_export_keys(npt_ctx* ctx, const int32_t** dev_buf, int64_t* n_words) {
   hdr[11] = (int)o; o += sbw;
   hdr[12] = (int)o; o += 2ll * pr_n;
   if (o >= (1ll << 31)) return fail(ctx, NPT_ECAPACITY, "key exchange buffer too large");
+  hdr[13] = (int)o;
+  memcpy(ctx->kx_hdr, hdr, sizeof hdr);
   CK(ctx->d_kx.ensure((size_t)o));
   CK(ctx->d_kx_ctr.ensure(4));
   CK(cudaMemsetAsync(ctx->d_kx_ctr.p, 0, 16, ctx->s_comp));
@@ -1356,14 +1406,12 @@ int npt_export_keys(npt_ctx* ctx, const int32_t** dev_buf, int64_t* n_words) {
   return NPT_OK;
 }
 
-int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words) {
-  if (!ctx || !dev_buf) return fail(ctx, NPT_EINVAL, "null argument");
-  if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_import_keys belongs between the last npt_submit and npt_end_chrom");
-  if (n_words < KX_HDR) return fail(ctx, NPT_EINVAL, "key buffer too short");
-  CK(cudaSetDevice(ctx->device));
+}  // extern "C"
+
+// the part of npt_import_keys that runs once the buffer's header is known on the host: enqueues the insert kernels on the
+// compute stream and does not wait for them
+static int import_keys_enqueue(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words, const int* hdr) {
   const DevCfg& dc = ctx->dc;
-  int hdr[KX_HDR];
-  CK(cudaMemcpy(hdr, dev_buf, sizeof hdr, cudaMemcpyDeviceToHost));
   if (hdr[0] != KX_MAGIC || hdr[7] != dc.S) return fail(ctx, NPT_EINVAL, "not a key buffer of a context with the same configuration");
   const long long end = (long long)hdr[12] + 2ll * hdr[5];
   if (hdr[1] < 0 || hdr[3] < 0 || hdr[5] < 0 || hdr[6] < 1 || end > n_words) return fail(ctx, NPT_EINVAL, "inconsistent key buffer header");
@@ -1374,8 +1422,22 @@ int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words) {
   if (hdr[3]) import_subs_kernel<<<g, 128, 0, ctx->s_comp>>>(dc, dev_buf + hdr[10], hdr[3], dev_buf + hdr[11], ctx->d_kx_slotmap.p);
   if (hdr[5] && dc.calc_breaks1) import_pairs_kernel<<<g, 128, 0, ctx->s_comp>>>(dc, dev_buf + hdr[12], hdr[5]);
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(ctx->s_comp));
   ctx->total_launches += 3;
+  return NPT_OK;
+}
+
+extern "C" {
+
+int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words) {
+  if (!ctx || !dev_buf) return fail(ctx, NPT_EINVAL, "null argument");
+  if (!ctx->in_chrom || ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_import_keys belongs between the last npt_submit and npt_end_chrom");
+  if (n_words < KX_HDR) return fail(ctx, NPT_EINVAL, "key buffer too short");
+  CK(cudaSetDevice(ctx->device));
+  int hdr[KX_HDR];
+  CK(cudaMemcpy(hdr, dev_buf, sizeof hdr, cudaMemcpyDeviceToHost));
+  int rc = import_keys_enqueue(ctx, dev_buf, n_words, hdr);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->s_comp));
   return NPT_OK;
 }
 
@@ -1408,3 +1470,5 @@ int npt_last_kernel_ms(npt_ctx* ctx, float* walk_ms, float* finalize_ms, int64_t
 }
 
 }  // extern "C"
+
+#include "comm.inl"

@@ -149,6 +149,18 @@ class Engine:
         self._keep.append(batch)
         self._ck(self.L.npt_submit(self.h, C.byref(s)))
 
+    def submit_packed(self, pb):
+        """pb: packed.PackedBatch (compact transfer format, host arrays kept alive until wait/end_chrom)."""
+        s = abi.npt_packed_batch()
+        s.n = pb.n
+        s.pos, s.flag, s.src = pb.pos.ctypes.data, pb.flag.ctypes.data, pb.src.ctypes.data
+        s.cigar_off, s.cigar16 = pb.cigar_off.ctypes.data, pb.cigar16.ctypes.data
+        s.n_wide, s.wide_idx, s.wide_word = len(pb.wide_idx), pb.wide_idx.ctypes.data, pb.wide_word.ctypes.data
+        s.seq_off, s.seq2 = pb.seq_off.ctypes.data, pb.seq2.ctypes.data
+        s.n_exc, s.exc_byte, s.exc_val = len(pb.exc_byte), pb.exc_byte.ctypes.data, pb.exc_val.ctypes.data
+        self._keep.append(pb)
+        self._ck(self.L.npt_submit_packed(self.h, C.byref(s)))
+
     def submit_device(self, n, pos, flag, src, cigar_off, cigar, seq_off, seq4):
         """Device pointers (ints) of a batch already resident in HBM."""
         s = abi.npt_batch()
@@ -207,12 +219,17 @@ class Engine:
         self._ck(self.L.npt_remap_clusters(self.h, g.ctypes.data, n_global))
 
 
-def run(cfg, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL):
+def run(cfg, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL, packed=False):
+    """packed=True sends every batch in the compact transfer format (npt_submit_packed)."""
     e = Engine(cfg)
     try:
         e.begin_chrom(chrom_index, ref_codes, annotation)
         for b in batches:
-            e.submit(b)
+            if packed:
+                from .packed import pack
+                e.submit_packed(pack(b))
+            else:
+                e.submit(b)
         e.end_chrom()
         r = e.fetch(what)
         r["_timing"] = e.kernel_ms()
