@@ -245,6 +245,19 @@ def run_ours(args, rank, world, local_rank):
     gen_s = time.perf_counter() - t0
 
     eng = engine.Engine(cfg)
+    if world > 1:
+        # the data path's collectives run inside libnpt on its own NCCL communicator (csrc/comm.inl); torch.distributed carries
+        # the 128-byte id, the barriers and the max-over-ranks of the timings
+        ident = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            eng.comm_init(ident[0], rank, world)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def device_step():
         eng.set_read_index_base(first)
@@ -253,13 +266,12 @@ def run_ours(args, rank, world, local_rank):
                           d["cigar"].data_ptr(), d["seq_off"].data_ptr(), d["seq4"].data_ptr())
         kx_ms = red_ms = 0.0
         if world > 1:
-            from nptranscript_b200 import multigpu
-            kx_ms = multigpu.exchange_keys(eng, rank, world)  # waits for this rank's kernels first (npt_wait inside)
-        eng.end_chrom()
+            eng.end_chrom_all()   # key exchange + numbering + all-reduce of the counters: all inside the library's step span
+            kx_ms, red_ms = eng.exchange_ms()
+        else:
+            eng.end_chrom()
         t = eng.kernel_ms()
-        if world > 1:
-            red_ms = multigpu.reduce_aggregates(eng)
-        t["merge_ms"] = red_ms  # the key exchange lies inside the library's step span (begin_chrom .. end_chrom)
+        t["merge_ms"] = 0.0
         t["kx_ms"], t["reduce_ms"] = kx_ms, red_ms
         return t
 
@@ -324,11 +336,9 @@ def run_ours(args, rank, world, local_rank):
             for b in host_chunks:
                 eng.submit(b)
         if world > 1:
-            from nptranscript_b200 import multigpu
-            multigpu.exchange_keys(eng, rank, world)
-        eng.end_chrom()
-        if world > 1:
-            multigpu.reduce_aggregates(eng)
+            eng.end_chrom_all()
+        else:
+            eng.end_chrom()
         r = eng.fetch_raw(abi.NPT_FETCH_ALL)
         nb = int(np.ctypeslib.as_array(r.break_off, shape=(e2e_reads + 1,))[-1])
         d2h = e2e_reads * (9 * 4 + 8) + nb * 4 + 4 * r.n_clusters * cfg.num_sources * r.cov_stride * 4
@@ -438,8 +448,7 @@ def run_ours(args, rank, world, local_rank):
                        "clusters": n_clusters, "sub_clusters": n_subs, "reads_on_serial_path": n_slow,
                        "self_check": {"reads": e2e_reads, "passed": sorted(checks)}, "gen_seconds": gen_s,
                        "merge_breakdown_ms": {"key_exchange_ms": float(np.mean(kx_list)), "reduce_ms": float(np.mean(red_list)),
-                                              "last_step": getattr(__import__("nptranscript_b200.multigpu", fromlist=["x"]).exchange_keys, "last", None),
-                                              "note": "key exchange = wait for own kernels + export + NCCL all-gather + import, inside the step span; reduce = NCCL all-reduces after end_chrom"} if world > 1 else None,
+                                              "note": "CUDA-event spans on rank 0 inside npt_end_chrom_all: key exchange = header all-gather + grouped NCCL broadcasts + import kernels (includes waiting for the slowest rank); reduce = grouped NCCL all-reduces of the counters; both inside the step span"} if world > 1 else None,
                        "timing": "CUDA events inside libnpt on its compute stream (npt_last_step_ms / npt_last_kernel_ms); wall ms/step %.2f" % wall_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": names[dom], "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms, "algorithmic_bytes": alg,

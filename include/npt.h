@@ -284,6 +284,37 @@ typedef struct npt_device_view {
 } npt_device_view;
 int npt_export_keys(npt_ctx* ctx, const int32_t** dev_buf, int64_t* n_words);
 int npt_import_keys(npt_ctx* ctx, const int32_t* dev_buf, int64_t n_words);
+/* The same protocol with the collectives inside the library (NCCL, loaded at run time with dlopen("libnccl.so.2"); csrc/comm.inl).
+ * Multi-process, one rank per GPU: rank 0 calls npt_comm_unique_id and hands the 128 bytes to the other ranks by any means
+ * (MPI, torch.distributed, a file); every rank calls npt_comm_init on its context; then npt_end_chrom_all replaces
+ * npt_end_chrom: export -> all-gather of the headers -> one group of broadcasts -> import kernels -> npt_end_chrom ->
+ * all-reduce of the counters, with two host waits in total.  npt_last_step_ms then covers the whole span. */
+#define NPT_COMM_ID_BYTES 128
+int npt_comm_unique_id(void* id128);
+int npt_comm_init(npt_ctx* ctx, const void* id128, int rank, int world);
+int npt_end_chrom_all(npt_ctx* ctx);
+int npt_last_exchange_ms(npt_ctx* ctx, float* key_exchange_ms, float* reduce_ms);
+
+/* In-process multi-GPU context: what a single-threaded host (the Java shim: one caller, one holder,
+ * J/cluster/IdentityProfileHolder.java:170-196) drives.  One npt_ctx per listed device, one host thread per device inside
+ * every call, NCCL communicators from ncclCommInitAll.  Each host batch is split into contiguous read ranges with about
+ * the same number of bases, one per device; results are defined exactly as for one context (sequential in submit order).
+ * npt_mg_fetch_results returns the global tables / coverage once and the per-read arrays of all devices back in submit order.
+ * A device may be listed more than once (several contexts on one GPU; used by the single-GPU tests): the collectives then
+ * run as device-to-device copies and an add kernel instead of NCCL. */
+typedef struct npt_mg npt_mg;
+int npt_mg_create(const npt_config* cfg, const int32_t* devices, int32_t n_devices, npt_mg** out);   /* cfg->device is ignored */
+void npt_mg_destroy(npt_mg* mg);
+const char* npt_mg_last_error(const npt_mg* mg);   /* mg may be NULL: error of the last failed npt_mg_create on this thread */
+int npt_mg_set_read_index_base(npt_mg* mg, int64_t base);
+int npt_mg_begin_chrom(npt_mg* mg, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot);
+int npt_mg_submit(npt_mg* mg, const npt_batch* batch);   /* NPT_MEM_HOST only; arrays untouched until npt_mg_wait / npt_mg_end_chrom */
+int npt_mg_wait(npt_mg* mg);
+int npt_mg_end_chrom(npt_mg* mg);
+int npt_mg_fetch_results(npt_mg* mg, int what, npt_results* out);
+int npt_mg_release_results(npt_mg* mg);
+int npt_mg_last_step_ms(npt_mg* mg, float* step_ms, float* key_exchange_ms, float* reduce_ms);   /* max over the devices */
+
 /* Host-side alternative (tables merged on the host by npt_merge_tables): reorders/zero-extends coverage rows so that
  * local cluster i lands at row global_id[i] of n_global rows. */
 int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global);

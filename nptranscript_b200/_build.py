@@ -14,7 +14,7 @@ LIBSYNTH = os.path.join(HERE, "synth", "libnptsynth.so")
 LIBBAM = os.path.join(HERE, "bam", "libnptbam.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared", "-ldl", "-lpthread"]
 
 
 @contextlib.contextmanager
@@ -44,7 +44,7 @@ def _nvcc():
 
 
 def build_libnpt(force=False, verbose=False):
-    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp")))
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp", ".inl")))
     srcs.append(os.path.join(ROOT, "include", "npt.h"))
     cus = [s for s in srcs if s.endswith((".cu", ".cpp"))]
     if not force and not _stale(LIBNPT, srcs):

@@ -178,6 +178,8 @@ struct npt_ctx {
   float stage_ms[6] = {0, 0, 0, 0, 0, 0};
 };
 
+static void comm_release(npt_ctx* ctx);   // comm.inl
+
 namespace {
 
 int fail(npt_ctx* c, int code, const char* fmt, ...) {
@@ -579,6 +581,7 @@ void npt_destroy(npt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  comm_release(ctx);
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();

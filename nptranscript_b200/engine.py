@@ -214,9 +214,131 @@ class Engine:
     def import_keys(self, dev_ptr, n_words):
         self._ck(self.L.npt_import_keys(self.h, dev_ptr, n_words))
 
+    # ---- collectives inside the library (csrc/comm.inl)
+    def comm_init(self, id_bytes, rank, world):
+        buf = C.create_string_buffer(bytes(id_bytes), abi.NPT_COMM_ID_BYTES)
+        self._ck(self.L.npt_comm_init(self.h, buf, rank, world))
+
+    def end_chrom_all(self):
+        """Collective end of chromosome: key exchange + end_chrom + sum of the counters, all inside libnpt over NCCL."""
+        self._ck(self.L.npt_end_chrom_all(self.h))
+        self._keep = []
+
+    def exchange_ms(self):
+        k, r = C.c_float(), C.c_float()
+        self._ck(self.L.npt_last_exchange_ms(self.h, C.byref(k), C.byref(r)))
+        return k.value, r.value
+
     def remap_clusters(self, global_id, n_global):
         g = np.ascontiguousarray(global_id, dtype=np.int32)
         self._ck(self.L.npt_remap_clusters(self.h, g.ctypes.data, n_global))
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(abi.NPT_COMM_ID_BYTES)
+    rc = lib().npt_comm_unique_id(buf)
+    if rc:
+        raise NptError(rc, lib().npt_last_error(None).decode())
+    return buf.raw
+
+
+def _annotation_struct(annotation):
+    st = np.asarray(annotation.start, dtype=np.int32)
+    en = np.asarray(annotation.end, dtype=np.int32)
+    sd = np.asarray(annotation.strand, dtype=np.uint8)
+    ni = np.asarray(annotation.name_id, dtype=np.int32)
+    nh = np.asarray(annotation.name_hash if annotation.kind == abi.NPT_ANNOT_GFF else [], dtype=np.uint32)
+    a = abi.npt_annotation()
+    a.kind, a.n = annotation.kind, len(st)
+    a.start = st.ctypes.data_as(C.POINTER(C.c_int32)); a.end = en.ctypes.data_as(C.POINTER(C.c_int32))
+    a.strand = sd.ctypes.data_as(C.POINTER(C.c_uint8)); a.name_id = ni.ctypes.data_as(C.POINTER(C.c_int32))
+    a.name_hash = nh.ctypes.data_as(C.POINTER(C.c_uint32)) if len(nh) else None
+    return a, (st, en, sd, ni, nh)
+
+
+class MultiEngine:
+    """One npt_mg: the in-process multi-GPU context (one npt_ctx and one host thread per device inside libnpt, NCCL between
+    them).  Same call sequence as Engine; host batches are split over the devices by the library."""
+
+    def __init__(self, cfg, devices):
+        self.L = lib()
+        self.S = cfg.num_sources
+        dv = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.L.npt_mg_create(C.byref(cfg), dv, len(devices), C.byref(h))
+        if rc:
+            raise NptError(rc, self.L.npt_mg_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def _ck(self, rc):
+        if rc:
+            raise NptError(rc, self.L.npt_mg_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.npt_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_read_index_base(self, base):
+        self._ck(self.L.npt_mg_set_read_index_base(self.h, base))
+
+    def begin_chrom(self, chrom_index, ref_codes, annotation):
+        ref = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+        a, keep = _annotation_struct(annotation)
+        self._ck(self.L.npt_mg_begin_chrom(self.h, chrom_index, ref.ctypes.data, len(ref), C.byref(a)))
+        self._keep = []
+
+    def submit(self, batch):
+        s = abi.npt_batch()
+        s.n, s.location = batch.n, abi.NPT_MEM_HOST
+        s.pos, s.flag, s.src = batch.pos.ctypes.data, batch.flag.ctypes.data, batch.src.ctypes.data
+        s.cigar_off, s.cigar = batch.cigar_off.ctypes.data, batch.cigar.ctypes.data
+        s.seq_off, s.seq4 = batch.seq_off.ctypes.data, batch.seq4.ctypes.data
+        self._keep.append(batch)
+        self._ck(self.L.npt_mg_submit(self.h, C.byref(s)))
+
+    def end_chrom(self):
+        self._ck(self.L.npt_mg_end_chrom(self.h))
+        self._keep = []
+
+    def fetch(self, what=abi.NPT_FETCH_ALL):
+        r = abi.npt_results()
+        self._ck(self.L.npt_mg_fetch_results(self.h, what, C.byref(r)))
+        return Results.from_struct(r, self.S, what)
+
+    def fetch_raw(self, what=abi.NPT_FETCH_ALL):
+        r = abi.npt_results()
+        self._ck(self.L.npt_mg_fetch_results(self.h, what, C.byref(r)))
+        return r
+
+    def release(self):
+        self._ck(self.L.npt_mg_release_results(self.h))
+
+    def step_ms(self):
+        s, k, r = C.c_float(), C.c_float(), C.c_float()
+        self._ck(self.L.npt_mg_last_step_ms(self.h, C.byref(s), C.byref(k), C.byref(r)))
+        return dict(step_ms=s.value, key_exchange_ms=k.value, reduce_ms=r.value)
+
+
+def run_mg(cfg, devices, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL):
+    e = MultiEngine(cfg, devices)
+    try:
+        e.begin_chrom(chrom_index, ref_codes, annotation)
+        for b in batches:
+            e.submit(b)
+        e.end_chrom()
+        r = e.fetch(what)
+        r["_timing"] = e.step_ms()
+        return r
+    finally:
+        e.close()
 
 
 def run(cfg, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL, packed=False):
