@@ -480,12 +480,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (config 2: default 10 M; other configs: see bench_configs.py)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="1Mi-read pinned host chunks used by the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=500_000)
     ap.add_argument("--ref-reads", type=int, default=500_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configuration 1..5 (2 = the headline one; the others: bench_configs.py)")
+    ap.add_argument("--host-scale", type=float, default=0.04, help="config 5: chromosome lengths as a fraction of GRCh38")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -495,6 +497,15 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.config != 2:
+        import bench_configs
+        if args.impl == "reference":
+            bench_configs.run_reference(args, rank, world)
+        else:
+            bench_configs.run(args, rank, world, local_rank)
+        return
+    if not args.reads:
+        args.reads = 10_000_000
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

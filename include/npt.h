@@ -315,21 +315,12 @@ int npt_mg_fetch_results(npt_mg* mg, int what, npt_results* out);
 int npt_mg_release_results(npt_mg* mg);
 int npt_mg_last_step_ms(npt_mg* mg, float* step_ms, float* key_exchange_ms, float* reduce_ms);   /* max over the devices */
 
-/* Host-side alternative (tables merged on the host by npt_merge_tables): reorders/zero-extends coverage rows so that
- * local cluster i lands at row global_id[i] of n_global rows. */
-int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global);
 int npt_device_view_get(npt_ctx* ctx, npt_device_view* out);
-/* Host-side merge of the table part of every rank's npt_results (first-read indices already global, see
- * npt_set_read_index_base): global first-appearance ids, summed counts, and per-rank local->global maps
- * (cluster map indexed by local cluster id; sub map indexed by local sub-cluster position, cluster-major,
- * giving the global k of ".t<k>").  No device work; the merged npt_results carries only table fields. */
-void* npt_merge_tables(int nranks, const npt_results* const* tables, int num_sources);
-const npt_results* npt_merged_results(void* merged);
-const int32_t* npt_merged_cluster_map(void* merged, int rank);
-const int32_t* npt_merged_sub_map(void* merged, int rank);
-void npt_merge_free(void* merged);
 /* Offset added to the batch-relative read index to form the global submit index (sharded runs). */
 int npt_set_read_index_base(npt_ctx* ctx, int64_t base);
+/* Global submit index of the first read of the NEXT npt_submit (any time inside a chromosome): sharded runs whose ranks
+ * take turns in the submit order, e.g. wave k of rank r starts at (k * ranks + r) * wave_size. */
+int npt_set_next_read_index(npt_ctx* ctx, int64_t index);
 
 /* pinned host memory for batches (cudaHostAlloc) */
 void* npt_alloc_pinned(size_t bytes);

@@ -73,9 +73,8 @@ class npt_device_view(C.Structure):
 # every symbol include/npt.h declares (checked by tests/test_abi.py against the header text and the built .so)
 SYMBOLS = [
     "npt_abi_version", "npt_create", "npt_destroy", "npt_last_error", "npt_begin_chrom", "npt_submit", "npt_submit_packed", "npt_wait",
-    "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_remap_clusters", "npt_device_view_get",
-    "npt_set_read_index_base", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
-    "npt_merge_tables", "npt_merged_results", "npt_merged_cluster_map", "npt_merged_sub_map", "npt_merge_free",
+    "npt_end_chrom", "npt_fetch_results", "npt_release_results", "npt_device_view_get",
+    "npt_set_read_index_base", "npt_set_next_read_index", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
     "npt_export_keys", "npt_import_keys",
     "npt_comm_unique_id", "npt_comm_init", "npt_end_chrom_all", "npt_last_exchange_ms",
     "npt_mg_create", "npt_mg_destroy", "npt_mg_last_error", "npt_mg_set_read_index_base", "npt_mg_begin_chrom", "npt_mg_submit", "npt_mg_wait",
@@ -100,9 +99,10 @@ def declare(lib):
     lib.npt_end_chrom.argtypes = [vp]
     lib.npt_fetch_results.argtypes = [vp, C.c_int, P(npt_results)]
     lib.npt_release_results.argtypes = [vp]
-    lib.npt_remap_clusters.argtypes = [vp, vp, i32]
     lib.npt_device_view_get.argtypes = [vp, P(npt_device_view)]
     lib.npt_set_read_index_base.argtypes = [vp, i64]
+    lib.npt_set_next_read_index.argtypes = [vp, i64]
+    lib.npt_set_next_read_index.restype = C.c_int
     lib.npt_alloc_pinned.argtypes = [C.c_size_t]
     lib.npt_alloc_pinned.restype = vp
     lib.npt_free_pinned.argtypes = [vp]
@@ -111,16 +111,6 @@ def declare(lib):
     lib.npt_last_step_ms.argtypes = [vp, P(C.c_float)]
     lib.npt_last_stage_ms.argtypes = [vp, P(C.c_float)]
     lib.npt_last_stage_ms.restype = C.c_int
-    lib.npt_merge_tables.argtypes = [C.c_int, P(P(npt_results)), C.c_int]
-    lib.npt_merge_tables.restype = vp
-    lib.npt_merged_results.argtypes = [vp]
-    lib.npt_merged_results.restype = P(npt_results)
-    lib.npt_merged_cluster_map.argtypes = [vp, C.c_int]
-    lib.npt_merged_cluster_map.restype = P(i32)
-    lib.npt_merged_sub_map.argtypes = [vp, C.c_int]
-    lib.npt_merged_sub_map.restype = P(i32)
-    lib.npt_merge_free.argtypes = [vp]
-    lib.npt_merge_free.restype = None
     lib.npt_export_keys.argtypes = [vp, P(vp), P(i64)]
     lib.npt_import_keys.argtypes = [vp, vp, i64]
     lib.npt_comm_unique_id.argtypes = [vp]
@@ -145,7 +135,7 @@ def declare(lib):
               "npt_mg_last_step_ms"):
         getattr(lib, s).restype = C.c_int
     for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_submit_packed", "npt_wait", "npt_end_chrom", "npt_fetch_results",
-              "npt_release_results", "npt_remap_clusters", "npt_device_view_get", "npt_set_read_index_base",
+              "npt_release_results", "npt_device_view_get", "npt_set_read_index_base",
               "npt_last_kernel_ms", "npt_last_step_ms", "npt_export_keys", "npt_import_keys"):
         getattr(lib, s).restype = C.c_int
     return lib

@@ -19,7 +19,7 @@ namespace npt {
 
 constexpr int FW_WARPS_MAX = 16;
 constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE;
-__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : 0); }
+__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : FW_BRK_BUF * 32); }
 
 __device__ __forceinline__ void fw_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");

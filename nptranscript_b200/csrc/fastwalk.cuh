@@ -63,6 +63,12 @@ constexpr int FW_MAX_JUNC = 2;     // breaks (prev, pos) per read: BRK_INLINE = 
 constexpr int FW_MAX_EXTRA = 4;    // rare extra events per read (see below)
 constexpr int FW_RARE_WORDS = 16;  // per-read record of rare events, uint32 words
 constexpr int FW_BRK_INLINE = 6;
+// Without depth recording (host mode, opts_host.txt) nothing is kept per aligned block, so the number of blocks is free and
+// the break list may be long: a spliced read has two breaks per junction.  The lane keeps them in FW_BRK_BUF words of shared
+// memory (the place of the coverage ring, which is not needed then) and moves the list to the batch's overflow area at the end
+// of the read, like walk_kernel<2> does for the serial walker.
+constexpr int FW_LONG_JUNC = 30;
+constexpr int FW_BRK_BUF = 2 * FW_LONG_JUNC + 2;
 
 // entry flags, one nibble per position (position 8W + i of ring word W sits in nibble i counted from the top)
 constexpr unsigned FW_COV = 0x11111111u;   // emitted by an M element (depth +1)
@@ -159,7 +165,7 @@ FW_HD void fw_give_up(FwLane& L) { L.flags |= FWF_SLOW; L.ck = L.cend; L.mRem = 
 // ---- the rare part of a step: some emission lies more than break_thresh behind the last match (CigarCluster.add :470-498) ----
 // emissions in the reference's order: the dq positions of the D element (never matches), then the n positions of the M piece
 template <bool RECORD>
-FW_HD void fw_far_step(FwLane& L, const DevCfg& c, const BatchDev& b, int p0, int n, int dq, unsigned mh, unsigned ml) {
+FW_HD void fw_far_step(FwLane& L, const DevCfg& c, const BatchDev& b, int p0, int n, int dq, unsigned mh, unsigned ml, uint32_t* aux, int RS) {
   const int prev = L.pp0 + fw_last_idx(L.pmh, L.pml);
   const int f = fw_first_idx(mh, ml, n);            // first match of the M piece (n = none)
   const int i0 = fw_max(0, prev + c.T + 1 - p0);    // first offset that is more than T behind prev
@@ -175,9 +181,12 @@ FW_HD void fw_far_step(FwLane& L, const DevCfg& c, const BatchDev& b, int p0, in
     }
   }
   if (f < n && f >= i0) {                           // the first match closes the break (prev, pos)
-    if (L.njunc == FW_MAX_JUNC) { fw_give_up(L); return; }
-    b.break_arena[L.r * FW_BRK_INLINE + L.nb] = prev;
-    b.break_arena[L.r * FW_BRK_INLINE + L.nb + 1] = p0 + f;
+    if (L.njunc == (RECORD ? FW_MAX_JUNC : FW_LONG_JUNC)) { fw_give_up(L); return; }
+    if (L.nb + 1 < FW_BRK_INLINE) {
+      b.break_arena[L.r * FW_BRK_INLINE + L.nb] = prev;
+      b.break_arena[L.r * FW_BRK_INLINE + L.nb + 1] = p0 + f;
+    }
+    if (!RECORD) { aux[L.nb * RS] = (uint32_t)prev; aux[(L.nb + 1) * RS] = (uint32_t)(p0 + f); }
     if (RECORD) { b.frare[L.r * FW_RARE_WORDS + 4 + 2 * L.njunc] = (unsigned)prev; b.frare[L.r * FW_RARE_WORDS + 5 + 2 * L.njunc] = (unsigned)(p0 + f); }
     L.nb += 2; L.njunc++;
   }
@@ -197,7 +206,8 @@ FW_HD void fw_double_qrk(FwLane& L, const BatchDev& b, int p0, int qe) {
 
 // ---- one step ---------------------------------------------------------------------------------------------------------
 // cig[i] = CIGAR word (L.cs + i), i < FW_CIG_TILE; seq[k] = raw (little-endian) word k of the base tile; refg[W] = reference
-// grid word W (positions 8W..8W+7, first in the top nibble); ring[j * RS] = lane-private ring word j, j < FW_RING + FW_RING_PAD.
+// grid word W (positions 8W..8W+7, first in the top nibble); ring[j * RS] = lane-private ring word j, j < FW_RING + FW_RING_PAD
+// (RECORD) or lane-private break buffer word j, j < FW_BRK_BUF (!RECORD).
 // `live` = the lane holds a read the fast walk has not given up; ringLimit = last refPos a step may start from without
 // running past the 256 positions the ring holds behind the first unflushed entry.
 // The step takes an element only when it can restate it: I S H P always, D of at most 16 positions after the first M, M.  At
@@ -251,7 +261,7 @@ FW_HD void fw_step(FwLane& L, const DevCfg& c, const BatchDev& b, const uint32_t
   const unsigned mh = vh & ~nzh, ml = vl & ~nzl;     // matches
   const int m = n > dq ? n : dq;
   const int last = p0 + m - 1;
-  if ((m > 0) & (last - L.pp0 > c.T)) fw_far_step<RECORD>(L, c, b, p0, n, dq, mh, ml);   // some emission is more than T behind the last match
+  if ((m > 0) & (last - L.pp0 > c.T)) fw_far_step<RECORD>(L, c, b, p0, n, dq, mh, ml, ring, RS);   // some emission is more than T behind the last match
   if (mh | ml) { L.pmh = mh; L.pml = ml; L.pp0 = p0; }
   if (RECORD) {
     if ((dq > 0) & (p0 < L.qEnd)) fw_double_qrk(L, b, p0, fw_min(L.qEnd, p0 + dq));
@@ -311,19 +321,19 @@ FW_HD void fw_round_end(FwLane& L, const DevCfg& c, const BatchDev& b, const uin
   if (fin && !slow) {                              // the block ends here
     const unsigned cnt = RECORD ? (unsigned)(L.flushE - L.blkFirstE) : 0u;
     const unsigned v = (unsigned)L.blkFirstE | (cnt << 16);
-    if (cnt >= 0x10000u || (unsigned)L.blkFirstE >= 0x10000u) slow = true;
+    if (RECORD && (cnt >= 0x10000u || (unsigned)L.blkFirstE >= 0x10000u)) slow = true;   // the packed block header holds 16 bits each
     if (L.nblk == 0) L.blk0 = v; else if (L.nblk == 1) L.blk1 = v; else L.blk2 = v;
-    L.nblk++;
+    if (RECORD || L.nblk < FW_MAX_BLOCKS) L.nblk++;
   }
   if (isN && !slow) {                              // the N element itself: skips reference positions (:523-525)
-    if (L.nblk == FW_MAX_BLOCKS) slow = true;      // a fourth block would open behind it
+    if (RECORD && L.nblk == FW_MAX_BLOCKS) slow = true;      // a fourth block would open behind it
     const int len = (int)(wN >> 4);
     L.refPos += len; L.sumN += len;
     L.ck++;
     L.maxPos = L.refPos; L.flushE = L.blkFirstE = (L.refPos + 1) >> 5;   // the next block is open from here
     if (L.refPos > c.G) slow = true;
   }
-  if (endRead && !slow && (L.nb + 1 > FW_BRK_INLINE || L.rdEndM > L.nbases)) slow = true;
+  if (endRead && !slow && ((RECORD && L.nb + 1 > FW_BRK_INLINE) || L.rdEndM > L.nbases)) slow = true;
   if (slow) {
     const long long r = L.r;
     b.rflags[r] = 0x20u;    // NPT_RF_SLOWPATH: walked again by the exact serial device path
@@ -337,9 +347,32 @@ FW_HD void fw_round_end(FwLane& L, const DevCfg& c, const BatchDev& b, const uin
   } else if (endRead) {
     const long long r = L.r;
     const int alnEnd = L.refPos;  // CigarCluster.addEnd :466-469
-    b.break_arena[r * FW_BRK_INLINE + L.nb] = alnEnd;
-    b.nbreaks[r] = L.nb + 1;
-    b.break_loc[r] = 0xFFFFFFFFu;
+    const int n_all = L.nb + 1;
+    b.nbreaks[r] = n_all;
+    if (n_all <= FW_BRK_INLINE) {
+      b.break_arena[r * FW_BRK_INLINE + L.nb] = alnEnd;
+      b.break_loc[r] = 0xFFFFFFFFu;
+    } else {   // !RECORD only: the whole list goes to the overflow area
+#if defined(__CUDA_ARCH__)
+      const unsigned loc = atomicAdd(b.bctr, (unsigned)n_all);
+#else
+      const unsigned loc = b.bctr[0]; b.bctr[0] += (unsigned)n_all;
+#endif
+      if (loc + (unsigned)n_all > b.break_cap) {
+#if defined(__CUDA_ARCH__)
+        atomicOr(b.bctr + 1, 1u);   // too small: the host enlarges it (bctr[0] = the need) and the serial walker redoes the long lists
+#else
+        b.bctr[1] |= 1u;
+#endif
+        b.break_loc[r] = 0xFFFFFFFEu;
+      } else {
+        int* dst = b.break_arena + b.n * FW_BRK_INLINE + loc;
+        dst[0] = L.alnStart;
+        for (int i = 1; i < L.nb; i++) dst[i] = (int)ring[i * RS];
+        dst[L.nb] = alnEnd;
+        b.break_loc[r] = loc;
+      }
+    }
     b.read_st[r] = L.st_r;
     b.read_en[r] = (L.st_r != 0 && L.refPos == L.refEndM) ? L.rdEndM : 0;   // getReadPositionAtReferencePosition(alignmentEnd)
     b.maps_sum[r] = c.record_depth ? alnEnd - (L.alnStart - 1) - L.sumN : 0;   // positions M and D elements emitted

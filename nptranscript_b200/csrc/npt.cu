@@ -97,6 +97,7 @@ struct npt_ctx {
   DevCfg dc{};
   bool ref_smem = false;
   DBuf<uint32_t> d_ref;
+  DBuf<uint8_t> d_ref_codes;
   DBuf<int> d_ostart, d_oname;
   DBuf<uint8_t> d_ostrand;
   DBuf<int4> d_gx; DBuf<unsigned> d_gxhash;
@@ -133,10 +134,11 @@ struct npt_ctx {
   // finalize products
   unsigned h_counters[CN_COUNT]{};
   int n_clusters = 0, n_subs = 0;
-  int cov_rows = 0;           // rows of d_cov_out (n_clusters, or n_global after npt_remap_clusters)
+  int cov_rows = 0;           // rows of d_cov_out (n_clusters)
   int64_t n_pairs = 0;
   int64_t n_total = 0;
   int64_t n_slow = 0;            // reads the fast walk handed to the serial walker (this chromosome)
+  float brk_per_read = 0;        // largest overflow need (ints per read) of a retired batch of this chromosome
   long long total_breaks = 0;
   DBuf<long long> d_ex_first;
   DBuf<unsigned> d_ex_u[5];
@@ -204,6 +206,24 @@ __global__ void init_tables_kernel(Slot* cl, unsigned ncl, Slot* sb, unsigned ns
   for (size_t k = i; k < ncl; k += stride) { cl[k].word = 0; cl[k].min_idx = ~0ULL; }
   for (size_t k = i; k < nsb; k += stride) { sb[k].word = 0; sb[k].min_idx = ~0ULL; }
   for (size_t k = i; k < npr; k += stride) { pr[k].key = 0; pr[k].count = 0; pr[k].pad = 0; }
+}
+
+// reference codes (one byte per base) -> packed words: ref[w] = bases 8w..8w+7 (0-based), grid[W] = positions 8W..8W+7 (1-based),
+// first in the top nibble, zero beyond the reference
+__global__ void pack_reference_kernel(const uint8_t* __restrict__ codes, long long n, uint32_t* ref, int nwords, uint32_t* grid, int gwords) {
+  const int total = nwords > gwords ? nwords : gwords;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    uint32_t a = 0, g = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const long long i = 8ll * w + k;          // 0-based base index = position i + 1
+      if (i < n) a |= (uint32_t)(codes[i] & 0xF) << (28 - 4 * k);
+      const long long j = i - 1;                // grid word w, nibble k = position 8w + k = base index 8w + k - 1
+      if (j >= 0 && j < n) g |= (uint32_t)(codes[j] & 0xF) << (28 - 4 * k);
+    }
+    if (w < nwords) ref[w] = a;
+    if (w < gwords) grid[w] = g;
+  }
 }
 
 // cluster table slots -> dense arrays indexed by the cluster's dense id
@@ -490,6 +510,9 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
     CK(cudaStreamSynchronize(ctx->s_comp));
     pool_put(ctx, B.d.break_arena, B.arena_bytes);
     B.d.break_arena = bigger; B.d.break_cap = need; B.arena_bytes = bigger_bytes;
+    // the serial store-all pass now redoes every long list, also those of reads the fast walk had finished (their overflow
+    // slots were handed out from the counter that has just been reset)
+    if (B.d.fast) { ctx->n_slow += h[7]; B.d.fast = 0; }
     int rc = launch_batch(ctx, B, 1);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->s_comp));
@@ -497,6 +520,8 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
   release_scratch(ctx, B);
   if (B.staging >= 0) { ctx->stg[B.staging].busy = false; ctx->stg[B.staging].batch_index = -1; }
   if (B.d.fast) ctx->n_slow += h[7];
+  // overflow ints per read this batch needed: the next batches of the chromosome reserve that much (plus a quarter)
+  ctx->brk_per_read = std::max(ctx->brk_per_read, (float)((double)h[0] / (double)std::max<int64_t>(B.n, 1)));
   B.retired = true;
   return NPT_OK;
 }
@@ -585,7 +610,7 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();
-  ctx->d_ref.release(); ctx->d_refg.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
+  ctx->d_ref.release(); ctx->d_ref_codes.release(); ctx->d_refg.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
   ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
@@ -613,6 +638,13 @@ int npt_set_read_index_base(npt_ctx* ctx, int64_t base) {
   if (ctx->in_chrom && !ctx->batches.empty()) return fail(ctx, NPT_ESTATE, "npt_set_read_index_base after the first npt_submit of a chromosome");
   ctx->idx_user_base = base;
   ctx->idx_base = base;  // also valid when called between npt_begin_chrom and the first npt_submit
+  return NPT_OK;
+}
+
+int npt_set_next_read_index(npt_ctx* ctx, int64_t index) {
+  if (!ctx) return NPT_EINVAL;
+  if (index < 0 || index >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "read index out of range");
+  ctx->idx_base = index;
   return NPT_OK;
 }
 
@@ -657,22 +689,19 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   for (int s = 0; s < cf.num_sources; s++) if (cf.rna[s]) dc.rna_mask |= 1u << s;
   dc.annot_kind = annot->kind; dc.n_orf = n_orf; dc.G = (int)ref_len; dc.stride = (int)ref_len + 2;
 
-  // reference: 8 bases per word, first base in the top nibble, 4 words of padding
+  // reference: 8 bases per word, first base in the top nibble, 4 words of padding; and the same bases on the position grid
+  // of the fast walk: word W = positions 8W..8W+7 (1-based).  The codes are uploaded as they are (one byte per base) and
+  // packed by a kernel: two host loops over a 250 Mb chromosome cost more than walking its reads.
   const int nwords = (int)((ref_len + 7) / 8) + 4;
-  std::vector<uint32_t> words(nwords, 0);
-  for (int64_t i = 0; i < ref_len; i++) words[i >> 3] |= (uint32_t)(ref_codes[i] & 0xF) << (28 - 4 * (i & 7));
-  CK(ctx->d_ref.ensure(nwords));
-  CK(cudaMemcpy(ctx->d_ref.p, words.data(), (size_t)nwords * 4, cudaMemcpyHostToDevice));
+  const int gwords = (int)(ref_len >> 3) + 1 + 4;
+  CK(ctx->d_ref.ensure(nwords)); CK(ctx->d_refg.ensure(gwords));
+  CK(ctx->d_ref_codes.ensure((size_t)ref_len));
+  CK(cudaMemcpyAsync(ctx->d_ref_codes.p, ref_codes, (size_t)ref_len, cudaMemcpyHostToDevice, ctx->s_comp));
+  pack_reference_kernel<<<ctx->sm_count * 8, 256, 0, ctx->s_comp>>>(ctx->d_ref_codes.p, (long long)ref_len, ctx->d_ref.p, nwords, ctx->d_refg.p, gwords);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->s_comp));   // ref_codes is the caller's again when npt_begin_chrom returns
   dc.ref_words = ctx->d_ref.p; dc.ref_nwords = nwords;
-  {
-    // the same bases on the position grid of the fast walk: word W = positions 8W..8W+7 (1-based), first in the top nibble
-    const int gwords = (int)(ref_len >> 3) + 1 + 4;
-    std::vector<uint32_t> gw(gwords, 0);
-    for (int64_t i = 0; i < ref_len; i++) { const int64_t p = i + 1; gw[p >> 3] |= (uint32_t)(ref_codes[i] & 0xF) << (28 - 4 * (p & 7)); }
-    CK(ctx->d_refg.ensure(gwords));
-    CK(cudaMemcpy(ctx->d_refg.p, gw.data(), (size_t)gwords * 4, cudaMemcpyHostToDevice));
-    dc.refg_words = ctx->d_refg.p; dc.refg_nwords = gwords;
-  }
+  dc.refg_words = ctx->d_refg.p; dc.refg_nwords = gwords;
   CK(ctx->d_ostart.ensure(n_orf)); CK(ctx->d_oname.ensure(n_orf)); CK(ctx->d_ostrand.ensure(n_orf));
   if (n_orf) {
     CK(cudaMemcpy(ctx->d_ostart.p, annot->start, (size_t)n_orf * 4, cudaMemcpyHostToDevice));
@@ -818,6 +847,19 @@ static int submit_impl(npt_ctx* ctx, const npt_batch* b, const npt_packed_batch*
   if (n == 0) return NPT_OK;
   if (ctx->idx_base + n >= (1LL << 40)) return fail(ctx, NPT_EINVAL, "more than 2^40 reads");
   CK(cudaSetDevice(ctx->device));
+  {
+    // Retire what has finished, and keep at most two batches in flight: a batch holds ~1.1 KB of scratch per read (coverage
+    // entries, headers, sort buffers) until it is retired, and a long run of device-resident waves (500 M reads as 50
+    // submits) would otherwise pile all of it up.  The stream runs in order, so waiting for the oldest costs nothing.
+    int in_flight = 0;
+    for (size_t i = 0; i < ctx->batches.size(); i++)
+      if (!ctx->batches[i].retired) {
+        if (cudaEventQuery(ctx->batches[i].done) == cudaSuccess) { int rc = retire_batch(ctx, i); if (rc) return rc; }
+        else in_flight++;
+      }
+    for (size_t i = 0; i < ctx->batches.size() && in_flight >= 2; i++)
+      if (!ctx->batches[i].retired) { int rc = retire_batch(ctx, i); if (rc) return rc; in_flight--; }
+  }
   Batch B;
   B.n = n;
   BatchDev& d = B.d;
@@ -918,7 +960,11 @@ static int submit_impl(npt_ctx* ctx, const npt_batch* b, const npt_packed_batch*
   }
   d.cluster = ob; d.sub = ob + n; d.start_pos = ob + 2 * n; d.end_pos = ob + 3 * n; d.read_st = ob + 4 * n; d.read_en = ob + 5 * n;
   d.rflags = (unsigned*)(ob + 6 * n); d.maps_sum = ob + 7 * n; d.err_sum = ob + 8 * n; d.nbreaks = ob + 9 * n; d.break_loc = (unsigned*)(ob + 10 * n);
-  d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>(n / 4, 4096), 1LL << 30);
+  // overflow area for break lists longer than the inline slot: a quarter of an int per read for virus-shaped reads (a few
+  // per cent have a third junction), 24 ints per read in host mode (spliced reads: two breaks per junction), or what
+  // earlier batches of this chromosome needed; too small is not an error (the batch is redone with the exact size)
+  const double per_read = std::max<double>(ctx->cfg.coronavirus ? 0.25 : 24.0, 1.25 * ctx->brk_per_read);
+  d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>((int64_t)(n * per_read), 4096), 1LL << 30);
   CK(pool_get(ctx, (void**)&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int), &B.arena_bytes));
   CK(pool_get(ctx, (void**)&B.bctr, 8 * sizeof(unsigned), &B.bctr_bytes));
   CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
@@ -1321,28 +1367,6 @@ int npt_release_results(npt_ctx* ctx) {
   cudaStreamSynchronize(ctx->s_copy);
   free_batches(ctx);
   ctx->finalized = false;
-  return NPT_OK;
-}
-
-int npt_remap_clusters(npt_ctx* ctx, const int32_t* global_id, int32_t n_global) {
-  if (!ctx || !global_id) return fail(ctx, NPT_EINVAL, "null argument");
-  if (!ctx->finalized) return fail(ctx, NPT_ESTATE, "npt_remap_clusters before npt_end_chrom");
-  if (!ctx->dc.record_depth) return NPT_OK;
-  CK(cudaSetDevice(ctx->device));
-  // row_of_prov[prov] = global_id[local_rank[prov]]
-  const int nc = ctx->n_clusters;
-  std::vector<int> rank(std::max(nc, 1)), row(std::max(nc, 1));
-  if (nc) CK(cudaMemcpy(rank.data(), ctx->d_cl_rank.p, (size_t)nc * 4, cudaMemcpyDeviceToHost));
-  for (int p = 0; p < nc; p++) {
-    const int g = global_id[rank[p]];
-    if (g < 0 || g >= n_global) return fail(ctx, NPT_EINVAL, "global id %d out of range", g);
-    row[p] = g;
-  }
-  CK(ctx->d_vals.ensure(std::max(nc, 1)));
-  if (nc) CK(cudaMemcpyAsync(ctx->d_vals.p, row.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->s_comp));
-  int rc = coverage_rows(ctx, ctx->d_vals.p, n_global);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->s_comp));
   return NPT_OK;
 }
 

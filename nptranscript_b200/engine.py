@@ -139,6 +139,9 @@ class Engine:
     def set_read_index_base(self, base):
         self._ck(self.L.npt_set_read_index_base(self.h, base))
 
+    def set_next_read_index(self, index):
+        self._ck(self.L.npt_set_next_read_index(self.h, index))
+
     def submit(self, batch):
         """batch: synth.Batch-like with host numpy arrays (kept alive until wait/end_chrom)."""
         s = abi.npt_batch()
@@ -228,10 +231,6 @@ class Engine:
         k, r = C.c_float(), C.c_float()
         self._ck(self.L.npt_last_exchange_ms(self.h, C.byref(k), C.byref(r)))
         return k.value, r.value
-
-    def remap_clusters(self, global_id, n_global):
-        g = np.ascontiguousarray(global_id, dtype=np.int32)
-        self._ck(self.L.npt_remap_clusters(self.h, g.ctypes.data, n_global))
 
 
 def comm_unique_id():

@@ -1,18 +1,11 @@
-"""Multi-GPU: reads shard across ranks (contiguous ranges of the global submit order); there is no data-path collective
-while reads are walked.  At end of chromosome the per-shard tables merge by key.
+"""Host-side model of the multi-rank table merge, in numpy.
 
-Device path (exchange_keys / reduce_aggregates, NCCL): every rank exports the KEYS of its cluster, sub-cluster and
-break-point-pair tables with their first-appearance indices as one packed device buffer (npt_export_keys); one all-gather;
-every rank inserts the other ranks' keys into its own tables (npt_import_keys).  All ranks then hold the same key set with
-the same minima, so npt_end_chrom numbers clusters (CigarClusters.java:83) and sub-clusters (CigarCluster.java:660)
-identically everywhere, per-read ids come out global, and the counters — coverage rows, ORF counters, sub-cluster counts,
-break sums, pair counts, now in the same order on every rank — are summed in place with all-reduces.
-
-Host path (merge_tables, also through libnpt's npt_merge_tables): the same merge on plain result dicts with vectorised
-numpy; the CPU tests drive it with oracle output under gloo, and it is the independent check of the device path.
+The product path merges on the devices inside libnpt (csrc/comm.inl: npt_comm_init + npt_end_chrom_all, or npt_mg_*): keys
+are exchanged over NCCL, inserted into every rank's tables, numbered identically everywhere and the counters all-reduced.
+This module restates the same merge on plain result dicts — unique keys, id = rank of the minimum first-read index, summed
+counters, local->global id maps — so that the N>1 logic is covered on CPU (tests/test_multirank_gloo.py: world_size 2,
+gloo, oracle output per rank) and serves as an independent check of the device protocol.
 """
-import time
-
 import numpy as np
 
 _SENT = np.int64(-(1 << 62))
@@ -162,44 +155,6 @@ def merge_tables(tables):
     return out, maps
 
 
-def merge_tables_native(tables):
-    """Same contract as merge_tables, through libnpt's npt_merge_tables (C++ hash maps; ~20x faster than the numpy version,
-    which stays as the independent check in the tests)."""
-    import ctypes as C
-    from . import abi, engine
-    L = engine.lib()
-    S = len(tables[0]["total_counts"])
-    keep, structs = [], []
-    spec = dict(cl_first_read=np.int64, cl_key_off=np.uint32, cl_key_tok=np.int32, cl_sub_off=np.uint32, sub_first_read=np.int64,
-                sub_key_off=np.uint32, sub_key=np.int32, sub_count=np.int32, sub_break_sum=np.int32, sub_sum_off=np.uint32, sub_sums=np.int64,
-                sub_flags=np.uint8, total_counts=np.int32, spliced=np.int32, unspliced=np.int32, pair_src=np.int32, pair_level=np.int32,
-                pair_start=np.int32, pair_end=np.int32, pair_count=np.int32)
-    ct = {np.int64: C.c_int64, np.uint32: C.c_uint32, np.int32: C.c_int32, np.uint8: C.c_uint8}
-    for t in tables:
-        r = abi.npt_results()
-        r.n_clusters, r.n_subs, r.n_pairs = len(t["cl_first_read"]), len(t["sub_first_read"]), len(t["pair_src"])
-        r.n_orf = t["spliced"].shape[-1] if t["spliced"].size else 0
-        for k, dt in spec.items():
-            a = np.ascontiguousarray(t[k], dtype=dt)
-            keep.append(a)
-            setattr(r, k, a.ctypes.data_as(C.POINTER(ct[dt])))
-        structs.append(r)
-    arr = (C.POINTER(abi.npt_results) * len(structs))(*[C.pointer(x) for x in structs])
-    h = L.npt_merge_tables(len(structs), arr, S)
-    try:
-        m = L.npt_merged_results(h).contents
-        out = engine.Results.from_struct(m, S, abi.NPT_FETCH_TABLES)
-        maps = []
-        for r, t in enumerate(tables):
-            nc, ns = len(t["cl_first_read"]), len(t["sub_first_read"])
-            cm = np.ctypeslib.as_array(L.npt_merged_cluster_map(h, r), shape=(nc,)).copy() if nc else np.zeros(0, np.int32)
-            sm = np.ctypeslib.as_array(L.npt_merged_sub_map(h, r), shape=(ns,)).copy() if ns else np.zeros(0, np.int32)
-            maps.append((cm, sm))
-    finally:
-        L.npt_merge_free(h)
-    return out, maps
-
-
 def remap_reads(res, cmap, smap, cl_sub_off=None):
     """Rewrite a rank's per-read local ids to global ids.  smap is cluster-major over the rank's local sub-clusters."""
     cl, sb = res["cluster_id"].copy(), res["sub_id"].copy()
@@ -217,87 +172,3 @@ def permute_rows(rows, cmap, n_global):
     if len(cmap):
         out[cmap] = rows
     return out
-
-
-class _DevPtr:
-    """Expose a raw device pointer to torch (zero-copy) through __cuda_array_interface__."""
-
-    def __init__(self, ptr, n, typestr="<i4"):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
-def exchange_keys(eng, rank, world):
-    """Step 1 of the device-side protocol (after the last submit, before end_chrom): every rank's table keys reach every
-    other rank over NCCL and are inserted into its tables.  Returns ms."""
-    import torch
-    import torch.distributed as dist
-    t0 = time.perf_counter()
-    eng.wait()  # this rank's kernels
-    t1 = time.perf_counter()
-    ptr, n = eng.export_keys()
-    t2 = time.perf_counter()
-    sizes = torch.zeros(world, dtype=torch.int64, device="cuda")
-    sizes[rank] = n
-    dist.all_reduce(sizes)
-    sizes = sizes.cpu().tolist()
-    t3 = time.perf_counter()  # includes waiting for the slowest rank
-    m = int(max(sizes))
-    mine = torch.zeros(m, dtype=torch.int32, device="cuda")
-    mine[:n] = torch.as_tensor(_DevPtr(ptr, n, "<i4"), device="cuda")
-    allbuf = torch.empty(world * m, dtype=torch.int32, device="cuda")
-    dist.all_gather_into_tensor(allbuf, mine)
-    torch.cuda.synchronize()
-    t4 = time.perf_counter()
-    for r in range(world):
-        if r != rank:
-            eng.import_keys(allbuf[r * m:].data_ptr(), int(sizes[r]))
-    t5 = time.perf_counter()
-    exchange_keys.last = dict(wait_own_kernels_ms=1e3 * (t1 - t0), export_ms=1e3 * (t2 - t1), sizes_allreduce_ms=1e3 * (t3 - t2),
-                              all_gather_ms=1e3 * (t4 - t3), import_ms=1e3 * (t5 - t4), words=int(n))
-    return 1e3 * (t5 - t0)
-
-
-def reduce_aggregates(eng):
-    """Step 2 (after end_chrom): sum the counters, which are now in the same global order on every rank.  Returns ms."""
-    import torch
-    import torch.distributed as dist
-    t0 = time.perf_counter()
-    v = eng.device_view()
-    for ptr, n, dt in ((v.coverage, v.coverage_elems, "<i4"), (v.small_counts, v.small_elems, "<i4"), (v.sub_count, v.sub_count_elems, "<i4"),
-                       (v.sub_break_sum, v.sub_break_sum_elems, "<i4"), (v.sub_sums, v.sub_sums_elems, "<i8"), (v.pair_count, v.pair_count_elems, "<i4")):
-        if ptr and n:
-            dist.all_reduce(torch.as_tensor(_DevPtr(ptr, n, dt), device="cuda"))
-    torch.cuda.synchronize()
-    return 1e3 * (time.perf_counter() - t0)
-
-
-def merge_across_ranks_host(eng, rank, world, timing=False):
-    """Older GPU path, kept for comparison (call after end_chrom): tables fetched and merged on the host, coverage rows permuted on
-    the device and all-reduced.  0.18 s per step at 10 M reads per rank (sorting and hashing ~0.5 M break-point pairs on the host).
-    Returns the merge time in ms (timing=True) or (global tables, (cluster_map, sub_map), local cl_sub_off)."""
-    import torch
-    import torch.distributed as dist
-    from . import abi
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = eng.fetch(abi.NPT_FETCH_TABLES)
-    t1 = time.perf_counter()
-    mine = local_tables(res, 0)  # first-read indices are already global (npt_set_read_index_base)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, mine)
-    t2 = time.perf_counter()
-    glob, maps = merge_tables_native(gathered)
-    t3 = time.perf_counter()
-    cmap, smap = maps[rank]
-    eng.remap_clusters(cmap, glob["n_clusters"])
-    v = eng.device_view()
-    if v.coverage and v.coverage_elems:
-        cov = torch.as_tensor(_DevPtr(v.coverage, v.coverage_elems), device="cuda")
-        dist.all_reduce(cov)
-    small = torch.as_tensor(_DevPtr(v.small_counts, v.small_elems), device="cuda")
-    dist.all_reduce(small)
-    torch.cuda.synchronize()
-    t4 = time.perf_counter()
-    ms = 1e3 * (t4 - t0)
-    merge_across_ranks_host.last = dict(fetch_ms=1e3 * (t1 - t0), gather_ms=1e3 * (t2 - t1), merge_ms=1e3 * (t3 - t2), device_ms=1e3 * (t4 - t3))
-    return ms if timing else (glob, (cmap, smap), res["cl_sub_off"])

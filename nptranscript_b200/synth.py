@@ -21,6 +21,15 @@ class _Params(C.Structure):
     ]
 
 
+class _HostParams(C.Structure):
+    _fields_ = [
+        ("chrom_len", C.c_int32), ("n_genes", C.c_int32), ("gene_exon_off", C.c_void_p), ("exon_start", C.c_void_p), ("exon_end", C.c_void_p),
+        ("p_skip", C.c_double), ("p_trunc5", C.c_double), ("p_intergenic", C.c_double), ("gene_skew", C.c_double),
+        ("p_mismatch", C.c_double), ("p_ins", C.c_double), ("p_del", C.c_double), ("indel_mean", C.c_double), ("p_neg", C.c_double),
+        ("num_sources", C.c_int32), ("src_fixed", C.c_int32), ("transcriptome", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -34,6 +43,8 @@ def lib():
         _lib.npts_copy.argtypes = [C.c_void_p] * 8
         _lib.npts_free.argtypes = [C.c_void_p]
         _lib.npts_genome.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
+        _lib.npts_generate_host.restype = C.c_void_p
+        _lib.npts_generate_host.argtypes = [C.POINTER(_HostParams), C.c_void_p, C.c_uint64, C.c_uint64, C.c_int64, C.c_int]
     return _lib
 
 
@@ -98,6 +109,51 @@ def generate(w: Workload, seed: int, n: int, first_index: int = 0, num_sources: 
     finally:
         L.npts_free(h)
     return b
+
+
+def _collect(L, h, n, alloc):
+    try:
+        nn, nc, ns = C.c_int64(), C.c_int64(), C.c_int64()
+        L.npts_sizes(h, C.byref(nn), C.byref(nc), C.byref(ns))
+
+        def mk(count, dt):
+            if alloc is None:
+                return np.empty(count, dtype=dt)
+            return np.frombuffer(alloc(max(1, count * np.dtype(dt).itemsize)), dtype=dt, count=count)
+
+        b = Batch(mk(n, np.int32), mk(n, np.uint16), mk(n, np.uint16), mk(n + 1, np.uint32), mk(nc.value, np.uint32),
+                  mk(n + 1, np.uint64), mk(ns.value, np.uint8))
+        L.npts_copy(h, b.pos.ctypes.data, b.flag.ctypes.data, b.src.ctypes.data, b.cigar_off.ctypes.data,
+                    b.cigar.ctypes.data if nc.value else None, b.seq_off.ctypes.data, b.seq4.ctypes.data if ns.value else None)
+    finally:
+        L.npts_free(h)
+    return b
+
+
+def host_genome_codes(c) -> np.ndarray:
+    """Seeded uniform ACGT for a workloads.HostChromosome (no polyA tail)."""
+    out = np.empty(c.length, dtype=np.uint8)
+    lib().npts_genome(c.seed * 1000003 + c.index, c.length, 0, out.ctypes.data)
+    return out
+
+
+def generate_host(c, genome, seed: int, n: int, first_index: int = 0, num_sources: int = 1, src_fixed: int = -1, transcriptome: bool = False,
+                  nthreads: int = 0, alloc=None) -> Batch:
+    """Spliced long reads on one chromosome of the synthetic gene model (workloads.HostChromosome); read i depends only on
+    (seed, first_index + i).  transcriptome=True: source 0 carries the full transcripts aligned error-free."""
+    p = _HostParams()
+    off = np.ascontiguousarray(c.gene_exon_off, np.int32); es = np.ascontiguousarray(c.exon_start, np.int32); ee = np.ascontiguousarray(c.exon_end, np.int32)
+    p.chrom_len, p.n_genes = c.length, c.n_genes
+    p.gene_exon_off, p.exon_start, p.exon_end = off.ctypes.data, es.ctypes.data, ee.ctypes.data
+    p.p_skip, p.p_trunc5, p.p_intergenic, p.gene_skew = c.p_skip, c.p_trunc5, c.p_intergenic, c.gene_skew
+    p.p_mismatch, p.p_ins, p.p_del, p.indel_mean, p.p_neg = c.p_mismatch, c.p_ins, c.p_del, c.indel_mean, c.p_neg
+    p.num_sources, p.src_fixed, p.transcriptome = num_sources, src_fixed, int(transcriptome)
+    if nthreads <= 0:
+        nthreads = os.cpu_count() or 1
+    L = lib()
+    g = np.ascontiguousarray(genome, np.uint8)
+    h = L.npts_generate_host(C.byref(p), g.ctypes.data, seed, first_index, n, nthreads)
+    return _collect(L, h, n, alloc)
 
 
 def from_reads(reads) -> Batch:

@@ -86,6 +86,10 @@ struct npts_out {
   std::vector<uint8_t> seq4;
 };
 
+struct Noise { double p_mismatch, p_ins, p_del, indel_mean; bool eqx, clips; };
+static void emit_blocks(const Noise& P, const uint8_t* genome, Rng& r, const int* bs, const int* be, int nb, std::vector<uint32_t>& cig,
+                        std::vector<uint8_t>& bases);
+
 static void gen_read(const npts_params& P, const uint8_t* genome, uint64_t seed, uint64_t idx, int32_t& pos, uint16_t& flag, uint16_t& src,
                      std::vector<uint32_t>& cig, std::vector<uint8_t>& bases) {
   Rng r(seed, idx);
@@ -127,6 +131,13 @@ static void gen_read(const npts_params& P, const uint8_t* genome, uint64_t seed,
   pos = bs[0];
   flag = (uint16_t)(r.uni() < P.p_neg ? 16 : 0);
   src = (uint16_t)(P.src_fixed >= 0 ? P.src_fixed : (int)(idx % (uint64_t)std::max(1, P.num_sources)));
+  Noise N{P.p_mismatch, P.p_ins, P.p_del, P.indel_mean, P.use_eqx != 0, true};
+  emit_blocks(N, genome, r, bs, be, nb, cig, bases);
+}
+
+// aligned blocks -> CIGAR + bases with per-base noise and soft clips
+static void emit_blocks(const Noise& P, const uint8_t* genome, Rng& r, const int* bs, const int* be, int nb, std::vector<uint32_t>& cig,
+                        std::vector<uint8_t>& bases) {
   static const uint8_t c4[4] = {1, 2, 4, 8};
   auto push = [&](int len, int op) {
     if (len <= 0) return;
@@ -134,7 +145,7 @@ static void gen_read(const npts_params& P, const uint8_t* genome, uint64_t seed,
     else cig.push_back(((uint32_t)len << 4) | (uint32_t)op);
   };
   auto geo = [&]() { int l = 1; double q = 1.0 - 1.0 / P.indel_mean; while (r.uni() < q && l < 30) l++; return l; };
-  int clip5 = r.range(0, 30), clip3 = r.range(10, 80);
+  int clip5 = P.clips ? r.range(0, 30) : 0, clip3 = P.clips ? r.range(10, 80) : 0;
   if (clip5) { push(clip5, 4); for (int i = 0; i < clip5; i++) bases.push_back(c4[r.next() & 3]); }
   for (int b = 0; b < nb; b++) {
     if (b > 0) push(bs[b] - be[b - 1] - 1, 3);
@@ -153,7 +164,7 @@ static void gen_read(const npts_params& P, const uint8_t* genome, uint64_t seed,
         bool mm = !edge && (r.uni() < P.p_mismatch);
         uint8_t c = g;
         if (mm) { do { c = c4[r.next() & 3]; } while (c == g); }
-        if (P.use_eqx) push(1, mm ? 8 : 7); else push(1, 0);
+        if (P.eqx) push(1, mm ? 8 : 7); else push(1, 0);
         bases.push_back(c); p++;
       }
     }
@@ -162,7 +173,10 @@ static void gen_read(const npts_params& P, const uint8_t* genome, uint64_t seed,
   for (int i = 0; i < clip3; i++) bases.push_back(c4[r.next() & 3]);
 }
 
-void* npts_generate(const npts_params* P, const uint8_t* genome, uint64_t seed, uint64_t first_index, int64_t n, int nthreads) {
+}  // extern "C"
+
+template <typename Gen>
+static void* generate_with(Gen gen, int64_t n, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   npts_out* O = new npts_out();
   O->pos.resize(n); O->flag.resize(n); O->src.resize(n);
@@ -179,7 +193,7 @@ void* npts_generate(const npts_params* P, const uint8_t* genome, uint64_t seed, 
       if (c >= nch) break;
       auto& vc = ccig[c]; auto& vs = cseq[c];
       for (int64_t i = c * CH; i < std::min(n, (c + 1) * CH); i++) {
-        gen_read(*P, genome, seed, first_index + (uint64_t)i, O->pos[i], O->flag[i], O->src[i], cig, bases);
+        gen(i, O->pos[i], O->flag[i], O->src[i], cig, bases);
         O->cigar_off[i + 1] = (uint32_t)cig.size();          // lengths for now
         O->seq_off[i + 1] = (uint64_t)((bases.size() + 1) / 2);
         vc.insert(vc.end(), cig.begin(), cig.end());
@@ -199,6 +213,67 @@ void* npts_generate(const npts_params* P, const uint8_t* genome, uint64_t seed, 
     if (!cseq[c].empty()) memcpy(O->seq4.data() + O->seq_off[i0], cseq[c].data(), cseq[c].size());
   }
   return O;
+}
+
+extern "C" {
+
+void* npts_generate(const npts_params* P, const uint8_t* genome, uint64_t seed, uint64_t first_index, int64_t n, int nthreads) {
+  return generate_with([=](int64_t i, int32_t& pos, uint16_t& flag, uint16_t& src, std::vector<uint32_t>& cig, std::vector<uint8_t>& bases) {
+    gen_read(*P, genome, seed, first_index + (uint64_t)i, pos, flag, src, cig, bases);
+  }, n, nthreads);
+}
+
+// ---- host mode (BASELINE.json configs[4]): spliced long reads on one chromosome of a gene model.
+// read = random gene (popularity skewed), its exons with internal ones skipped at random, 5'-truncated; source 0 (with
+// transcriptome != 0) carries the full transcripts aligned error-free, the "transcriptome BAM" of --firstIsTranscriptome.
+typedef struct npts_host_params {
+  int32_t chrom_len;
+  int32_t n_genes;
+  const int32_t* gene_exon_off;   // n_genes + 1
+  const int32_t* exon_start;      // 1-based inclusive, ascending inside a gene
+  const int32_t* exon_end;
+  double p_skip, p_trunc5, p_intergenic, gene_skew;
+  double p_mismatch, p_ins, p_del, indel_mean, p_neg;
+  int32_t num_sources, src_fixed, transcriptome;
+} npts_host_params;
+
+#define NPTS_MAX_BLOCKS 64
+void* npts_generate_host(const npts_host_params* P, const uint8_t* genome, uint64_t seed, uint64_t first_index, int64_t n, int nthreads) {
+  const npts_host_params H = *P;
+  return generate_with([=](int64_t i, int32_t& pos, uint16_t& flag, uint16_t& src, std::vector<uint32_t>& cig, std::vector<uint8_t>& bases) {
+    const uint64_t idx = first_index + (uint64_t)i;
+    Rng r(seed, idx);
+    cig.clear(); bases.clear();
+    src = (uint16_t)(H.src_fixed >= 0 ? H.src_fixed : (int)(idx % (uint64_t)std::max(1, H.num_sources)));
+    const bool exact = H.transcriptome && src == 0;
+    int bs[NPTS_MAX_BLOCKS], be[NPTS_MAX_BLOCKS], nb = 0;
+    if (H.n_genes <= 0 || (!exact && r.uni() < H.p_intergenic)) {   // unspliced fragment anywhere
+      int len = std::max(100, (int)std::exp(std::log(900.0) + 0.5 * r.normal()));
+      len = std::min(len, std::max(1, H.chrom_len / 2));
+      int st = r.range(1, std::max(1, H.chrom_len - len - 1));
+      bs[0] = st; be[0] = std::min(H.chrom_len, st + len); nb = 1;
+    } else {
+      const int g = exact ? (int)(idx / (uint64_t)std::max(1, H.num_sources) % (uint64_t)H.n_genes)
+                          : std::min(H.n_genes - 1, (int)(H.n_genes * std::pow(r.uni(), H.gene_skew)));
+      const int e0 = H.gene_exon_off[g], e1 = H.gene_exon_off[g + 1];
+      int first = e0;
+      if (!exact && e1 - e0 > 1 && r.uni() < H.p_trunc5) first = r.range(e0, e1 - 1);   // direct RNA: 3'-anchored
+      for (int e = first; e < e1 && nb < NPTS_MAX_BLOCKS; e++) {
+        const bool inner = e > first && e < e1 - 1;
+        if (!exact && inner && r.uni() < H.p_skip) continue;
+        bs[nb] = H.exon_start[e]; be[nb] = H.exon_end[e]; nb++;
+      }
+      if (!exact && nb > 0 && r.uni() < 0.7) {   // the read starts somewhere inside its first exon
+        const int L = be[0] - bs[0];
+        if (L > 20) bs[0] += r.range(0, L - 20);
+      }
+    }
+    for (int b = 0; b < nb; b++) { if (be[b] < bs[b]) be[b] = bs[b]; if (be[b] > H.chrom_len) be[b] = H.chrom_len; }
+    pos = bs[0];
+    flag = (uint16_t)(r.uni() < H.p_neg ? 16 : 0);
+    Noise N{exact ? 0.0 : H.p_mismatch, exact ? 0.0 : H.p_ins, exact ? 0.0 : H.p_del, H.indel_mean, false, !exact};
+    emit_blocks(N, genome, r, bs, be, nb, cig, bases);
+  }, n, nthreads);
 }
 
 void npts_sizes(void* h, int64_t* n, int64_t* n_cigar, int64_t* n_seq_bytes) {

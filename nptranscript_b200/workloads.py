@@ -223,3 +223,77 @@ def ref_char_to_code(seq: str) -> np.ndarray:
         table[ord(ch)] = i
         table[ord(ch.lower())] = i
     return table[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)]
+
+
+# ---------------------------------------------------------------------------------------------- host mode (configs[4])
+@dataclass
+class HostChromosome:
+    """One chromosome of the synthetic human-like gene model (no human reference / GTF ships with the
+    reference): genes laid out left to right, GENCODE-like exon counts, exon and intron lengths; the exon table is what
+    GFFAnnotation's constructor would hold for this chromosome (one row per exon line, gene = the exon's Parent)."""
+    name: str
+    index: int
+    length: int
+    seed: int
+    gene_exon_off: np.ndarray = None   # int32 [n_genes + 1]
+    exon_start: np.ndarray = None      # int32, 1-based inclusive
+    exon_end: np.ndarray = None
+    gene_strand: np.ndarray = None     # bool [n_genes]
+    # read model (spliced long reads, 8-12 % error)
+    p_skip: float = 0.12
+    p_trunc5: float = 0.5
+    p_intergenic: float = 0.03
+    gene_skew: float = 3.0
+    p_mismatch: float = 0.04
+    p_ins: float = 0.03
+    p_del: float = 0.03
+    indel_mean: float = 1.5
+    p_neg: float = 0.5
+
+    @property
+    def n_genes(self):
+        return len(self.gene_exon_off) - 1
+
+    @property
+    def annotation(self) -> Annotation:
+        per = np.diff(self.gene_exon_off)
+        gid = np.repeat(np.arange(self.n_genes), per)
+        genes = [f"G{self.index}x{g}" for g in gid]
+        return Annotation.gff(genes, self.exon_start.tolist(), self.exon_end.tolist(), np.repeat(self.gene_strand, per).tolist())
+
+
+def host_chromosome(index, length, seed=20200500, name=None) -> HostChromosome:
+    rng = np.random.default_rng(seed + 7919 * index)
+    starts, ends, off, strand = [], [], [0], []
+    margin = 5000 if length > 200000 else 300
+    p = margin
+    while True:
+        n_ex = int(min(40, 1 + rng.geometric(0.13)))
+        ex_len = np.maximum(30, np.exp(np.log(140.0) + 0.7 * rng.standard_normal(n_ex))).astype(np.int64)
+        in_len = np.maximum(80, np.exp(np.log(1500.0) + 1.1 * rng.standard_normal(n_ex))).astype(np.int64)
+        span = int(ex_len.sum() + in_len[:-1].sum())
+        if p + span + margin > length:
+            if starts or span + 2 * margin > length:
+                break
+            continue   # a chromosome this short (chrM) gets at least one gene that fits
+        q = p
+        for k in range(n_ex):
+            starts.append(q); ends.append(q + int(ex_len[k]) - 1)
+            q += int(ex_len[k]) + int(in_len[k])
+        off.append(len(starts)); strand.append(bool(rng.random() < 0.5))
+        p = q + int(np.exp(np.log(8000.0) + 1.0 * rng.standard_normal()))
+    c = HostChromosome(name=name or f"chr{index + 1}", index=index, length=length, seed=seed)
+    c.gene_exon_off = np.asarray(off, np.int32); c.exon_start = np.asarray(starts, np.int32); c.exon_end = np.asarray(ends, np.int32)
+    c.gene_strand = np.asarray(strand, bool)
+    return c
+
+
+# GRCh38-like relative lengths of chr1..22, X, Y, M (Mb), scaled by `scale` (1.0 = the real lengths)
+_GRCH38_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57, 0.0166]
+
+
+def human_like(scale=0.04, seed=20200500):
+    """25 chromosomes; scale 1.0 gives ~2e5 genes / ~1.6e6 exons, the default 0.04 keeps genome generation and HBM use of a
+    bench run small (chr1 = 9.9 Mb) while every per-chromosome code path (GFF exon search, reference out of shared memory,
+    a new cluster table per chromosome) is the same."""
+    return [host_chromosome(i, max(20000, int(mb * 1e6 * scale)), seed) for i, mb in enumerate(_GRCH38_MB)]

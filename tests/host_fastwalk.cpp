@@ -12,7 +12,7 @@ using namespace npt;
 
 template <bool RECORD>
 static void run_all(const DevCfg& c, const BatchDev& b) {
-  std::vector<uint32_t> tile(FW_TILE_STRIDE + 4), ring(FW_RING + FW_RING_PAD, 0);
+  std::vector<uint32_t> tile(FW_TILE_STRIDE + 4), ring(FW_RING + FW_RING_PAD + FW_BRK_BUF, 0);
   uint32_t* cigT = tile.data();
   uint32_t* seqT = tile.data() + FW_CIG_TILE;
   for (long long r = 0; r < b.n; r++) {
@@ -42,7 +42,7 @@ static void run_all(const DevCfg& c, const BatchDev& b) {
 extern "C" int hfw_run(int T, int G, int record, const uint32_t* refg, int refg_nwords, long long n, const int* pos, const uint32_t* cigar_off,
                        const uint32_t* cigar, const unsigned long long* seq_off, const uint8_t* seq4, int* nbreaks, int* break_arena,
                        int* read_st, int* read_en, int* maps_sum, int* err_sum, unsigned* rflags, unsigned* break_loc, uint4* fhdrA,
-                       unsigned* fmeta, unsigned* frare, uint4* fent, unsigned* slow_list, unsigned* bctr) {
+                       unsigned* fmeta, unsigned* frare, uint4* fent, unsigned* slow_list, unsigned* bctr, unsigned break_cap) {
   DevCfg c;
   memset(&c, 0, sizeof c);
   c.T = T; c.G = G; c.stride = G + 2; c.record_depth = record; c.refg_words = refg; c.refg_nwords = refg_nwords;
@@ -51,7 +51,7 @@ extern "C" int hfw_run(int T, int G, int record, const uint32_t* refg, int refg_
   b.n = n; b.pos = pos; b.cigar_off = cigar_off; b.cigar = cigar; b.seq_off = seq_off; b.seq4 = seq4;
   b.cigar_words = cigar_off[n]; b.seq_bytes = (long long)seq_off[n];
   b.nbreaks = nbreaks; b.break_arena = break_arena; b.read_st = read_st; b.read_en = read_en; b.maps_sum = maps_sum; b.err_sum = err_sum;
-  b.rflags = rflags; b.break_loc = break_loc; b.fhdrA = fhdrA; b.fmeta = fmeta; b.frare = frare; b.fent = fent; b.slow_list = slow_list; b.bctr = bctr; b.fast = 1;
+  b.rflags = rflags; b.break_loc = break_loc; b.fhdrA = fhdrA; b.fmeta = fmeta; b.frare = frare; b.fent = fent; b.slow_list = slow_list; b.bctr = bctr; b.fast = 1; b.break_cap = break_cap;
   if (record) run_all<true>(c, b); else run_all<false>(c, b);
   return (int)bctr[7];
 }

@@ -29,7 +29,7 @@ def _lib():
         assert r.returncode == 0, r.stderr
         os.replace(tmp, SO)
     L = C.CDLL(SO)
-    L.hfw_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong] + [C.c_void_p] * 19
+    L.hfw_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong] + [C.c_void_p] * 19 + [C.c_uint]
     return L
 
 
@@ -43,11 +43,11 @@ def ref_grid(codes):
     return (nib << sh).reshape(nw, 8).sum(axis=1).astype(np.uint32)
 
 
-def run_host(b, g, T, record):
+def run_host(b, g, T, record, break_cap=0):
     L = _lib()
     n = b.n
     refg = ref_grid(g)
-    out = dict(nbreaks=np.zeros(n, np.int32), arena=np.zeros(n * BRK_INLINE, np.int32), read_st=np.zeros(n, np.int32),
+    out = dict(nbreaks=np.zeros(n, np.int32), arena=np.zeros(n * BRK_INLINE + break_cap, np.int32), read_st=np.zeros(n, np.int32),
                read_en=np.zeros(n, np.int32), maps=np.zeros(n, np.int32), errs=np.zeros(n, np.int32), rflags=np.zeros(n, np.uint32),
                bloc=np.zeros(n, np.uint32), fhdrA=np.zeros(n * 4, np.uint32), fmeta=np.zeros(n, np.uint32),
                frare=np.zeros(n * RARE_WORDS, np.uint32),
@@ -59,7 +59,7 @@ def run_host(b, g, T, record):
                       out["read_st"].ctypes.data, out["read_en"].ctypes.data, out["maps"].ctypes.data, out["errs"].ctypes.data,
                       out["rflags"].ctypes.data, out["bloc"].ctypes.data, out["fhdrA"].ctypes.data, out["fmeta"].ctypes.data, out["frare"].ctypes.data,
                       out["fent"].ctypes.data,
-                      out["slow"].ctypes.data, out["bctr"].ctypes.data)
+                      out["slow"].ctypes.data, out["bctr"].ctypes.data, break_cap)
     out["nslow"] = nslow
     return out
 
@@ -214,3 +214,36 @@ def test_known_answers():
     assert run_host(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67, 68, 69)))]), g, 1000, 1)["nslow"] == 1
     check(synth.from_reads([(5, 0, 0, "65M28190N1600M", kat2((65, 66, 67)))]), g, w, 1000, min_fast=1.0)
     check(b, g, w, 1000, min_fast=1.0)
+
+
+def test_long_break_lists_without_depth_recording():
+    """host-mode shape: spliced reads with many junctions.  Without depth recording the fast walk keeps them (any number of
+    aligned blocks, up to 30 junctions) and moves lists longer than the inline slot to the overflow area; with a too small
+    overflow area it says so (bctr[1]) and reports the need (bctr[0])"""
+    c = workloads.human_like()[20]
+    g = synth.host_genome_codes(c)
+    b = synth.generate_host(c, g, 9, 3000, num_sources=2, transcriptome=True)
+    T = 50
+    ora = oracle.run(oracle.make_config(bin=10, break_thresh=T, record_depth=0, num_sources=2), g, workloads.SARS2.annotation, [b])
+    nb = np.diff(ora["break_off"].astype(np.int64))
+    assert (nb > BRK_INLINE).mean() > 0.3
+    cap = int(nb[nb > BRK_INLINE].sum())
+    out = run_host(b, g, T, 0, break_cap=cap)
+    slow = (out["rflags"] & 0x20) != 0
+    assert slow.mean() < 0.05 and out["bctr"][1] == 0 and out["bctr"][0] == nb[(nb > BRK_INLINE) & ~slow].sum()
+    for r in np.flatnonzero(~slow):
+        o = int(ora["break_off"][r])
+        want = ora["breaks"][o:o + nb[r]]
+        assert out["nbreaks"][r] == nb[r]
+        if nb[r] <= BRK_INLINE:
+            assert out["bloc"][r] == 0xFFFFFFFF and np.array_equal(out["arena"][r * BRK_INLINE:r * BRK_INLINE + nb[r]], want)
+        else:
+            at = b.n * BRK_INLINE + int(out["bloc"][r])
+            assert np.array_equal(out["arena"][at:at + nb[r]], want), r
+    for k, f in (("read_st", "read_st"), ("read_en", "read_en")):
+        assert np.array_equal(out[k][~slow], ora[f][~slow]), f
+    small = run_host(b, g, T, 0, break_cap=cap // 2)
+    assert small["bctr"][1] == 1 and small["bctr"][0] >= cap - nb[(nb > BRK_INLINE) & slow].sum()
+    # with depth recording those reads still go to the serial walker
+    rec = run_host(b, g, T, 1)
+    assert np.array_equal((rec["rflags"] & 0x20) != 0, (nb > BRK_INLINE) | slow | ((rec["rflags"] & 0x20) != 0)) and ((rec["rflags"] & 0x20) != 0)[nb > BRK_INLINE].all()

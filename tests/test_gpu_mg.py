@@ -1,7 +1,7 @@
 """npt_mg_* — the in-process multi-device context behind the C ABI (csrc/comm.inl) — on ONE GPU: a device listed several
 times gives several contexts whose collectives run as device-to-device copies and an add kernel; the submit split, the
 key exchange, the global numbering, the summed counters and the re-interleaved per-read results must equal the oracle on
-the unsharded input.  tests/multigpu_check.py runs the same check over NCCL on 2, 4 or 8 real devices."""
+the unsharded input.  tests/mg_check.py runs the same check over NCCL on 2, 4 or 8 real devices."""
 import numpy as np
 import pytest
 
