@@ -44,6 +44,8 @@ final class Npt {
   static final MethodHandle beginChrom =
       h("npt_begin_chrom", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
   static final MethodHandle submit = h("npt_submit", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+  // the compact transfer format (npt_packed_batch: 16-bit CIGAR words, 2-bit bases): half the bytes over PCIe
+  static final MethodHandle submitPacked = h("npt_submit_packed", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   static final MethodHandle waitAll = h("npt_wait", FunctionDescriptor.of(JAVA_INT, ADDRESS));
   static final MethodHandle endChrom = h("npt_end_chrom", FunctionDescriptor.of(JAVA_INT, ADDRESS));
   static final MethodHandle fetch = h("npt_fetch_results", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));

@@ -80,6 +80,7 @@ template <int MODE, bool REF_SMEM>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, const BatchDev b) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   if (MODE == 1 && ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  if (MODE == 1 && b.fast == 2 && ldcg(b.bctr + 8)) return;  // ... of the serial walker's reads only: the host re-runs their chain
   // behind the fast walk only the handed-over reads are walked here: blocks that would find the list empty leave at once
   // (the grid is sized for a whole batch; loading the reference into shared memory costs more than walking a few reads)
   if (b.fast && (unsigned long long)blockIdx.x * WALK_THREADS >= (unsigned long long)ldcg(b.bctr + 7)) return;
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const DevCfg c, cons
           if (MODE == 2) {
             const unsigned n_all = (unsigned)b.nbreaks[r];
             const unsigned loc = atomicAdd(b.bctr, n_all);
-            if (loc + n_all > b.break_cap) { atomicOr(b.bctr + 1, 1u); b.break_loc[r] = 0xFFFFFFFEu; ok = false; }
+            // beside a fast walk the bulk of the batch is clustered on another stream at this moment: only this chain is redone
+            if (loc + n_all > b.break_cap) { atomicOr(b.bctr + (b.fast == 2 ? 8 : 1), 1u); b.break_loc[r] = 0xFFFFFFFEu; ok = false; }
             else { b.break_loc[r] = loc; bdst = b.break_arena + b.n * BRK_INLINE + loc; }
           }
         }
@@ -659,9 +661,12 @@ constexpr int CLUSTER_THREADS = 128;
 #ifndef NPT_CLUSTER_MIN_BLOCKS
 #define NPT_CLUSTER_MIN_BLOCKS 1
 #endif
-__global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) cluster_kernel(const DevCfg c, const BatchDev b) {
+// which = 0: every read of the batch; 1: the reads the fast walk finished (the serial walker may still be writing the
+// others: only their SLOWPATH bit is looked at); 2: the reads of slow_list.  1 and 2 run concurrently on two streams.
+__global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) cluster_kernel(const DevCfg c, const BatchDev b, const int which) {
   extern __shared__ __align__(16) int s_int[];
   if (ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
+  if (which == 2 && ldcg(b.bctr + 8)) return;
   int* s_ostart = s_int;
   int* s_oname = s_ostart + c.n_orf;
   int* s_ostrand = s_oname + c.n_orf;
@@ -671,9 +676,13 @@ __global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) clust
   for (int i = threadIdx.x; i < ncnt; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
 
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += (long long)gridDim.x * blockDim.x) {
-    const unsigned slowbit = b.rflags[r] & 0x20u;  // diagnostic: walked by the serial path
-    if (b.rflags[r] & 0x10u) {  // bad record: not clustered
+  const long long n_mine = which == 2 ? (long long)ldcg(b.bctr + 7) : b.n;
+  for (long long k0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; k0 < n_mine; k0 += (long long)gridDim.x * blockDim.x) {
+    const long long r = which == 2 ? (long long)b.slow_list[k0] : k0;
+    const unsigned rf0 = which == 1 ? ldcg(b.rflags + r) : b.rflags[r];
+    const unsigned slowbit = rf0 & 0x20u;  // diagnostic: walked by the serial path
+    if (which == 1 && slowbit) continue;
+    if (rf0 & 0x10u) {  // bad record: not clustered
       b.cluster[r] = -1; b.sub[r] = -1; b.start_pos[r] = 0; b.end_pos[r] = 0;
       continue;
     }

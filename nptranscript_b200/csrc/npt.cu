@@ -88,7 +88,7 @@ struct npt_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   std::string err;
-  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_aux = nullptr;   // s_aux: the serial walker's reads beside the bulk
   bool in_chrom = false, finalized = false;
   // chromosome state
   int chrom_index = 0;
@@ -138,6 +138,8 @@ struct npt_ctx {
   int64_t n_pairs = 0;
   int64_t n_total = 0;
   int64_t n_slow = 0;            // reads the fast walk handed to the serial walker (this chromosome)
+  bool split_streams = false;
+  bool cov_dirty = true;         // d_cov may hold counts (fresh allocation, or a chromosome that was not finished)
   float brk_per_read = 0;        // largest overflow need (ints per read) of a retired batch of this chromosome
   long long total_breaks = 0;
   DBuf<long long> d_ex_first;
@@ -176,7 +178,8 @@ struct npt_ctx {
   float walk_ms = 0, fin_ms = 0;
   int64_t walk_launches = 0, total_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> walk_events;
-  std::vector<cudaEvent_t> stage_events;  // 7 per batch: before / after fast walk, walk<0>, walk<2>, cluster, walk<1>, coverage (keys + sort + accumulate)
+  std::vector<cudaEvent_t> stage_events;  // 12 per batch: (begin, end) of fast walk, walk<0>, walk<2> (+ clustering of its reads), cluster, walk<1>, coverage (keys + sort + accumulate)
+  std::vector<cudaEvent_t> order_events;  // fork / join of the second compute stream, 3 per batch
   float stage_ms[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -358,6 +361,13 @@ __global__ void kx_list_pairs_kernel(const PairEntry* pr, unsigned nslots, int* 
   }
 }
 
+// the first `used` elements of each of the COV_ARRAYS accumulation arrays back to zero (blockIdx.y = array)
+__global__ void clear_rows_kernel(int* cov, size_t arr_stride, size_t used) {
+  int* a = cov + (size_t)blockIdx.y * arr_stride;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < used; i += (size_t)gridDim.x * blockDim.x * 4)
+    for (int k = 0; k < 4; k++) if (i + k < used) a[i + k] = 0;
+}
+
 // Coverage rows: out[arr][row_of(prov)][src][:] = arr == 0 ? inclusive scan of the difference row : copy.
 // One block per (arr, prov, src) row; the "segmented prefix scan" of the design (segments = rows).
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8;
@@ -430,53 +440,74 @@ int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
   const BatchDev& bd = B.d;
   const DevCfg& dc = ctx->dc;
   const int T = WALK_THREADS;
-  cudaEvent_t ev[7];
+  cudaStream_t sc = ctx->s_comp, sa = ctx->s_aux;
+  // 12 events per batch: (begin, end) of the six stages of npt_last_stage_ms
+  cudaEvent_t ev[12];
   for (auto& e : ev) { CK(cudaEventCreate(&e)); ctx->stage_events.push_back(e); }
-  CK(cudaEventRecord(ev[0], ctx->s_comp));
+  cudaEvent_t fork_ev, join_cl, join_cov;   // ordering only
+  CK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&join_cl, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&join_cov, cudaEventDisableTiming));
+  ctx->order_events.push_back(fork_ev); ctx->order_events.push_back(join_cl); ctx->order_events.push_back(join_cov);
+  const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
   // ---- the fast walk: every read it can restate exactly (breaks, read offsets, coverage entries); the others go to slow_list
+  CK(cudaEventRecord(ev[0], sc));
+  // NPT_SPLIT=1 (experiment, off by default): the serial walker's few reads run beside the bulk on a second stream.  Measured
+  // slower (13.7 against 11.9 ms per 4 M reads, profiles/NOTES.md): the walk kernels need the largest shared-memory carve-out,
+  // cluster_kernel the smallest, and an SM only changes it when idle, so the two chains wait for each other.
+  const bool split = bd.fast && from_stage == 0 && ctx->split_streams;
   if (bd.fast && from_stage == 0) {
     const bool rec = ctx->fast_record;
     if (ctx->ref_smem) {
-      if (rec) fast_walk_kernel<true, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
-      else fast_walk_kernel<true, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+      if (rec) fast_walk_kernel<true, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, sc>>>(dc, bd);
+      else fast_walk_kernel<true, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, sc>>>(dc, bd);
     } else {
-      if (rec) fast_walk_kernel<false, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
-      else fast_walk_kernel<false, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, ctx->s_comp>>>(dc, bd);
+      if (rec) fast_walk_kernel<false, true><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, sc>>>(dc, bd);
+      else fast_walk_kernel<false, false><<<ctx->fw_blocks, ctx->fw_threads, ctx->fw_smem, sc>>>(dc, bd);
     }
     ctx->total_launches++;
   }
-  CK(cudaEventRecord(ev[1], ctx->s_comp));
+  CK(cudaEventRecord(ev[1], sc));
+  cudaStream_t sw = split ? sa : sc;   // where the serial walker runs
+  if (split) { CK(cudaEventRecord(fork_ev, sc)); CK(cudaStreamWaitEvent(sa, fork_ev, 0)); }
   // ---- the exact serial walker (all reads when the fast walk is off, else the reads of slow_list)
-  if (ctx->ref_smem) {
-    if (from_stage == 0) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    CK(cudaEventRecord(ev[2], ctx->s_comp));
-    walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-  } else {
-    if (from_stage == 0) walk_kernel<0, false><<<ctx->walk_blocks[0], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    CK(cudaEventRecord(ev[2], ctx->s_comp));
-    walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+  CK(cudaEventRecord(ev[2], sw));
+  if (from_stage == 0) {
+    if (ctx->ref_smem) walk_kernel<0, true><<<ctx->walk_blocks[0], T, ctx->walk_smem, sw>>>(dc, bd);
+    else walk_kernel<0, false><<<ctx->walk_blocks[0], T, ctx->walk_smem, sw>>>(dc, bd);
   }
-  CK(cudaEventRecord(ev[3], ctx->s_comp));
-  const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
-  cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
-  CK(cudaEventRecord(ev[4], ctx->s_comp));
-  ctx->total_launches += from_stage == 0 ? 3 : 2;
+  CK(cudaEventRecord(ev[3], sw));
+  CK(cudaEventRecord(ev[4], sw));
+  if (ctx->ref_smem) walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, sw>>>(dc, bd);
+  else walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, sw>>>(dc, bd);
+  if (split) cluster_kernel<<<std::min(cgrid, ctx->sm_count), CLUSTER_THREADS, ctx->cluster_smem, sw>>>(dc, bd, 2);
+  CK(cudaEventRecord(ev[5], sw));
+  if (split) CK(cudaEventRecord(join_cl, sa));
+  // ---- clustering of the bulk
+  CK(cudaEventRecord(ev[6], sc));
+  cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, sc>>>(dc, bd, split ? 1 : 0);
+  CK(cudaEventRecord(ev[7], sc));
+  ctx->total_launches += (from_stage == 0 ? 3 : 2) + (split ? 1 : 0);
+  // ---- coverage of the serial walker's reads (needs their clusters: after cluster_kernel<2> on its own stream)
+  CK(cudaEventRecord(ev[8], sw));
   if (dc.record_depth) {
-    if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    else walk_kernel<1, false><<<ctx->walk_blocks[1], T, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], T, ctx->walk_smem, sw>>>(dc, bd);
+    else walk_kernel<1, false><<<ctx->walk_blocks[1], T, ctx->walk_smem, sw>>>(dc, bd);
     ctx->total_launches++;
   }
-  CK(cudaEventRecord(ev[5], ctx->s_comp));
+  CK(cudaEventRecord(ev[9], sw));
+  if (split) CK(cudaEventRecord(join_cov, sa));
+  // ---- coverage of the fast reads: key = (coverage row, source) -> radix sort -> positional popcount per group
+  CK(cudaEventRecord(ev[10], sc));
   if (dc.record_depth && bd.fast) {
-    // coverage of the fast reads: key = (coverage row, source) -> radix sort -> positional popcount per group
     const int kgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + 255) / 256, (long long)ctx->sm_count * 16));
-    cov_key_kernel<<<kgrid, 256, 0, ctx->s_comp>>>(dc, bd, B.k_in, B.v_in, ctx->acc_pos_shift);
+    cov_key_kernel<<<kgrid, 256, 0, sc>>>(dc, bd, B.k_in, B.v_in, ctx->acc_pos_shift);
     size_t tmp = B.cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(B.cub_tmp, tmp, B.k_in, B.k_out, B.v_in, B.v_out, (int)bd.n, 0, B.key_bits, ctx->s_comp));
-    accumulate_kernel<<<ctx->acc_blocks, ACC_THREADS, sizeof(AccSmem), ctx->s_comp>>>(dc, bd, B.k_out, B.v_out, bd.bctr + 6);
+    CK(cub::DeviceRadixSort::SortPairs(B.cub_tmp, tmp, B.k_in, B.k_out, B.v_in, B.v_out, (int)bd.n, 0, B.key_bits, sc));
+    accumulate_kernel<<<ctx->acc_blocks, ACC_THREADS, sizeof(AccSmem), sc>>>(dc, bd, B.k_out, B.v_out, bd.bctr + 6);
     ctx->total_launches += 2 + (B.key_bits + 7) / 8 + 1;
   }
-  CK(cudaEventRecord(ev[6], ctx->s_comp));
+  CK(cudaEventRecord(ev[11], sc));
+  if (split) { CK(cudaStreamWaitEvent(sc, join_cl, 0)); CK(cudaStreamWaitEvent(sc, join_cov, 0)); }
   CK(cudaGetLastError());
   return NPT_OK;
 }
@@ -495,8 +526,35 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
   Batch& B = ctx->batches[bi];
   if (B.retired) return NPT_OK;
   CK(cudaEventSynchronize(B.done));
-  unsigned h[8];
+  unsigned h[12];
   CK(cudaMemcpy(h, B.bctr, sizeof h, cudaMemcpyDeviceToHost));
+  if (!h[1] && h[8] && B.d.fast) {
+    // Only the serial walker's reads ran out of overflow area; the bulk (fast walk, its clustering and coverage) is done.
+    // The area keeps what the fast walk stored and grows by what the chain can need at most (h[0] counts every request so
+    // far, failed ones included); then the chain runs again: store-all pass, clustering and coverage of slow_list.
+    const DevCfg& dc = ctx->dc;
+    const unsigned old_cap = B.d.break_cap, new_cap = (unsigned)std::min<unsigned long long>(2ull * h[0] + 16, 1ull << 31);
+    int* bigger = nullptr;
+    size_t bigger_bytes = 0;
+    CK(pool_get(ctx, (void**)&bigger, ((size_t)B.n * BRK_INLINE + new_cap) * sizeof(int), &bigger_bytes));
+    CK(cudaMemcpyAsync(bigger, B.d.break_arena, ((size_t)B.n * BRK_INLINE + old_cap) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
+    CK(cudaMemsetAsync(B.bctr + 3, 0, 2 * sizeof(unsigned), ctx->s_comp));   // read cursors of walk_kernel<1> and <2>
+    CK(cudaMemsetAsync(B.bctr + 8, 0, sizeof(unsigned), ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    pool_put(ctx, B.d.break_arena, B.arena_bytes);
+    B.d.break_arena = bigger; B.d.break_cap = new_cap; B.arena_bytes = bigger_bytes;
+    const BatchDev& bd = B.d;
+    if (ctx->ref_smem) walk_kernel<2, true><<<ctx->walk_blocks[2], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    else walk_kernel<2, false><<<ctx->walk_blocks[2], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    cluster_kernel<<<ctx->sm_count, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd, 2);
+    if (dc.record_depth) {
+      if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+      else walk_kernel<1, false><<<ctx->walk_blocks[1], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    ctx->total_launches += 3;
+  }
   if (h[1]) {
     // The overflow area for reads with more than BRK_INLINE breaks was too small; cluster_kernel and the coverage pass
     // skipped this batch.  h[0] is the exact need: enlarge and run the batch from the store-all pass on.  Running it
@@ -507,6 +565,7 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
     CK(pool_get(ctx, (void**)&bigger, ((size_t)B.n * BRK_INLINE + need) * sizeof(int), &bigger_bytes));
     CK(cudaMemcpyAsync(bigger, B.d.break_arena, (size_t)B.n * BRK_INLINE * sizeof(int), cudaMemcpyDeviceToDevice, ctx->s_comp));
     CK(cudaMemsetAsync(B.bctr, 0, 7 * sizeof(unsigned), ctx->s_comp));  // [7] = reads in slow_list stays
+    CK(cudaMemsetAsync(B.bctr + 8, 0, sizeof(unsigned), ctx->s_comp));
     CK(cudaStreamSynchronize(ctx->s_comp));
     pool_put(ctx, B.d.break_arena, B.arena_bytes);
     B.d.break_arena = bigger; B.d.break_cap = need; B.arena_bytes = bigger_bytes;
@@ -555,6 +614,8 @@ void free_batches(npt_ctx* ctx) {
   ctx->walk_events.clear();
   for (auto& e : ctx->stage_events) cudaEventDestroy(e);
   ctx->stage_events.clear();
+  for (auto& e : ctx->order_events) cudaEventDestroy(e);
+  ctx->order_events.clear();
 }
 
 }  // namespace
@@ -593,6 +654,7 @@ int npt_create(const npt_config* cfg, npt_ctx** out) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ctx->ev_a));
   CK(cudaEventCreate(&ctx->ev_b));
   CK(cudaEventCreate(&ctx->ev_c0));
@@ -629,6 +691,7 @@ void npt_destroy(npt_ctx* ctx) {
   if (ctx->ev_c1) cudaEventDestroy(ctx->ev_c1);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+  if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
   delete ctx;
 }
 
@@ -729,7 +792,12 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   const int max_cl = cf.max_clusters > 0 ? cf.max_clusters : (1 << 16);
   const int max_sb = cf.max_subclusters > 0 ? cf.max_subclusters : (1 << 21);
   const int max_pr = cf.max_break_pairs > 0 ? cf.max_break_pairs : (1 << 20);
-  const int max_cov = cf.record_depth ? (cf.max_coverage_clusters > 0 ? cf.max_coverage_clusters : 1024) : 0;
+  // dense coverage rows (COV_ARRAYS int32 rows of seqlen + 2 per cluster and source): default = what fits 4 GB, between 256
+  // clusters and max_clusters; the caller may ask for as many as HBM holds (rows are kept zero between chromosomes, so a
+  // large capacity costs memory but no time)
+  const size_t row_bytes = (size_t)COV_ARRAYS * cf.num_sources * ((size_t)ref_len + 2) * 4;
+  const int auto_cov = (int)std::min<size_t>((size_t)max_cl, std::max<size_t>(256, ((size_t)4 << 30) / row_bytes));
+  const int max_cov = cf.record_depth ? (cf.max_coverage_clusters > 0 ? cf.max_coverage_clusters : auto_cov) : 0;
   const unsigned ncl = pow2_at_least(2ull * max_cl), nsb = pow2_at_least(2ull * max_sb), npr = calc_breaks1 ? pow2_at_least(2ull * max_pr) : 1;
   CK(ctx->d_cl.ensure(ncl)); CK(ctx->d_sb.ensure(nsb)); CK(ctx->d_pr.ensure(npr));
   dc.cl = ctx->d_cl.p; dc.cl_mask = ncl - 1; dc.cl_cap = max_cl;
@@ -753,9 +821,13 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   CK(cudaMemsetAsync(ctx->d_sub_sums.p, 0, (size_t)std::max<unsigned>(dc.sums_cap, 1) * 8, ctx->s_comp));
   const size_t cov_elems = (size_t)COV_ARRAYS * max_cov * dc.S * dc.stride;
   if (cf.record_depth) {
+    const bool fresh = ctx->d_cov.cap < cov_elems;
     cudaError_t e = ctx->d_cov.ensure(cov_elems);
     if (e != cudaSuccess) return fail(ctx, NPT_ENOMEM, "coverage rows: %zu bytes for %d clusters (lower max_coverage_clusters)", cov_elems * 4, max_cov);
-    CK(cudaMemsetAsync(ctx->d_cov.p, 0, cov_elems * 4, ctx->s_comp));
+    // every row is zero when a chromosome begins: npt_end_chrom clears the rows it used; only a new allocation, or a
+    // chromosome that did not reach the end of npt_end_chrom, is cleared as a whole
+    if (fresh || ctx->cov_dirty) CK(cudaMemsetAsync(ctx->d_cov.p, 0, ctx->d_cov.cap * 4, ctx->s_comp));
+    ctx->cov_dirty = true;
   }
   dc.cov = ctx->d_cov.p; dc.cov_cap = max_cov;
   const int nsmall = dc.S * (1 + 2 * dc.n_orf);
@@ -775,6 +847,7 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
   if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
   CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  if (const char* e = getenv("NPT_SPLIT")) ctx->split_streams = atoi(e) != 0;
   {
     // persistent grids: resident blocks per SM from the occupancy API (NPT_WALK_BLOCKS_PER_SM overrides, for experiments)
     const char* env = getenv("NPT_WALK_BLOCKS_PER_SM");
@@ -966,12 +1039,12 @@ static int submit_impl(npt_ctx* ctx, const npt_batch* b, const npt_packed_batch*
   const double per_read = std::max<double>(ctx->cfg.coronavirus ? 0.25 : 24.0, 1.25 * ctx->brk_per_read);
   d.break_cap = (unsigned)std::min<int64_t>(std::max<int64_t>((int64_t)(n * per_read), 4096), 1LL << 30);
   CK(pool_get(ctx, (void**)&d.break_arena, ((size_t)n * BRK_INLINE + d.break_cap) * sizeof(int), &B.arena_bytes));
-  CK(pool_get(ctx, (void**)&B.bctr, 8 * sizeof(unsigned), &B.bctr_bytes));
-  CK(cudaMemsetAsync(B.bctr, 0, 8 * sizeof(unsigned), ctx->s_comp));
+  CK(pool_get(ctx, (void**)&B.bctr, 12 * sizeof(unsigned), &B.bctr_bytes));
+  CK(cudaMemsetAsync(B.bctr, 0, 12 * sizeof(unsigned), ctx->s_comp));
   d.bctr = B.bctr;
   // fast walk: work list of the serial walker; with depth recording also headers, the entry arena (16 bytes per 32 reference
   // positions a read covers: its share is (bytes of bases / 16) + 8 entries) and the sort buffers
-  d.fast = ctx->fast ? 1 : 0;
+  d.fast = ctx->fast ? (ctx->split_streams ? 2 : 1) : 0;   // 2: the serial walker's chain runs on the second stream
   if (d.fast && ((uint64_t)d.seq_bytes >> 4) + 2 >= (1ull << 32)) d.fast = 0;  // the walk names 16-byte chunks of the bases with 32 bits
   if (d.fast && ctx->fast_record && ((uint64_t)d.seq_bytes >> 4) + 8ull * (uint64_t)n + 8 >= (1ull << 32)) d.fast = 0;  // entry index is 32 bits
   if (d.fast) {
@@ -1045,9 +1118,12 @@ static int coverage_rows(npt_ctx* ctx, const int* d_row_of_prov, int n_rows) {
   if (n_prov > 0) {
     coverage_rows_kernel<<<4 * n_prov * dc.S, SCAN_THREADS, 0, ctx->s_comp>>>(dc.cov, dc.cov_cap, n_prov, dc.S, dc.stride, d_row_of_prov, n_rows,
                                                                             ctx->d_cov_out.p);
-    ctx->total_launches++;
+    clear_rows_kernel<<<dim3((unsigned)(((size_t)n_prov * dc.S * dc.stride + 1023) / 1024), COV_ARRAYS), 256, 0, ctx->s_comp>>>(
+        dc.cov, (size_t)dc.cov_cap * dc.S * dc.stride, (size_t)n_prov * dc.S * dc.stride);
+    ctx->total_launches += 2;
     CK(cudaGetLastError());
   }
+  ctx->cov_dirty = false;   // the rows this chromosome used are zero again
   ctx->cov_rows = n_rows;
   return NPT_OK;
 }
@@ -1062,8 +1138,8 @@ int npt_end_chrom(npt_ctx* ctx) {
   ctx->walk_ms = 0;
   for (auto& e : ctx->walk_events) { float ms = 0; CK(cudaEventElapsedTime(&ms, e.first, e.second)); ctx->walk_ms += ms; }
   for (int k = 0; k < 6; k++) ctx->stage_ms[k] = 0;
-  for (size_t i = 0; i + 7 <= ctx->stage_events.size(); i += 7)
-    for (int k = 0; k < 6; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->stage_events[i + k], ctx->stage_events[i + k + 1])); ctx->stage_ms[k] += ms; }
+  for (size_t i = 0; i + 12 <= ctx->stage_events.size(); i += 12)
+    for (int k = 0; k < 6; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->stage_events[i + 2 * k], ctx->stage_events[i + 2 * k + 1])); ctx->stage_ms[k] += ms; }
   CK(cudaMemcpy(ctx->h_counters, ctx->d_counters.p, sizeof ctx->h_counters, cudaMemcpyDeviceToHost));
   const unsigned er = ctx->h_counters[CN_ERROR];
   if (er) {

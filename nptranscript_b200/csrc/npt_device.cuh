@@ -89,7 +89,8 @@ struct BatchDev {
   int* break_arena;     // [n][BRK_INLINE] inline slots, then break_cap ints of overflow area
   unsigned break_cap;
   unsigned* bctr;       // per batch: [0] overflow-area cursor, [1] overflow-area full flag, [2..4] read cursors of walk_kernel<0/1/2>,
-                        // [5] read cursor of fast_walk_kernel, [6] tile cursor of accumulate_kernel, [7] reads in slow_list
+                        // [5] read cursor of fast_walk_kernel, [6] tile cursor of accumulate_kernel, [7] reads in slow_list,
+                        // [8] overflow-area full flag of the serial walker's chain when it runs beside a fast walk (12 words)
   // fast walk (fastwalk.cuh): when `fast` is set every read is first offered to fast_walk_kernel and only the reads it lists
   // in slow_list are walked by walk_kernel<0/1/2>
   int fast;

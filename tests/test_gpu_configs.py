@@ -60,3 +60,30 @@ def test_config5_host_chromosome(chrom):
     ora = oracle.run(oracle.make_config(**kw), g, c.annotation, bs, c.index)
     assert_same(dev, ora)
     assert dev["n_clusters"] > 10
+
+
+def test_many_clusters_default_coverage_capacity_and_reuse():
+    """bin=1 on fuzzed reads: thousands of clusters with coverage rows.  The default capacity (what fits 4 GB, here the
+    whole cluster table) holds them; the second chromosome on the same context finds the rows zero again (they are cleared
+    after use at end of chromosome instead of memset per chromosome); an explicit small capacity is an error, not a drop"""
+    from tests.fuzz import random_batch
+    g = synth.genome_codes(workloads.SARS2)[:6000].copy()
+    ann = workloads.Annotation.empty()   # host mode: coordinate keys, one cluster per distinct (start, end) pair at bin=1
+    kw = dict(bin=1, break_thresh=30, coronavirus=0, include_start=1, record_depth=1, num_sources=2, rna=[1, 1])
+    e = engine.Engine(engine.make_config(**kw))
+    try:
+        for seed, n in ((1, 6000), (2, 4000)):
+            b = random_batch(np.random.default_rng(seed), n, len(g), g, num_sources=2, weird=0.0, max_ops=12, big_n=400)
+            e.begin_chrom(3, g, ann)
+            e.submit(b)
+            e.end_chrom()
+            dev = e.fetch()
+            e.release()
+            ora = oracle.run(oracle.make_config(**kw), g, ann, [b], 3)
+            assert_same(dev, ora)
+            assert dev["n_clusters"] > 2000
+    finally:
+        e.close()
+    with pytest.raises(engine.NptError) as err:
+        engine.run(engine.make_config(**dict(kw, max_coverage_clusters=256)), g, ann, [b], 3)
+    assert err.value.code == -5 and "coverage rows" in str(err.value)

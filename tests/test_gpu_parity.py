@@ -184,13 +184,16 @@ def test_small_tables_report_capacity():
     assert e.value.code == abi.NPT_ECAPACITY
 
 
-def test_many_breaks_overflow_area():
-    """Reads with > BRK_INLINE breaks exercise the overflow area and its exact re-emit pass."""
+@pytest.mark.parametrize("depth", [0, 1])
+def test_many_breaks_overflow_area(depth):
+    """Reads with > BRK_INLINE breaks exercise the overflow area and both of its re-run paths: without depth recording the
+    fast walk stores the long lists itself and finds the area too small (whole batch redone from the store-all pass); with
+    depth recording those reads go to the serial walker, whose chain alone is redone beside the finished bulk."""
     w = workloads.SARS2
     g = synth.genome_codes(w)
     rng = np.random.default_rng(5)
     bs = [random_batch(rng, 6000, w.genome_len, g, big_n=400, max_ops=120)]
-    dev, ora = _both(dict(bin=10, break_thresh=100, record_depth=0), w, bs)
+    dev, ora = _both(dict(bin=10, break_thresh=100, record_depth=depth), w, bs)
     nb = np.diff(ora["break_off"].astype(np.int64))
     assert (nb > 6).sum() > 1500
     assert_same(dev, ora)

@@ -1,0 +1,107 @@
+"""Cluster-level writers (nptranscript_b200/writers.py): Java map iteration orders against hand-derived cases and the oracle's
+independent HashSet restatement; rows of 0.genes / 0.transcripts / 0.transcripts.fc built from oracle results (the same
+dict layout the device returns) against the invariants CigarClusters.process1 implies; files written and read back."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from nptranscript_b200 import engine, synth, workloads, writers
+from oracle import oracle, py_oracle
+
+
+def test_hashmap_order_matches_the_oracles_hashset_restatement():
+    rng = np.random.default_rng(3)
+    for trial in range(30):
+        n = int(rng.integers(1, 200))
+        names = list(dict.fromkeys("".join(chr(int(c)) for c in rng.integers(65, 91, int(rng.integers(1, 4)))) for _ in range(n)))
+        want = py_oracle.java_hashset_order(names)
+        if want is None:
+            continue
+        got = [names[i] for i in writers.hashmap_order([writers.java_string_hash(x) for x in names])]
+        assert got == want
+
+
+def test_map_orders_hand_derived():
+    # three keys in bucket 1 of a 16-table: A (hash 1), B (33), C (17); nine fillers make 12 entries
+    hashes = [1, 33, 17] + list(range(2, 11))
+    # HashMap: no resize before the 13th entry -> bucket order, chains in insertion order
+    assert writers.hashmap_order(hashes) == [0, 1, 2] + list(range(3, 12))
+    # ConcurrentHashMap: the 12th put reaches sizeCtl = 12 -> transfer to 32.  Bucket 1 = A, B (bit 16 clear), C (set): lastRun = C,
+    # A and B are PREPENDED to the low list -> B, A; C moves to bucket 17
+    assert writers.concurrent_hashmap_order(hashes) == [1, 0] + list(range(3, 12)) + [2]
+    # a 13th entry doubles the HashMap too; its split keeps the chain order: A, B stay, C moves
+    assert writers.hashmap_order(hashes + [11]) == [0, 1] + list(range(3, 13)) + [2]
+    # nine keys in one bucket of a small table: HashMap doubles once per append from the 9th on, ConcurrentHashMap presizes 16 -> 128
+    same = [5 + 1024 * k for k in range(9)]
+    assert sorted(writers.hashmap_order(same)) == list(range(9))
+    assert sorted(writers.concurrent_hashmap_order(same)) == list(range(9))
+    with pytest.raises(writers.TreeBinNotRestated):
+        writers.hashmap_order([7] * 11)   # equal hashCodes ("Aa" / "BB" ...): the 9th and 10th double the table to 64, the 11th treeifies
+    assert writers.java_string_hash("leader_N") == (sum(ord(c) * 31 ** (7 - i) for i, c in enumerate("leader_N")) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert writers.java_list_hash([0, 282, 298]) == ((((31 + 0) * 31 + 282) * 31 + 298) + 2 ** 31) % 2 ** 32 - 2 ** 31
+
+
+def _report(n=4000, S=2, depth=0, fit=0):
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    b = synth.generate(w, 11, n, num_sources=S)
+    kw = dict(bin=100, break_thresh=1000, record_depth=depth, num_sources=S, track_break_sums=1, first_is_transcriptome=fit)
+    res = oracle.run(oracle.make_config(**kw), g, w.annotation, [b])
+    names = [f"read{i}" for i in range(n)]
+    rep = writers.ChromosomeReport(res, w.annotation, "MT007544.1", 0, engine.make_config(**kw), w.genome_len, src=b.src, read_names=names,
+                                   source_names=[f"s{i}.bam" for i in range(S)])
+    return rep, res, b
+
+
+def test_rows_follow_process1():
+    rep, res, b = _report()
+    genes, trans, fc = rep.rows()
+    nc, ns = res["n_clusters"], res["n_subs"]
+    assert len(genes) == nc == len(fc) and len(trans) == ns
+    gcols = [x.split("\t") for x in genes]
+    assert all(len(x) == 13 + rep.S for x in gcols)
+    # coronavirus mode: clusters by descending read count (stable), every id once
+    tot = [int(x[12]) for x in gcols]
+    assert tot == sorted(tot, reverse=True) and sum(tot) == int((res["cluster_id"] >= 0).sum())
+    assert sorted(x[0] for x in gcols) == sorted(f"ID0.{c}" for c in range(nc))
+    assert all(x[11] == "-1" and x[9] == "-" and x[10] == "0" for x in gcols)      # totLen before writeDepthH5, empty span
+    keys = rep.keys
+    assert [x[8] for x in gcols] == [keys[int(x[0].split(".")[1])] for x in gcols]
+    # the most frequent cluster is the canonical leader -> N junction and has a leader break
+    top = gcols[0]
+    assert top[8].startswith("leader_leader,N_") and top[7] == "1" and top[4] == "5_3"
+    tcols = [x.split("\t") for x in trans]
+    assert all(len(x) == 13 + rep.S and x[0] == x[9] and x[6] == "1" and x[11] == "NA" for x in tcols)
+    assert sum(int(x[12]) for x in tcols) == sum(tot)
+    # transcripts of a cluster are contiguous and in the order of the cluster rows
+    owner = [x[0].rsplit(".t", 1)[0] for x in tcols]
+    assert [o for i, o in enumerate(owner) if i == 0 or owner[i - 1] != o] == [x[0] for x in gcols]
+    # consensus start <= end, exon count = round(breaks / 2)
+    assert all(int(x[2]) <= int(x[3]) for x in tcols)
+    # feature counts: Start/End lists pair up, Length = sum of block lengths of the best-supported transcript
+    for x in (y.split("\t") for y in fc):
+        st, en = [int(v) for v in x[2].split(";")], [int(v) for v in x[3].split(";")]
+        assert len(st) == len(en) == len(x[1].split(";")) and int(x[5]) == sum(e - s for s, e in zip(st, en))
+
+
+def test_first_is_transcriptome_names_and_files(tmp_path):
+    rep, res, b = _report(n=1500, depth=1, fit=1)
+    names = rep.sub_names_final()
+    so = res["cl_sub_off"].astype(np.int64)
+    g = so[np.maximum(res["cluster_id"], 0)] + res["sub_id"]
+    for s in range(res["n_subs"]):
+        hits = np.flatnonzero((res["cluster_id"] >= 0) & (g == s) & (b.src == 0))
+        assert names[s] == (f"read{hits[-1]}" if len(hits) else names[s]) and (len(hits) > 0 or ".t" in names[s])
+    paths = rep.write(str(tmp_path), polya=33)
+    base = {os.path.basename(p) for p in paths}
+    assert {"0transcripts.txt.gz", "0genes.txt.gz", "0transcripts.fc.txt.gz", "0annot.txt.gz", "0readToCluster.txt.gz"} <= base
+    assert any(x.startswith("0.breakpoints.s0.bam.0") for x in base) and any(x.startswith("0.clusters.depth.") for x in base)
+    with gzip.open(tmp_path / "0genes.txt.gz", "rt") as f:
+        lines = f.read().splitlines()
+    assert lines[0] == "#s0.bam\ts1.bam\t" and lines[1].startswith("ID\tchrom\tstart\tend\ttype_nme") and len(lines) == 2 + res["n_clusters"]
+    with gzip.open(tmp_path / "0annot.txt.gz", "rt") as f:
+        assert f.read().splitlines()[-1].split("\t")[:3] == ["3UTR", "29675", "29860"]     # the reference-held 0.annot.tsv row
+    with gzip.open(tmp_path / "0readToCluster.txt.gz", "rt") as f:
+        assert len(f.read().splitlines()) == 1 + int((res["read_flags"] & 0x10 == 0).sum())
