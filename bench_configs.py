@@ -41,7 +41,9 @@ def _plan(no, rank, world, args):
         per = args.reads or 5_000_000
         fixed = rank if world == 8 else -1
         P.update(name="configs[2] 229E, 8 source BAMs combined, %d reads per GPU (%s)" % (per, "GPU k holds BAM k" if world == 8 else "sources alternate"),
-                 cfg_kw=dict(bin=10, break_thresh=1000, record_depth=1, calc_breaks=1, track_break_sums=1, num_sources=8, max_coverage_clusters=1024),
+                 # bin 10 on 40 M reads: millions of sub-clusters and break-point pairs once every rank holds every rank's keys
+                 cfg_kw=dict(bin=10, break_thresh=1000, record_depth=1, calc_breaks=1, track_break_sums=1, num_sources=8, max_coverage_clusters=1024,
+                             max_subclusters=1 << 23, max_break_pairs=1 << 23),
                  chroms=[dict(index=0, genome=synth.genome_codes(w), annotation=w.annotation, n=per, first=rank * per,
                               gen=lambda n, first, alloc=None: synth.generate(w, 20200310, n, first_index=first, num_sources=8, src_fixed=fixed, alloc=alloc))])
     elif no == 4:

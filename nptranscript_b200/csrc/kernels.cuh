@@ -663,7 +663,8 @@ constexpr int CLUSTER_THREADS = 128;
 #endif
 // which = 0: every read of the batch; 1: the reads the fast walk finished (the serial walker may still be writing the
 // others: only their SLOWPATH bit is looked at); 2: the reads of slow_list.  1 and 2 run concurrently on two streams.
-__global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) cluster_kernel(const DevCfg c, const BatchDev b, const int which) {
+template <int which>
+__global__ void __launch_bounds__(CLUSTER_THREADS, NPT_CLUSTER_MIN_BLOCKS) cluster_kernel(const DevCfg c, const BatchDev b) {
   extern __shared__ __align__(16) int s_int[];
   if (ldcg(b.bctr + 1)) return;  // break lists incomplete (overflow area too small): the host re-runs this batch
   if (which == 2 && ldcg(b.bctr + 8)) return;

@@ -108,6 +108,7 @@ struct npt_ctx {
   DBuf<unsigned long long> d_sub_sums, d_sub_min0;
   int walk_blocks[3] = {0, 0, 0};   // grid sizes of walk_kernel<0/1/2>
   size_t walk_smem = 0, cluster_smem = 0;
+  int cluster_occ = 8, covkey_occ = 6;   // resident cluster_kernel / cov_key_kernel blocks per SM
   // fast walk (fastwalk.cuh / fastcov.cuh)
   DBuf<uint32_t> d_refg;
   bool fast = false, fast_record = false;
@@ -138,7 +139,8 @@ struct npt_ctx {
   int64_t n_pairs = 0;
   int64_t n_total = 0;
   int64_t n_slow = 0;            // reads the fast walk handed to the serial walker (this chromosome)
-  bool split_streams = false;
+  bool split_streams = true;
+  float slow_share = 0;          // reads of the last retired batch that went to the serial walker, as a share of the batch
   bool cov_dirty = true;         // d_cov may hold counts (fresh allocation, or a chromosome that was not finished)
   float brk_per_read = 0;        // largest overflow need (ints per read) of a retired batch of this chromosome
   long long total_breaks = 0;
@@ -448,13 +450,16 @@ int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
   CK(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&join_cl, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&join_cov, cudaEventDisableTiming));
   ctx->order_events.push_back(fork_ev); ctx->order_events.push_back(join_cl); ctx->order_events.push_back(join_cov);
-  const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, (long long)ctx->sm_count * 16));
+  // exactly two waves of resident blocks (grid-stride loop inside): a grid that is not a multiple of what fits the device ends
+  // in a part-filled last wave (2 368 blocks at 7 instead of 8 blocks per SM cost 1.5x, r02i); one wave alone is 15 % slower
+  // than two (5.4 against 4.7 ms per 10 M reads: the second wave evens out the per-read differences)
+  const int cgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + CLUSTER_THREADS - 1) / CLUSTER_THREADS, 2ll * ctx->sm_count * ctx->cluster_occ));
   // ---- the fast walk: every read it can restate exactly (breaks, read offsets, coverage entries); the others go to slow_list
   CK(cudaEventRecord(ev[0], sc));
-  // NPT_SPLIT=1 (experiment, off by default): the serial walker's few reads run beside the bulk on a second stream.  Measured
-  // slower (13.7 against 11.9 ms per 4 M reads, profiles/NOTES.md): the walk kernels need the largest shared-memory carve-out,
-  // cluster_kernel the smallest, and an SM only changes it when idle, so the two chains wait for each other.
-  const bool split = bd.fast && from_stage == 0 && ctx->split_streams;
+  // The serial walker's few reads (walk<0>, walk<2>, their clustering, walk<1>) run beside the bulk on a second stream: each
+  // is one long dependent chain in a handful of warps (0.65 + 0.9 ms per batch whatever its size), hidden behind
+  // cluster_kernel and the coverage stage (-1.1 ms per 10 M reads; NPT_SPLIT=0 puts everything on one stream).
+  const bool split = bd.fast == 2 && from_stage == 0;
   if (bd.fast && from_stage == 0) {
     const bool rec = ctx->fast_record;
     if (ctx->ref_smem) {
@@ -479,12 +484,13 @@ int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
   CK(cudaEventRecord(ev[4], sw));
   if (ctx->ref_smem) walk_kernel<2, true><<<ctx->walk_blocks[2], T, ctx->walk_smem, sw>>>(dc, bd);
   else walk_kernel<2, false><<<ctx->walk_blocks[2], T, ctx->walk_smem, sw>>>(dc, bd);
-  if (split) cluster_kernel<<<std::min(cgrid, ctx->sm_count), CLUSTER_THREADS, ctx->cluster_smem, sw>>>(dc, bd, 2);
+  if (split) cluster_kernel<2><<<std::min(cgrid, ctx->sm_count), CLUSTER_THREADS, ctx->cluster_smem, sw>>>(dc, bd);
   CK(cudaEventRecord(ev[5], sw));
   if (split) CK(cudaEventRecord(join_cl, sa));
   // ---- clustering of the bulk
   CK(cudaEventRecord(ev[6], sc));
-  cluster_kernel<<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, sc>>>(dc, bd, split ? 1 : 0);
+  if (split) cluster_kernel<1><<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, sc>>>(dc, bd);
+  else cluster_kernel<0><<<cgrid, CLUSTER_THREADS, ctx->cluster_smem, sc>>>(dc, bd);
   CK(cudaEventRecord(ev[7], sc));
   ctx->total_launches += (from_stage == 0 ? 3 : 2) + (split ? 1 : 0);
   // ---- coverage of the serial walker's reads (needs their clusters: after cluster_kernel<2> on its own stream)
@@ -499,7 +505,7 @@ int launch_batch(npt_ctx* ctx, const Batch& B, int from_stage) {
   // ---- coverage of the fast reads: key = (coverage row, source) -> radix sort -> positional popcount per group
   CK(cudaEventRecord(ev[10], sc));
   if (dc.record_depth && bd.fast) {
-    const int kgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + 255) / 256, (long long)ctx->sm_count * 16));
+    const int kgrid = (int)std::max<long long>(1, std::min<long long>((bd.n + 255) / 256, (long long)ctx->sm_count * ctx->covkey_occ));
     cov_key_kernel<<<kgrid, 256, 0, sc>>>(dc, bd, B.k_in, B.v_in, ctx->acc_pos_shift);
     size_t tmp = B.cub_bytes;
     CK(cub::DeviceRadixSort::SortPairs(B.cub_tmp, tmp, B.k_in, B.k_out, B.v_in, B.v_out, (int)bd.n, 0, B.key_bits, sc));
@@ -546,7 +552,7 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
     const BatchDev& bd = B.d;
     if (ctx->ref_smem) walk_kernel<2, true><<<ctx->walk_blocks[2], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
     else walk_kernel<2, false><<<ctx->walk_blocks[2], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
-    cluster_kernel<<<ctx->sm_count, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd, 2);
+    cluster_kernel<2><<<ctx->sm_count, CLUSTER_THREADS, ctx->cluster_smem, ctx->s_comp>>>(dc, bd);
     if (dc.record_depth) {
       if (ctx->ref_smem) walk_kernel<1, true><<<ctx->walk_blocks[1], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
       else walk_kernel<1, false><<<ctx->walk_blocks[1], WALK_THREADS, ctx->walk_smem, ctx->s_comp>>>(dc, bd);
@@ -578,7 +584,7 @@ int retire_batch(npt_ctx* ctx, size_t bi) {
   }
   release_scratch(ctx, B);
   if (B.staging >= 0) { ctx->stg[B.staging].busy = false; ctx->stg[B.staging].batch_index = -1; }
-  if (B.d.fast) ctx->n_slow += h[7];
+  if (B.d.fast) { ctx->n_slow += h[7]; ctx->slow_share = (float)((double)h[7] / (double)std::max<int64_t>(B.n, 1)); }
   // overflow ints per read this batch needed: the next batches of the chromosome reserve that much (plus a quarter)
   ctx->brk_per_read = std::max(ctx->brk_per_read, (float)((double)h[0] / (double)std::max<int64_t>(B.n, 1)));
   B.retired = true;
@@ -846,7 +852,16 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   ctx->walk_smem = (ctx->ref_smem ? (size_t)((nwords + 3) & ~3) * 4 : 0) + (size_t)(WALK_THREADS / 32) * 2 * 32 * TILE_STRIDE * 4 + 36 * 4;
   ctx->cluster_smem = (size_t)dc.n_orf * 12 + (size_t)dc.S * (1 + 2 * dc.n_orf) * 4 + 16;
   if (ctx->cluster_smem > ctx->smem_optin) return fail(ctx, NPT_EINVAL, "annotation too large for shared memory (%zu bytes)", ctx->cluster_smem);
-  CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  CK(cudaFuncSetAttribute(cluster_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  CK(cudaFuncSetAttribute(cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  CK(cudaFuncSetAttribute(cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+  {
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cluster_kernel<0>, CLUSTER_THREADS, ctx->cluster_smem));
+    ctx->cluster_occ = std::max(1, occ);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_key_kernel, 256, 0));
+    ctx->covkey_occ = std::max(1, occ);
+  }
   if (const char* e = getenv("NPT_SPLIT")) ctx->split_streams = atoi(e) != 0;
   {
     // persistent grids: resident blocks per SM from the occupancy API (NPT_WALK_BLOCKS_PER_SM overrides, for experiments)
@@ -1044,7 +1059,10 @@ static int submit_impl(npt_ctx* ctx, const npt_batch* b, const npt_packed_batch*
   d.bctr = B.bctr;
   // fast walk: work list of the serial walker; with depth recording also headers, the entry arena (16 bytes per 32 reference
   // positions a read covers: its share is (bytes of bases / 16) + 8 entries) and the sort buffers
-  d.fast = ctx->fast ? (ctx->split_streams ? 2 : 1) : 0;   // 2: the serial walker's chain runs on the second stream
+  // 2: the serial walker's chain runs on the second stream — worth it while that chain is a few reads (latency of one warp);
+  // with many of them (host mode: 1 % of the reads have more junctions than the fast walk keeps) the two streams only get in
+  // each other's way (98.7 -> 106.8 ms on the host-mode bench), so the last retired batch's share decides
+  d.fast = ctx->fast ? ((ctx->split_streams && ctx->slow_share < 5e-4f) ? 2 : 1) : 0;
   if (d.fast && ((uint64_t)d.seq_bytes >> 4) + 2 >= (1ull << 32)) d.fast = 0;  // the walk names 16-byte chunks of the bases with 32 bits
   if (d.fast && ctx->fast_record && ((uint64_t)d.seq_bytes >> 4) + 8ull * (uint64_t)n + 8 >= (1ull << 32)) d.fast = 0;  // entry index is 32 bits
   if (d.fast) {

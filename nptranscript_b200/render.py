@@ -111,9 +111,10 @@ def sub_names(res, src, read_names, chrom_index, first_is_transcriptome=False):
     return [read_names[int(j)] if (j >= 0 and c >= 0) else b for j, b, c in zip(last0, base, cl)]
 
 
-def read_to_cluster_rows(res, read_names, annotation, chrom_name, chrom_index, record_depth, qvals=None, coronavirus=True):
+def read_to_cluster_rows(res, read_names, annotation, chrom_name, chrom_index, record_depth, qvals=None, coronavirus=True, spans=None):
     """Rows of 0.readToCluster.txt.gz exactly as IdentityProfile1.commit builds them (:133-136); header Outputs.java:313-318.
-    span columns are "." / 0 for CSV and empty annotations (Annotation.getSpan :252-255)."""
+    span columns are "." / 0 for CSV and empty annotations (Annotation.getSpan :252-255); GFF mode passes spans = per-read
+    (span string, number of genes) from writers.gff_span."""
     keys = cluster_keys(res, annotation, chrom_index, coronavirus)
     rows = []
     bo = res["break_off"]
@@ -137,7 +138,7 @@ def read_to_cluster_rows(res, read_names, annotation, chrom_name, chrom_index, r
         rows.append("\t".join([read_names[i], cluster_id(chrom_index, c), sub_id(chrom_index, c, k), str(int(res.get("src", np.zeros(res["n_reads"], int))[i])),
                                str(en_r - st_r), str(st_r), str(en_r), type_nme, chrom_name, str(int(res["start_pos"][i])),
                                str(int(res["end_pos"][i])), strand, "0", "1" if fl & abi.NPT_RF_LEADER else "0", err, keys[c], strand, breaks,
-                               ".", "0", q]))
+                               spans[i][0] if spans is not None else ".", str(spans[i][1]) if spans is not None else "0", q]))
     return rows
 
 

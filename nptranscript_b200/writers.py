@@ -130,12 +130,46 @@ def _java_round(x):
     return int(math.floor(x + 0.5))
 
 
+def gff_span(breaks, forward, annotation, enforce_strand=False, tolerance1=5):
+    """GFFAnnotation.getSpan (J/cluster/GFFAnnotation.java:219-292) for one read: which genes explain its breaks.
+    Returns (span string, exon rows hit = what the call adds to CigarCluster.span, gene names in SortedSet order).
+    Rows are the exon lines in file order; the greedy cover walks the HashMap<String, Set<Integer>> entries in iteration order,
+    stably sorted by descending set size, and unions them into the FIRST entry's set until it holds every break that lies in
+    an exon (the reference mutates that set; the count of genes taken is what matters)."""
+    n = len(annotation.genes)
+    ok = (lambda i: True) if not enforce_strand else (lambda i: bool(forward) == bool(annotation.strand[i]))
+    start_, end_ = int(breaks[0]), int(breaks[-1])
+    istart = next((i for i in range(n) if ok(i) and annotation.end[i] > start_ - tolerance1), -1)
+    iend = next((i for i in range(n - 1, -1, -1) if ok(i) and annotation.start[i] < end_ + tolerance1), -1)
+    if not (istart >= 0 and iend >= 0 and istart <= iend):
+        return ".", [], []
+    m, order, rows, in_exons = {}, [], [], set()
+    for i in range(istart, iend + 1):
+        for j, pos in enumerate(breaks):
+            if annotation.start[i] <= pos + tolerance1 and annotation.end[i] >= pos - tolerance1:
+                g = annotation.genes[i]
+                if g not in m:
+                    m[g] = set(); order.append(g)
+                m[g].add(j); rows.append(i); in_exons.add(j)
+    names = set()
+    if m:
+        it = [order[k] for k in hashmap_order([java_string_hash(g) for g in order])]   # entrySet() order
+        vals = sorted(it, key=lambda g: -len(m[g]))                                   # Collections.sort is stable
+        cover = m[vals[0]]
+        names.add(vals[0])
+        k = 0
+        while len(cover) < len(in_exons):
+            k += 1
+            cover |= m[vals[k]]
+            names.add(vals[k])
+    gl = sorted(names)   # TreeSet<String>: String.compareTo = UTF-16 code unit order = Python's order for BMP text
+    return ";".join(gl), sorted(set(rows)), gl
+
+
 class ChromosomeReport:
     """Everything process1 prints for one chromosome, from one npt_results (tables + per-read arrays)."""
 
     def __init__(self, res, annotation, chrom_name, chrom_index, cfg, seqlen, src=None, read_names=None, source_names=None):
-        if annotation.kind == abi.NPT_ANNOT_GFF:
-            raise NotImplementedError("the gene-set span of GFF mode (GFFAnnotation.getSpan) is not built: rows need it for gene_nme / span")
         self.res, self.annotation, self.chrom, self.ci, self.cfg, self.seqlen = res, annotation, chrom_name, chrom_index, cfg, seqlen
         self.S = cfg.num_sources
         self.src, self.read_names = src, read_names
@@ -149,6 +183,28 @@ class ChromosomeReport:
         np.minimum.at(self.start_pos, cl[ok], res["start_pos"][ok])   # CigarCluster.merge :633-634
         np.maximum.at(self.end_pos, cl[ok], res["end_pos"][ok])
         self._sub_name = None
+        # GFF mode: the span of every read (IdentityProfile1.java:333) and of every cluster (CigarCluster.span, merged :640)
+        self.read_span = None
+        self.cluster_span = [set() for _ in range(nc)]
+        if annotation.kind == abi.NPT_ANNOT_GFF:
+            bo = res["break_off"].astype(np.int64)
+            self.read_span = []
+            for i in range(res["n_reads"]):
+                if cl[i] < 0:
+                    self.read_span.append((".", 0)); continue
+                fwd = not (int(res["read_flags"][i]) & abi.NPT_RF_NEG)
+                st, rows, names = gff_span([int(x) for x in res["breaks"][bo[i]:bo[i + 1]]], fwd, annotation, bool(cfg.enforce_strand))
+                self.read_span.append((st, len(names)))
+                self.cluster_span[int(cl[i])].update(rows)
+
+    def _gene_names(self, c):
+        """Annotation.getString(cc.span, geneNames) :257-268: genes of the span's exon rows in row order, ';'-joined (a gene
+        appears once per row), and the number of distinct names."""
+        rows = sorted(self.cluster_span[c])
+        if not rows:
+            return "-", 0
+        g = [self.annotation.genes[i] for i in rows]
+        return ";".join(g), len(set(g))
 
     # ---- ids
     def sub_names_final(self):
@@ -205,7 +261,7 @@ class ChromosomeReport:
             st, en = int(self.start_pos[c]), int(self.end_pos[c])
             type_ind = (0 if en >= self.seqlen - cfg.end_thresh else 1) if st <= cfg.start_thresh else (2 if en >= self.seqlen - cfg.end_thresh else 3)
             type_nme = render.TYPE_NAMES[type_ind]
-            gene_nme, n_gene = "-", 0   # Annotation.getString on the empty span of CSV / empty annotations
+            gene_nme, n_gene = self._gene_names(c)   # "-" / 0 on the empty span of CSV and empty annotations
             read_count = "\t".join(str(int(x)) for x in r["cl_read_count"][c])
             best, best_sum = None, 0
             for s in order:
@@ -272,7 +328,7 @@ class ChromosomeReport:
             head = ("readID\tclusterId\tsubID\tsource\tlength\tstart_read\tend_read\ttype_nme\tchrom\tstartPos\tendPos\tstrand\tnum_breaks\tleader_break\t"
                     "errorRatio\tORFs\tstrand\tbreaks\tspan\tspan_count\tqval")
             gz("readToCluster", [head] + render.read_to_cluster_rows(r, self.read_names, self.annotation, self.chrom, self.ci, bool(self.cfg.record_depth),
-                                                                     coronavirus=bool(self.cfg.coronavirus)))
+                                                                     coronavirus=bool(self.cfg.coronavirus), spans=self.read_span))
         if npy:
             for (s, j), m in render.breakpoint_matrices(self.res, self.S).items():
                 p = os.path.join(resdir, f"{genome_index}.breakpoints.{self.source_names[s]}.{j}.npy")

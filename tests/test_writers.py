@@ -105,3 +105,37 @@ def test_first_is_transcriptome_names_and_files(tmp_path):
         assert f.read().splitlines()[-1].split("\t")[:3] == ["3UTR", "29675", "29860"]     # the reference-held 0.annot.tsv row
     with gzip.open(tmp_path / "0readToCluster.txt.gz", "rt") as f:
         assert len(f.read().splitlines()) == 1 + int((res["read_flags"] & 0x10 == 0).sum())
+
+
+def test_gff_span_hand_cases():
+    A = workloads.Annotation.gff(["g1", "g1", "g2", "g3"], [100, 300, 290, 1000], [200, 400, 420, 1100], [True, True, True, False])
+    # both breaks of the first block lie in g1's first exon, the second block's in g1's second exon and in g2: g1 alone explains all
+    assert writers.gff_span([110, 190, 305, 395], True, A) == ("g1", [0, 1, 2], ["g1"])
+    # the last break only lies in g2's exon (401..420 is outside g1's 300..400 + 5): g1 (3 breaks) first, then g2 to cover the 4th
+    assert writers.gff_span([110, 190, 305, 415], True, A) == ("g1;g2", [0, 1, 2], ["g1", "g2"])
+    # no exon row between the first one that ends after the read's start and the last one that starts before its end -> "."
+    assert writers.gff_span([500, 600], True, A) == (".", [], [])
+    assert writers.gff_span([2000, 2100], True, A) == (".", [], [])
+    # rows out of position order (file order is what counts): the window exists, nothing overlaps -> empty string, not "."
+    B = workloads.Annotation.gff(["g9", "g1"], [900, 100], [1000, 200], [True, True])
+    assert writers.gff_span([500, 600], True, B) == ("", [], [])
+    # enforceStrand: only rows of the read's strand take part
+    assert writers.gff_span([1005, 1095], True, A, enforce_strand=True) == (".", [], [])
+    assert writers.gff_span([1005, 1095], False, A, enforce_strand=True) == ("g3", [3], ["g3"])
+
+
+def test_report_in_gff_mode():
+    c = workloads.human_like()[22]
+    g = synth.host_genome_codes(c)
+    b = synth.generate_host(c, g, 5, 1500, num_sources=2, transcriptome=True)
+    kw = dict(bin=100, break_thresh=50, coronavirus=0, include_start=0, record_depth=0, first_is_transcriptome=1, track_break_sums=1, num_sources=2, rna=[1, 1])
+    res = oracle.run(oracle.make_config(**kw), g, c.annotation, [b], c.index)
+    rep = writers.ChromosomeReport(res, c.annotation, c.name, c.index, engine.make_config(**kw), c.length, src=b.src, read_names=[f"r{i}" for i in range(b.n)])
+    genes, trans, fc = rep.rows()
+    assert len(genes) == res["n_clusters"] and len(trans) == res["n_subs"]
+    # host mode: clusters in ConcurrentHashMap order (no sort by count); spliced reads name their gene
+    named = [x.split("\t") for x in genes if x.split("\t")[9] != "-"]
+    assert len(named) > 0.5 * len(genes) and all(int(x[10]) >= 1 for x in named)
+    assert sum(1 for s, n in rep.read_span if n > 0) > 0.8 * b.n
+    # source-0 reads are the transcripts themselves: their sub-clusters carry a read name as id
+    assert any(not x.split("\t")[0].startswith("ID") for x in trans)
