@@ -17,7 +17,10 @@
 
 namespace npt {
 
-constexpr int FW_WARPS_MAX = 16;
+#ifndef NPT_FW_WARPS
+#define NPT_FW_WARPS 16
+#endif
+constexpr int FW_WARPS_MAX = NPT_FW_WARPS;
 constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE;
 __host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : FW_BRK_BUF * 32); }
 

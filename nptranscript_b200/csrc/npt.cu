@@ -657,15 +657,24 @@ int npt_create(const npt_config* cfg, npt_ctx** out) {
   ctx->device = cfg->device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&ctx->ev_a));
-  CK(cudaEventCreate(&ctx->ev_b));
-  CK(cudaEventCreate(&ctx->ev_c0));
-  CK(cudaEventCreate(&ctx->ev_c1));
-  for (auto& s : ctx->stg) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  auto init = [&]() -> int {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev_a));
+    CK(cudaEventCreate(&ctx->ev_b));
+    CK(cudaEventCreate(&ctx->ev_c0));
+    CK(cudaEventCreate(&ctx->ev_c1));
+    for (auto& s : ctx->stg) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return NPT_OK;
+  };
+  const int rc = init();
+  if (rc) {   // nothing of a half-built context survives; the message moves to where npt_last_error(NULL) finds it
+    g_create_error = ctx->err;
+    npt_destroy(ctx);
+    return rc;
+  }
   *out = ctx;
   return NPT_OK;
 }
@@ -809,8 +818,11 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   dc.cl = ctx->d_cl.p; dc.cl_mask = ncl - 1; dc.cl_cap = max_cl;
   dc.sb = ctx->d_sb.p; dc.sb_mask = nsb - 1; dc.sb_cap = max_sb;
   dc.pr = ctx->d_pr.p; dc.pr_mask = npr - 1; dc.pr_cap = max_pr;
-  dc.tok_cap = (unsigned)std::min<unsigned long long>(24ull * max_cl + (1 << 20), 1ull << 30);   // records incl. lost insertion races
-  dc.sbkey_cap = (unsigned)std::min<unsigned long long>(12ull * max_sb + (1 << 20), 1ull << 30);
+  // record arenas: a thread that loses the race for an empty slot leaks the record it had written, and when a chromosome
+  // starts every resident thread can race for the same hot key at once: the slack covers 16 words for each of them
+  const unsigned long long slack = std::max<unsigned long long>(1ull << 20, 16ull * ctx->sm_count * 2048);
+  dc.tok_cap = (unsigned)std::min<unsigned long long>(24ull * max_cl + slack, 1ull << 30);
+  dc.sbkey_cap = (unsigned)std::min<unsigned long long>(12ull * max_sb + slack, 1ull << 30);
   dc.sums_cap = cf.track_break_sums ? dc.sbkey_cap : 0;
   CK(ctx->d_cl_rec.ensure(dc.tok_cap)); CK(ctx->d_sb_rec.ensure(dc.sbkey_cap));
   CK(ctx->d_sub_count.ensure((size_t)nsb * dc.S)); CK(ctx->d_sub_break_sum.ensure(nsb));

@@ -288,6 +288,68 @@ class ChromosomeReport:
                 fc.append("\t".join([self.keys[c], str(en), str(st), str(en), "+;+", "0", read_count]))
         return genes, trans, fc
 
+    def gff_bed(self, gff_thresh=(1,), max_transcripts=1):
+        """CigarCluster.writeGFF / writeGFF1 / printBed (J/cluster/CigarCluster.java:143-330) for every cluster in getConsensus
+        order: (lines of each GFF writer — one, or two with --firstIsTranscriptome —, lines of each source's BED file).
+        gff_thresh = --gffThresh a[:b], max_transcripts = --maxTranscriptsPerGeneInGFF.  Literal quirks kept: the threshold
+        loop looks at the first `number of writers` sources only; a transcript written by both writers reaches the BED files
+        twice; BED colour is always that of source 0.  The <type>.ref.fa sequences written alongside are not produced."""
+        r, cfg = self.res, self.cfg
+        nw = 2 if cfg.first_is_transcriptome else 1
+        gff = [[] for _ in range(nw)]
+        bed = [[] for _ in range(self.S)]
+        so = r["cl_sub_off"].astype(np.int64)
+        names = self.sub_names_final()
+
+        def line(k, typ, parent, ID, start, end, type_nme, key2, gene_id, strand, counts, breaks):
+            cs = ",".join(str(int(x)) for x in counts)
+            gn = key2.replace(";", "_")
+            gff[k].append(f"{self.chrom}\tnp\t{typ}\t{start}\t{end}\t.\t{strand}\t.\tID={ID}" + (f";Parent={parent}" if parent is not None else "") +
+                          f";gene_id={ID if parent is None else parent};gene_type={type_nme};type=ORF;gene_name={gn};count={cs}")
+            if breaks is None:
+                return
+            for i in range(0, len(breaks) - 1, 2):
+                gff[k].append(f"{self.chrom}\tnp\texon\t{int(breaks[i])}\t{int(breaks[i + 1])}\t.\t{strand}\t.\tID={ID}.e.{i};Parent={ID};gene_id={gene_id};"
+                              f"type=ORF;gene_name={gn};count={cs}")
+            sp, ep = int(breaks[0]) - 1, int(breaks[-1]) - 1
+            sizes = ",".join(str(int(breaks[i + 1]) - int(breaks[i])) for i in range(0, len(breaks) - 1, 2))
+            starts = ",".join(str(int(breaks[i]) - 1 - sp) for i in range(0, len(breaks) - 1, 2))
+            for i in range(self.S):
+                if counts[i] > 0:
+                    bed[i].append(f"{self.chrom}\t{sp}\t{ep}\t{ID}.{gene_id}\t{int(counts[i])}\t{strand}\t{sp}\t{ep}\t0,0,0\t{len(breaks) // 2}\t{sizes}\t{starts}")
+
+        for c in self.cluster_order():
+            st, en = int(self.start_pos[c]), int(self.end_pos[c])
+            type_ind = (0 if en >= self.seqlen - cfg.end_thresh else 1) if st <= cfg.start_thresh else (2 if en >= self.seqlen - cfg.end_thresh else 3)
+            type_nme = render.TYPE_NAMES[type_ind]
+            strand = "-" if r["sub_flags"][so[c]] & 2 else "+"
+            cid = render.cluster_id(self.ci, c)
+            subs = sorted(self.sub_order(c), key=lambda s_: int(r["sub_count"][s_].sum()))   # Collections.sort by Count.sum(), stable
+            if int(r["sub_count"][subs[-1]].sum()) < 1:
+                continue
+            write_any, starts, ends = [False] * nw, [2 ** 31 - 1] * nw, [0] * nw
+            for i in range(len(subs) - 1, len(subs) - 1 - max_transcripts, -1):
+                if i < 0:
+                    break
+                s_ = subs[i]
+                cnt = r["sub_count"][s_]
+                wg = [any(int(cnt[j]) >= gff_thresh[0] for j in range(min(nw, self.S)))] * nw
+                if cfg.first_is_transcriptome:
+                    t1 = gff_thresh[1]
+                    wg[0] = int(cnt[0]) >= 1 and any(int(cnt[j]) >= t1 for j in range(1, min(nw, self.S)))
+                br = render.consensus_breaks(r, s_, self.src, bool(cfg.first_is_transcriptome))
+                if br is None:
+                    raise ValueError("GFF output needs the break sums (track_break_sums)")
+                for k in range(nw):
+                    if wg[k]:
+                        write_any[k] = True
+                        starts[k], ends[k] = min(starts[k], int(br[0])), max(ends[k], int(br[-1]))
+                        line(k, "transcript", cid, names[s_], int(br[0]), int(br[-1]), type_nme, self.keys[c], names[s_], strand, cnt, br)
+            for k in range(nw):
+                if write_any[k]:
+                    line(k, "gene", None, cid, starts[k], ends[k], type_nme, self.keys[c], cid, strand, r["cl_read_count"][c], None)
+        return gff, bed
+
     def _is_leader(self, pos):
         if self.annotation.kind == abi.NPT_ANNOT_EMPTY:
             return pos < 100   # EmptyAnnotation.isLeader
@@ -302,9 +364,10 @@ class ChromosomeReport:
         gh = "ID\tchrom\tstart\tend\ttype_nme\tnum_exons\tisoforms\tleader_break\tORFs\tspan\tspan_length\ttotLen\tcountTotal\t" + counts
         return dict(transcripts=["#" + nme, th], genes=["#" + nme, gh], fc=["#npTranscript output", "Geneid\tChr\tStart\tEnd\tStrand\tLength\t" + nme])
 
-    def write(self, resdir, genome_index=0, polya=0, npy=True):
+    def write(self, resdir, genome_index=0, polya=0, npy=True, gff_thresh=None, max_transcripts=1):
         """Writes <genome_index>transcripts.txt.gz, genes.txt.gz, transcripts.fc.txt.gz, readToCluster.txt.gz (when read names
-        were given), annot.txt.gz, and .npy mirrors of the break-point and depth matrices.  Returns the list of paths."""
+        were given), annot.txt.gz, with gff_thresh (--writeGFF) <k>.gff.gz and <genome_index><k>.bed.gz (the "#date:" header line of the
+        GFF is left out), and .npy mirrors of the break-point and depth matrices.  Returns the list of paths."""
         os.makedirs(resdir, exist_ok=True)
         genes, trans, fc = self.rows()
         h = self.headers()
@@ -329,6 +392,23 @@ class ChromosomeReport:
                     "errorRatio\tORFs\tstrand\tbreaks\tspan\tspan_count\tqval")
             gz("readToCluster", [head] + render.read_to_cluster_rows(r, self.read_names, self.annotation, self.chrom, self.ci, bool(self.cfg.record_depth),
                                                                      coronavirus=bool(self.cfg.coronavirus), spans=self.read_span))
+        if gff_thresh is not None:   # --writeGFF
+            gff, bed = self.gff_bed(gff_thresh, max_transcripts)
+            for k, lines in enumerate(gff):
+                p = os.path.join(resdir, f"{k}.gff.gz")
+                with gzip.open(p, "wt") as f:
+                    f.write("##gff-version 3\n#description: \n#provider: \n#contact: \n#format: gff3\n")
+                    f.write(f"##sequence-region {self.chrom} 0 {self.seqlen}\n")
+                    for ln in lines:
+                        f.write(ln + "\n")
+                out.append(p)
+            for k, lines in enumerate(bed):
+                p = os.path.join(resdir, f"{genome_index}{k}.bed.gz")
+                with gzip.open(p, "wt") as f:
+                    f.write(f'track name="{self.source_names[k]}" description="{self.source_names[k]}" itemRgb="On" \n')
+                    for ln in lines:
+                        f.write(ln + "\n")
+                out.append(p)
         if npy:
             for (s, j), m in render.breakpoint_matrices(self.res, self.S).items():
                 p = os.path.join(resdir, f"{genome_index}.breakpoints.{self.source_names[s]}.{j}.npy")

@@ -139,3 +139,34 @@ def test_report_in_gff_mode():
     assert sum(1 for s, n in rep.read_span if n > 0) > 0.8 * b.n
     # source-0 reads are the transcripts themselves: their sub-clusters carry a read name as id
     assert any(not x.split("\t")[0].startswith("ID") for x in trans)
+
+
+def test_gff_and_bed_lines(tmp_path):
+    rep, res, b = _report(n=3000, S=2, depth=0, fit=1)
+    gff, bed = rep.gff_bed(gff_thresh=(2, 1), max_transcripts=3)
+    assert len(gff) == 2 and len(bed) == 2
+    for lines in gff:
+        cols = [x.split("\t") for x in lines]
+        assert all(len(c) == 9 and c[1] == "np" and c[2] in ("transcript", "exon", "gene") and int(c[3]) <= int(c[4]) for c in cols)
+        # every transcript is followed by its exons, every cluster's block ends with its gene line spanning its transcripts
+        genes = [c for c in cols if c[2] == "gene"]
+        assert genes and all("Parent=" not in c[8] and c[8].startswith("ID=ID0.") for c in genes)
+        tr = [c for c in cols if c[2] == "transcript"]
+        assert tr and all(";Parent=ID0." in c[8] for c in tr)
+        per_gene = {}
+        for c in tr:
+            per_gene.setdefault(c[8].split(";Parent=")[1].split(";")[0], []).append((int(c[3]), int(c[4])))
+        for g in genes:
+            span = per_gene[g[8].split(";")[0][3:]]
+            assert int(g[3]) == min(a for a, _ in span) and int(g[4]) == max(e for _, e in span) and len(span) <= 3
+    # writer 0 (the transcriptome's) only lists transcripts seen in source 0 and in some other source
+    for c in (x.split("\t") for x in gff[0]):
+        if c[2] == "transcript":
+            cnt = [int(v) for v in c[8].split("count=")[1].split(",")]
+            assert cnt[0] >= 1 and cnt[1] >= 1
+    for k, lines in enumerate(bed):
+        for c in (x.split("\t") for x in lines):
+            assert len(c) == 12 and int(c[4]) > 0 and int(c[9]) == len(c[10].split(",")) == len(c[11].split(",")) and c[11].split(",")[0] == "0"
+            assert int(c[2]) - int(c[1]) == int(c[11].split(",")[-1]) + int(c[10].split(",")[-1])   # last block ends at the transcript's end
+    paths = rep.write(str(tmp_path), gff_thresh=(2, 1), max_transcripts=3, npy=False)
+    assert {"0.gff.gz", "1.gff.gz", "00.bed.gz", "01.bed.gz"} <= {os.path.basename(p) for p in paths}
