@@ -67,6 +67,29 @@ int64_t nptb_ref_len(const nptb_reader* r, int32_t i);
 int nptb_next_batch(nptb_reader* r, const nptb_filter* f, int32_t src, int64_t max_batch_reads, nptb_batch* out);
 const char* nptb_last_error(const nptb_reader* r);
 
+/* The batch in the compact transfer format of npt_submit_packed (include/npt.h): 16-bit CIGAR words + the list of elements of
+ * 4 095 or longer, 2-bit bases + the list of seq4 bytes that hold anything but A C G T.  Field for field the layout of
+ * npt_packed_batch (tests/test_bam_pack.py checks the offsets), so that a pointer to it can be handed to npt_submit_packed.
+ * Buffers belong to the reader (same allocator as the batches: pinned when nptb_open got npt_alloc_pinned) and are valid
+ * until the next nptb_pack / nptb_close; pos, flag, src, cigar_off and seq_off are the batch's own arrays. */
+typedef struct nptb_packed {
+  int64_t n;
+  const int32_t* pos;
+  const uint16_t* flag;
+  const uint16_t* src;
+  const uint32_t* cigar_off;
+  const uint16_t* cigar16;
+  int64_t n_wide;
+  const uint32_t* wide_idx;
+  const uint32_t* wide_word;
+  const uint64_t* seq_off;
+  const uint8_t* seq2;
+  int64_t n_exc;
+  const uint64_t* exc_byte;
+  const uint8_t* exc_val;
+} nptb_packed;
+int nptb_pack(nptb_reader* r, const nptb_batch* b, nptb_packed* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,14 @@ class BatchStruct(C.Structure):
                 ("n_short", C.c_int64), ("n_low_mapq", C.c_int64), ("n_secondary", C.c_int64), ("stopped_at_max_reads", C.c_int32)]
 
 
-SYMBOLS = ["nptb_open", "nptb_close", "nptb_n_refs", "nptb_ref_name", "nptb_ref_len", "nptb_next_batch", "nptb_last_error"]
+class PackedStruct(C.Structure):
+    """nptb_packed = npt_packed_batch, field for field"""
+    _fields_ = [("n", C.c_int64), ("pos", C.c_void_p), ("flag", C.c_void_p), ("src", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar16", C.c_void_p),
+                ("n_wide", C.c_int64), ("wide_idx", C.c_void_p), ("wide_word", C.c_void_p), ("seq_off", C.c_void_p), ("seq2", C.c_void_p),
+                ("n_exc", C.c_int64), ("exc_byte", C.c_void_p), ("exc_val", C.c_void_p)]
+
+
+SYMBOLS = ["nptb_open", "nptb_close", "nptb_n_refs", "nptb_ref_name", "nptb_ref_len", "nptb_next_batch", "nptb_last_error", "nptb_pack"]
 
 
 def lib():
@@ -50,6 +57,8 @@ def lib():
         L.nptb_next_batch.restype = C.c_int
         L.nptb_last_error.argtypes = [C.c_void_p]
         L.nptb_last_error.restype = C.c_char_p
+        L.nptb_pack.argtypes = [C.c_void_p, C.POINTER(BatchStruct), C.POINTER(PackedStruct)]
+        L.nptb_pack.restype = C.c_int
         _lib = L
     return _lib
 
@@ -86,9 +95,11 @@ class Reader:
         except Exception:
             pass
 
-    def batches(self, src=0, max_batch_reads=1 << 20, fail_thresh=0.0, min_mapq=0, max_reads=0, ref_include=None, copy=True, decode_names=False):
+    def batches(self, src=0, max_batch_reads=1 << 20, fail_thresh=0.0, min_mapq=0, max_reads=0, ref_include=None, copy=True, decode_names=False,
+                packed=False):
         """Yields (ref_id, synth.Batch, dict(q1, mapq, name_off, names_bytes[, names])).  copy=False hands out views valid until the
-        next batch."""
+        next batch.  packed=True adds extra["packed"] = the batch in the compact transfer format (packed.PackedBatch, packed by
+        nptb_pack on the reader's threads; copies when copy=True, else views valid until the next batch)."""
         L = lib()
         flt = Filter(fail_thresh, min_mapq, max_reads, None)
         keep = None
@@ -120,6 +131,19 @@ class Reader:
                 arrs = [a.copy() for a in arrs]
                 q1, mq = q1.copy(), mq.copy()
             extra.update(q1=q1, mapq=mq)
+            if packed:
+                from .packed import PackedBatch
+                ps = PackedStruct()
+                if L.nptb_pack(self.h, C.byref(b), C.byref(ps)) != 0:
+                    raise BamError(L.nptb_last_error(self.h).decode())
+                ncig, nseq = int(co[-1]), int(so[-1])
+
+                def pv(ptr, m, dt):
+                    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(1, m * np.dtype(dt).itemsize),))[:m * np.dtype(dt).itemsize].view(dt)
+                    return a.copy() if copy else a
+                extra["packed"] = PackedBatch(arrs[0], arrs[1], arrs[2], arrs[3], pv(ps.cigar16, ncig, np.uint16), pv(ps.wide_idx, ps.n_wide, np.uint32),
+                                              pv(ps.wide_word, ps.n_wide, np.uint32), arrs[5], pv(ps.seq2, (nseq + 1) // 2, np.uint8),
+                                              pv(ps.exc_byte, ps.n_exc, np.uint64), pv(ps.exc_val, ps.n_exc, np.uint8))
             yield b.ref_id, Batch(*arrs), extra
 
 

@@ -84,6 +84,8 @@ struct nptb_reader {
   // batch buffers
   Buf<int32_t> pos; Buf<uint16_t> flag, src; Buf<uint32_t> cigar_off, cigar, name_off; Buf<uint64_t> seq_off; Buf<uint8_t> seq4, mapq;
   Buf<double> q1; Buf<char> names;
+  // compact transfer format of the current batch (nptb_pack)
+  Buf<uint16_t> cigar16; Buf<uint32_t> wide_idx, wide_word; Buf<uint8_t> seq2, exc_val; Buf<uint64_t> exc_byte;
   std::vector<RecInfo> scan;
   std::vector<uint32_t> kept;
   // totals
@@ -224,6 +226,7 @@ nptb_reader* nptb_open(const char* path, int nthreads, void* (*alloc)(size_t), v
   void (*f)(void*) = free_ ? free_ : free;
 #define INIT(b) r->b.alloc = a; r->b.free_ = f
   INIT(pos); INIT(flag); INIT(src); INIT(cigar_off); INIT(cigar); INIT(name_off); INIT(seq_off); INIT(seq4); INIT(mapq); INIT(q1); INIT(names);
+  INIT(cigar16); INIT(wide_idx); INIT(wide_word); INIT(seq2); INIT(exc_val); INIT(exc_byte);
 #undef INIT
   for (int v = 0; v < 256; v++) r->err_prob[v] = std::pow(10.0, -(double)(int8_t)(uint8_t)v / 10.0);
   if (read_header(r) < 0) { say(r->err.c_str()); nptb_close(r); return nullptr; }
@@ -234,6 +237,7 @@ void nptb_close(nptb_reader* r) {
   if (!r) return;
   r->pos.release(); r->flag.release(); r->src.release(); r->cigar_off.release(); r->cigar.release(); r->name_off.release();
   r->seq_off.release(); r->seq4.release(); r->mapq.release(); r->q1.release(); r->names.release();
+  r->cigar16.release(); r->wide_idx.release(); r->wide_word.release(); r->seq2.release(); r->exc_val.release(); r->exc_byte.release();
   if (r->map) munmap((void*)r->map, r->fsize);
   if (r->fd >= 0) close(r->fd);
   delete r;
@@ -385,6 +389,73 @@ int nptb_next_batch(nptb_reader* r, const nptb_filter* f, int32_t src, int64_t m
   out->n_short = r->n_short; out->n_low_mapq = r->n_low_mapq; out->n_secondary = r->n_secondary;
   out->stopped_at_max_reads = r->stopped ? 1 : 0;
   return n > 0 ? 1 : 0;
+}
+
+// ---- compact transfer format (npt_packed_batch of include/npt.h): every output element depends on one input element, so the
+// arrays are cut into ranges for the thread pool; the (rare) wide elements and exception bytes are collected per range and
+// concatenated in order
+int nptb_pack(nptb_reader* r, const nptb_batch* b, nptb_packed* out) {
+  if (!r || !b || !out) return -1;
+  const int64_t n = b->n;
+  const size_t ncig = n ? b->cigar_off[n] : 0, nseq = n ? (size_t)b->seq_off[n] : 0, nseq2 = (nseq + 1) / 2;
+  if (!r->cigar16.reserve(ncig + 8, 0) || !r->seq2.reserve(nseq2 + 16, 0)) return fail(r, "out of memory");
+  const int nt = std::max(1, r->nthreads);
+  // CIGAR: (len << 4 | op) fits 16 bits when len < 4095; longer elements keep their op under an all-ones length
+  std::vector<std::vector<uint32_t>> widx(nt), wword(nt);
+  {
+    const size_t per = (ncig + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t] {
+        const size_t lo = std::min(ncig, t * per), hi = std::min(ncig, (t + 1) * per);
+        for (size_t i = lo; i < hi; i++) {
+          const uint32_t w = b->cigar[i];
+          if ((w >> 4) >= 4095u) { r->cigar16.p[i] = (uint16_t)(0xFFF0u | (w & 15u)); widx[t].push_back((uint32_t)i); wword[t].push_back(w); }
+          else r->cigar16.p[i] = (uint16_t)w;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  // bases: seq4 byte j (two 4-bit codes) -> nibble j of the seq2 stream (two 2-bit codes); A C G T = 1 2 4 8 -> 0 1 2 3
+  static const uint8_t code2[16] = {0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0};
+  static const uint8_t ok4[16] = {0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<std::vector<uint64_t>> eidx(nt);
+  std::vector<std::vector<uint8_t>> eval(nt);
+  {
+    const size_t per = ((nseq2 + nt - 1) / nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t] {
+        const size_t lo = std::min(nseq2, t * per), hi = std::min(nseq2, (t + 1) * per);
+        for (size_t m = lo; m < hi; m++) {
+          uint8_t o = 0;
+          for (int k = 0; k < 2; k++) {
+            const size_t j = 2 * m + k;
+            uint8_t v = 0;
+            if (j < nseq) {
+              v = b->seq4[j];
+              if (!(ok4[v >> 4] & ok4[v & 15])) { eidx[t].push_back((uint64_t)j); eval[t].push_back(v); }
+            }
+            o = (uint8_t)((o << 4) | (code2[v >> 4] << 2) | code2[v & 15]);
+          }
+          r->seq2.p[m] = o;
+        }
+      });
+    for (auto& x : th) x.join();
+  }
+  size_t nw = 0, ne = 0;
+  for (int t = 0; t < nt; t++) { nw += widx[t].size(); ne += eidx[t].size(); }
+  if (!r->wide_idx.reserve(nw + 1, 0) || !r->wide_word.reserve(nw + 1, 0) || !r->exc_byte.reserve(ne + 1, 0) || !r->exc_val.reserve(ne + 1, 0))
+    return fail(r, "out of memory");
+  size_t ow = 0, oe = 0;
+  for (int t = 0; t < nt; t++) {
+    if (!widx[t].empty()) { memcpy(r->wide_idx.p + ow, widx[t].data(), widx[t].size() * 4); memcpy(r->wide_word.p + ow, wword[t].data(), wword[t].size() * 4); ow += widx[t].size(); }
+    if (!eidx[t].empty()) { memcpy(r->exc_byte.p + oe, eidx[t].data(), eidx[t].size() * 8); memcpy(r->exc_val.p + oe, eval[t].data(), eval[t].size()); oe += eidx[t].size(); }
+  }
+  out->n = n; out->pos = b->pos; out->flag = b->flag; out->src = b->src; out->cigar_off = b->cigar_off; out->cigar16 = r->cigar16.p;
+  out->n_wide = (int64_t)nw; out->wide_idx = r->wide_idx.p; out->wide_word = r->wide_word.p;
+  out->seq_off = b->seq_off; out->seq2 = r->seq2.p; out->n_exc = (int64_t)ne; out->exc_byte = r->exc_byte.p; out->exc_val = r->exc_val.p;
+  return 0;
 }
 
 }  // extern "C"

@@ -107,6 +107,30 @@ def test_round_trip_of_a_synthetic_batch(tmp_path):
     assert (extra["q1"] == 500).all()
 
 
+@pytest.mark.parametrize("threads", [1, 5])
+def test_compact_format_from_bam_equals_the_numpy_packer(tmp_path, threads):
+    """nptb_pack (C++, on the reader's threads) and packed.pack (numpy) give the same arrays, and unpacking them gives back the
+    batch; reads with N / IUPAC bases and junction-sized N elements take the exception and wide lists"""
+    from nptranscript_b200 import abi, packed
+    w = workloads.SARS2
+    b = synth.generate(w, 78, 3000)
+    rng = np.random.default_rng(1)
+    k = rng.integers(0, len(b.seq4), 200)
+    b.seq4[k] = rng.integers(0, 256, 200).astype(np.uint8)
+    path = os.path.join(str(tmp_path), "pk.bam")
+    bam.write_bam(path, [(w.name, w.genome_len)], bam.records_from_batch(b))
+    (ref_id, got, extra), = list(bam.Reader(path, nthreads=threads).batches(packed=True))
+    pb, want = extra["packed"], packed.pack(got)
+    for x, y in zip(pb.arrays(), want.arrays()):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    cig, seq4 = packed.unpack(pb)
+    assert np.array_equal(cig, got.cigar) and np.array_equal(seq4, got.seq4)
+    assert len(pb.wide_idx) > 0 and len(pb.exc_byte) > 0 and pb.nbytes() < 0.55 * got.nbytes()
+    # nptb_packed is npt_packed_batch field for field (a pointer to one is what npt_submit_packed takes)
+    assert [(n, getattr(bam.PackedStruct, n).offset) for n, _ in bam.PackedStruct._fields_] == \
+           [(n, getattr(abi.npt_packed_batch, n).offset) for n, _ in abi.npt_packed_batch._fields_]
+
+
 def test_malformed_files_are_reported(tmp_path):
     p = os.path.join(str(tmp_path), "bad.bam")
     open(p, "wb").write(b"not a bam file at all, not even gzip..........")
@@ -140,7 +164,7 @@ def test_struct_layout_matches_c():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "npt_bam.h"\nint main(){\n'
     probes = []
-    for cname, st in (("nptb_filter", bam.Filter), ("nptb_batch", bam.BatchStruct)):
+    for cname, st in (("nptb_filter", bam.Filter), ("nptb_batch", bam.BatchStruct), ("nptb_packed", bam.PackedStruct)):
         src += f'printf("%zu\\n", sizeof({cname}));\n'
         probes.append((cname, None, C.sizeof(st)))
         for fname, _ in st._fields_:
