@@ -22,7 +22,7 @@ namespace npt {
 #endif
 constexpr int FW_WARPS_MAX = NPT_FW_WARPS;
 constexpr int FW_PW_TILE = 32 * FW_TILE_STRIDE;
-__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : FW_BRK_BUF * 32); }
+__host__ __device__ constexpr int fw_warp_words(bool record) { return FW_PW_TILE + (record ? (FW_RING + FW_RING_PAD) * 32 : 0); }
 
 __device__ __forceinline__ void fw_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -51,6 +51,9 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
   const uint32_t tileS = (uint32_t)__cvta_generic_to_shared(tileT);
   const uint32_t* cigL = tileT + lane * FW_TILE_STRIDE;
   const uint32_t* seqL = cigL + FW_CIG_TILE;
+  // the lane's coverage ring (shared memory, lane-interleaved) or, without depth recording, its break-list scratch (global)
+  uint32_t* auxL = RECORD ? ringT + lane : c.fw_scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * FW_BRK_BUF;
+  const int auxS = RECORD ? 32 : 1;
   unsigned* cursor = b.bctr + 5;
   const unsigned cig_words = (unsigned)b.cigar_words;                   // cigar_off is 32 bits
   const unsigned long long seq_bytes = (unsigned long long)b.seq_bytes;
@@ -113,10 +116,10 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
     // ---- (2) FW_R steps: [one element that is not M] + [start of the M behind it] + [<= 16 positions of the current M]
     const int ringLimit = (L.flushE << 5) + FW_RING * 8 - 2 * FW_PIECE - 2;
 #pragma unroll 1
-    for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigL, seqL, refg, ringT + lane, 32, live, ringLimit);
+    for (int it = 0; it < FW_R; it++) fw_step<RECORD>(L, c, b, cigL, seqL, refg, auxL, auxS, live, ringLimit);
     __syncwarp();
     // ---- (3) N elements, completed entries, closed blocks, finished reads
-    fw_round_end<RECORD>(L, c, b, cigL, ringT + lane, 32);
+    fw_round_end<RECORD>(L, c, b, cigL, auxL, auxS);
     __syncwarp();
   }
 }

@@ -64,10 +64,10 @@ constexpr int FW_MAX_EXTRA = 4;    // rare extra events per read (see below)
 constexpr int FW_RARE_WORDS = 16;  // per-read record of rare events, uint32 words
 constexpr int FW_BRK_INLINE = 6;
 // Without depth recording (host mode, opts_host.txt) nothing is kept per aligned block, so the number of blocks is free and
-// the break list may be long: a spliced read has two breaks per junction.  The lane keeps them in FW_BRK_BUF words of shared
-// memory (the place of the coverage ring, which is not needed then) and moves the list to the batch's overflow area at the end
-// of the read, like walk_kernel<2> does for the serial walker.
-constexpr int FW_LONG_JUNC = 30;
+// the break list may be long: a spliced read has two breaks per junction.  The lane keeps them in FW_BRK_BUF words of a
+// lane-private scratch in global memory (written at junctions only: a few stores per read) and moves the list to the batch's
+// overflow area at the end of the read, like walk_kernel<2> does for the serial walker.
+constexpr int FW_LONG_JUNC = 127;
 constexpr int FW_BRK_BUF = 2 * FW_LONG_JUNC + 2;
 
 // entry flags, one nibble per position (position 8W + i of ring word W sits in nibble i counted from the top)
@@ -207,7 +207,7 @@ FW_HD void fw_double_qrk(FwLane& L, const BatchDev& b, int p0, int qe) {
 // ---- one step ---------------------------------------------------------------------------------------------------------
 // cig[i] = CIGAR word (L.cs + i), i < FW_CIG_TILE; seq[k] = raw (little-endian) word k of the base tile; refg[W] = reference
 // grid word W (positions 8W..8W+7, first in the top nibble); ring[j * RS] = lane-private ring word j, j < FW_RING + FW_RING_PAD
-// (RECORD) or lane-private break buffer word j, j < FW_BRK_BUF (!RECORD).
+// (RECORD) or lane-private break scratch word j, j < FW_BRK_BUF (!RECORD; global memory, RS = 1).
 // `live` = the lane holds a read the fast walk has not given up; ringLimit = last refPos a step may start from without
 // running past the 256 positions the ring holds behind the first unflushed entry.
 // The step takes an element only when it can restate it: I S H P always, D of at most 16 positions after the first M, M.  At

@@ -110,7 +110,7 @@ struct npt_ctx {
   size_t walk_smem = 0, cluster_smem = 0;
   int cluster_occ = 8, covkey_occ = 6;   // resident cluster_kernel / cov_key_kernel blocks per SM
   // fast walk (fastwalk.cuh / fastcov.cuh)
-  DBuf<uint32_t> d_refg;
+  DBuf<uint32_t> d_refg, d_fw_scratch;
   bool fast = false, fast_record = false;
   int fw_blocks = 0, fw_threads = 0, acc_blocks = 0, acc_pos_shift = 0;
   size_t fw_smem = 0;
@@ -687,7 +687,7 @@ void npt_destroy(npt_ctx* ctx) {
   free_batches(ctx);
   for (auto& pb : ctx->pool_free) cudaFree(pb.first);
   ctx->pool_free.clear();
-  ctx->d_ref.release(); ctx->d_ref_codes.release(); ctx->d_refg.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
+  ctx->d_ref.release(); ctx->d_ref_codes.release(); ctx->d_refg.release(); ctx->d_fw_scratch.release(); ctx->d_ostart.release(); ctx->d_oname.release(); ctx->d_exc_first.release(); ctx->d_exc_u[0].release(); ctx->d_exc_u[1].release(); ctx->d_fin_sum_off.release(); ctx->d_fin_sums.release(); ctx->d_pair_keys.release(); ctx->d_pair_keys2.release(); ctx->d_pair_cnt.release(); ctx->d_pair_cnt2.release(); ctx->d_kx.release(); ctx->d_kx_slotmap.release(); ctx->d_kx_ctr.release();
   ctx->d_ostrand.release(); ctx->d_gx.release(); ctx->d_gxhash.release(); ctx->d_cl.release();
   ctx->d_cl_rec.release(); ctx->d_sb.release(); ctx->d_sb_rec.release(); ctx->d_sub_count.release(); ctx->d_sub_break_sum.release();
   ctx->d_sub_sums.release(); ctx->d_sub_min0.release(); ctx->d_pr.release();
@@ -923,6 +923,10 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
           else { CK(cudaFuncSetAttribute(fast_walk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_walk_kernel<false, false>, ctx->fw_threads, ctx->fw_smem)); }
         }
         ctx->fw_blocks = ctx->sm_count * std::max(1, occ);
+        if (!ctx->fast_record) {
+          CK(ctx->d_fw_scratch.ensure((size_t)ctx->fw_blocks * ctx->fw_threads * FW_BRK_BUF));
+          dc.fw_scratch = ctx->d_fw_scratch.p;
+        }
         if (ctx->fast_record) {
           CK(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
           ctx->acc_blocks = ctx->sm_count;

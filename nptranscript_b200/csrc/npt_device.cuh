@@ -49,6 +49,7 @@ struct DevCfg {
   int ref_nwords;             // words incl. padding
   const uint32_t* refg_words; // the same bases on the POSITION grid of the fast walk: word W = positions 8W..8W+7 (1-based,
   int refg_nwords;            // position 0 is padding), first in the top nibble; padded by 4 words
+  uint32_t* fw_scratch;       // fast walk without depth recording: FW_BRK_BUF words per resident thread (long break lists)
   const int* orf_start;
   const int* orf_name;
   const uint8_t* orf_strand;

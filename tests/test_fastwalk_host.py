@@ -218,7 +218,7 @@ def test_known_answers():
 
 def test_long_break_lists_without_depth_recording():
     """host-mode shape: spliced reads with many junctions.  Without depth recording the fast walk keeps them (any number of
-    aligned blocks, up to 30 junctions) and moves lists longer than the inline slot to the overflow area; with a too small
+    aligned blocks, up to 127 junctions) and moves lists longer than the inline slot to the overflow area; with a too small
     overflow area it says so (bctr[1]) and reports the need (bctr[0])"""
     c = workloads.human_like()[20]
     g = synth.host_genome_codes(c)
