@@ -309,6 +309,7 @@ const char* npt_mg_last_error(const npt_mg* mg);   /* mg may be NULL: error of t
 int npt_mg_set_read_index_base(npt_mg* mg, int64_t base);
 int npt_mg_begin_chrom(npt_mg* mg, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot);
 int npt_mg_submit(npt_mg* mg, const npt_batch* batch);   /* NPT_MEM_HOST only; arrays untouched until npt_mg_wait / npt_mg_end_chrom */
+int npt_mg_submit_packed(npt_mg* mg, const npt_packed_batch* batch);   /* the same in the compact transfer format */
 int npt_mg_wait(npt_mg* mg);
 int npt_mg_end_chrom(npt_mg* mg);
 int npt_mg_fetch_results(npt_mg* mg, int what, npt_results* out);

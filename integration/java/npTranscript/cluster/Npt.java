@@ -60,6 +60,7 @@ final class Npt {
   static final MethodHandle mgBeginChrom =
       h("npt_mg_begin_chrom", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS));
   static final MethodHandle mgSubmit = h("npt_mg_submit", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+  static final MethodHandle mgSubmitPacked = h("npt_mg_submit_packed", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   static final MethodHandle mgEndChrom = h("npt_mg_end_chrom", FunctionDescriptor.of(JAVA_INT, ADDRESS));
   static final MethodHandle mgFetch = h("npt_mg_fetch_results", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
   static final MethodHandle mgRelease = h("npt_mg_release_results", FunctionDescriptor.of(JAVA_INT, ADDRESS));

@@ -77,7 +77,7 @@ SYMBOLS = [
     "npt_set_read_index_base", "npt_set_next_read_index", "npt_alloc_pinned", "npt_free_pinned", "npt_last_kernel_ms", "npt_last_step_ms", "npt_last_stage_ms",
     "npt_export_keys", "npt_import_keys",
     "npt_comm_unique_id", "npt_comm_init", "npt_end_chrom_all", "npt_last_exchange_ms",
-    "npt_mg_create", "npt_mg_destroy", "npt_mg_last_error", "npt_mg_set_read_index_base", "npt_mg_begin_chrom", "npt_mg_submit", "npt_mg_wait",
+    "npt_mg_create", "npt_mg_destroy", "npt_mg_last_error", "npt_mg_set_read_index_base", "npt_mg_begin_chrom", "npt_mg_submit", "npt_mg_submit_packed", "npt_mg_wait",
     "npt_mg_end_chrom", "npt_mg_fetch_results", "npt_mg_release_results", "npt_mg_last_step_ms",
 ]
 NPT_COMM_ID_BYTES = 128
@@ -125,13 +125,14 @@ def declare(lib):
     lib.npt_mg_set_read_index_base.argtypes = [vp, i64]
     lib.npt_mg_begin_chrom.argtypes = [vp, i32, vp, i64, P(npt_annotation)]
     lib.npt_mg_submit.argtypes = [vp, P(npt_batch)]
+    lib.npt_mg_submit_packed.argtypes = [vp, P(npt_packed_batch)]
     lib.npt_mg_wait.argtypes = [vp]
     lib.npt_mg_end_chrom.argtypes = [vp]
     lib.npt_mg_fetch_results.argtypes = [vp, C.c_int, P(npt_results)]
     lib.npt_mg_release_results.argtypes = [vp]
     lib.npt_mg_last_step_ms.argtypes = [vp, P(C.c_float), P(C.c_float), P(C.c_float)]
     for s in ("npt_comm_unique_id", "npt_comm_init", "npt_end_chrom_all", "npt_last_exchange_ms", "npt_mg_create", "npt_mg_set_read_index_base",
-              "npt_mg_begin_chrom", "npt_mg_submit", "npt_mg_wait", "npt_mg_end_chrom", "npt_mg_fetch_results", "npt_mg_release_results",
+              "npt_mg_begin_chrom", "npt_mg_submit", "npt_mg_submit_packed", "npt_mg_wait", "npt_mg_end_chrom", "npt_mg_fetch_results", "npt_mg_release_results",
               "npt_mg_last_step_ms"):
         getattr(lib, s).restype = C.c_int
     for s in ("npt_create", "npt_begin_chrom", "npt_submit", "npt_submit_packed", "npt_wait", "npt_end_chrom", "npt_fetch_results",

@@ -67,12 +67,17 @@ struct LocalGroup {
   std::condition_variable cv;
   int arrived = 0;
   long long generation = 0;
-  void barrier() {
+  bool aborted = false;   // a member failed: nobody waits for it any more (until the next chromosome)
+  bool barrier() {
     std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
     const long long g = generation;
     if (++arrived == (int)members.size()) { arrived = 0; generation++; cv.notify_all(); }
-    else cv.wait(lk, [&] { return generation != g; });
+    else cv.wait(lk, [&] { return generation != g || aborted; });
+    return !aborted;
   }
+  void abort() { std::lock_guard<std::mutex> lk(mu); aborted = true; cv.notify_all(); }
+  void reset() { std::lock_guard<std::mutex> lk(mu); aborted = false; arrived = 0; }
 };
 
 __global__ void local_sum_kernel(int* const* ptrs, int n, long long count) {
@@ -118,11 +123,14 @@ static int end_chrom_all(npt_ctx* ctx) {
   cudaEvent_t e0, e1, e2, e3;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
   auto drop = [&] { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); };
+  // an error of one member of a local group releases the others from their barriers (they fail with NPT_ESTATE)
+  auto bail = [&](int code) { drop(); if (cm.local) cm.local->abort(); return code; };
+  auto sync_group = [&]() { return cm.local->barrier() ? NPT_OK : fail(ctx, NPT_ESTATE, "another context of the group failed"); };
   // 1. this rank's keys
   const int32_t* mine = nullptr;
   int64_t my_words = 0;
   int rc = npt_export_keys(ctx, &mine, &my_words);
-  if (rc) { drop(); return rc; }
+  if (rc) return bail(rc);
   CK(cudaEventRecord(e0, st));
   // headers of all ranks -> host
   std::vector<int> hdrs((size_t)W * KX_HDR);
@@ -132,13 +140,13 @@ static int end_chrom_all(npt_ctx* ctx) {
     CK(cudaMemcpyAsync(hdrs.data(), ctx->d_kx_hdrs.p, hdrs.size() * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   } else {
-    cm.local->barrier();   // every member has exported (npt_export_keys waits for its stream)
+    if ((rc = sync_group())) return bail(rc);   // every member has exported (npt_export_keys waits for its stream)
     for (int r = 0; r < W; r++) memcpy(hdrs.data() + (size_t)r * KX_HDR, cm.local->members[r]->kx_hdr, KX_HDR * sizeof(int));
   }
   std::vector<long long> off(W + 1, 0);
   for (int r = 0; r < W; r++) {
     const int* h = hdrs.data() + (size_t)r * KX_HDR;
-    if (h[0] != KX_MAGIC || h[13] < KX_HDR) { drop(); return fail(ctx, NPT_EINVAL, "rank %d sent no key buffer", r); }
+    if (h[0] != KX_MAGIC || h[13] < KX_HDR) return bail(fail(ctx, NPT_EINVAL, "rank %d sent no key buffer", r));
     off[r + 1] = off[r] + ((h[13] + 3) & ~3);   // 16-byte aligned sections
   }
   CK(ctx->d_kx_all.ensure((size_t)off[W]));
@@ -155,14 +163,14 @@ static int end_chrom_all(npt_ctx* ctx) {
   }
   // 3. insert the other ranks' keys
   for (int r = 0; r < W; r++)
-    if (r != me && (rc = import_keys_enqueue(ctx, ctx->d_kx_all.p + off[r], hdrs[(size_t)r * KX_HDR + 13], hdrs.data() + (size_t)r * KX_HDR))) { drop(); return rc; }
+    if (r != me && (rc = import_keys_enqueue(ctx, ctx->d_kx_all.p + off[r], hdrs[(size_t)r * KX_HDR + 13], hdrs.data() + (size_t)r * KX_HDR))) return bail(rc);
   CK(cudaEventRecord(e1, st));
-  if (!cm.nc) { CK(cudaStreamSynchronize(st)); cm.local->barrier(); }   // nobody rewrites its d_kx before everyone has copied it
+  if (!cm.nc) { CK(cudaStreamSynchronize(st)); if ((rc = sync_group())) return bail(rc); }   // nobody rewrites its d_kx before everyone has copied it
   // 4. global numbering
-  if ((rc = npt_end_chrom(ctx))) { drop(); return rc; }
+  if ((rc = npt_end_chrom(ctx))) return bail(rc);
   // 5. sum the counters in place
   npt_device_view v;
-  if ((rc = npt_device_view_get(ctx, &v))) { drop(); return rc; }
+  if ((rc = npt_device_view_get(ctx, &v))) return bail(rc);
   struct Arr { void* p; long long n; bool wide; } arrs[6] = {{v.coverage, v.coverage_elems, false}, {v.small_counts, v.small_elems, false},
       {v.sub_count, v.sub_count_elems, false}, {v.sub_break_sum, v.sub_break_sum_elems, false}, {v.sub_sums, v.sub_sums_elems, true},
       {v.pair_count, v.pair_count_elems, false}};
@@ -173,7 +181,7 @@ static int end_chrom_all(npt_ctx* ctx) {
       if (a.p && a.n) NCK(nccl().AllReduce(a.p, a.p, (size_t)a.n, a.wide ? ncclInt64 : ncclInt32, ncclSum, cm.nc, st));
     NCK(nccl().GroupEnd());
   } else {
-    cm.local->barrier();   // every member has finished npt_end_chrom (it waits for its stream)
+    if ((rc = sync_group())) return bail(rc);   // every member has finished npt_end_chrom (it waits for its stream)
     if (me == 0) {
       DBuf<int*> d_ptrs;
       CK(d_ptrs.ensure((size_t)W));
@@ -182,11 +190,11 @@ static int end_chrom_all(npt_ctx* ctx) {
         long long cnt = -1;
         for (int r = 0; r < W; r++) {
           npt_device_view vr;
-          if ((rc = npt_device_view_get(cm.local->members[r], &vr))) { drop(); return rc; }
+          if ((rc = npt_device_view_get(cm.local->members[r], &vr))) return bail(rc);
           void* ps[6] = {vr.coverage, vr.small_counts, vr.sub_count, vr.sub_break_sum, vr.sub_sums, vr.pair_count};
           const long long ns[6] = {vr.coverage_elems, vr.small_elems, vr.sub_count_elems, vr.sub_break_sum_elems, 2 * vr.sub_sums_elems, vr.pair_count_elems};
           hp[r] = (int*)ps[k];
-          if (cnt >= 0 && cnt != ns[k]) { drop(); return fail(ctx, NPT_ECUDA, "internal: counter arrays differ in size between ranks"); }
+          if (cnt >= 0 && cnt != ns[k]) return bail(fail(ctx, NPT_ECUDA, "internal: counter arrays differ in size between ranks"));
           cnt = ns[k];
         }
         if (cnt <= 0 || !hp[0]) continue;
@@ -205,7 +213,7 @@ static int end_chrom_all(npt_ctx* ctx) {
       }
       d_ptrs.release();
     }
-    cm.local->barrier();
+    if ((rc = sync_group())) return bail(rc);
   }
   CK(cudaEventRecord(e3, st));
   CK(cudaEventRecord(ctx->ev_c1, st));
@@ -230,7 +238,11 @@ struct npt_mg {
   std::vector<std::vector<int64_t>> part;     // part[batch][device]
   // rebased offsets of a device's share of a batch (pinned; ring of three: a slot is reused only after the batch that used
   // it has been retired by a later npt_submit of that device)
-  struct Scratch { uint32_t* coff = nullptr; uint64_t* soff = nullptr; size_t cap = 0; };
+  struct Scratch {
+    uint32_t* coff = nullptr; uint64_t* soff = nullptr; size_t cap = 0;
+    uint32_t* widx = nullptr; size_t wcap = 0;      // rebased wide-element / exception indices of a packed share
+    uint64_t* eidx = nullptr; size_t ecap = 0;
+  };
   std::vector<Scratch> scratch;               // [device * 3 + slot]
   int64_t n_batches = 0;
   // merged results
@@ -309,7 +321,7 @@ const char* npt_mg_last_error(const npt_mg* m) { return m ? m->err.c_str() : g_c
 void npt_mg_destroy(npt_mg* m) {
   if (!m) return;
   for (auto* c : m->ctx) npt_destroy(c);
-  for (auto& s : m->scratch) { if (s.coff) cudaFreeHost(s.coff); if (s.soff) cudaFreeHost(s.soff); }
+  for (auto& s : m->scratch) { if (s.coff) cudaFreeHost(s.coff); if (s.soff) cudaFreeHost(s.soff); if (s.widx) cudaFreeHost(s.widx); if (s.eidx) cudaFreeHost(s.eidx); }
   delete m;
 }
 
@@ -357,32 +369,38 @@ int npt_mg_set_read_index_base(npt_mg* m, int64_t base) {
 int npt_mg_begin_chrom(npt_mg* m, int32_t chrom_index, const uint8_t* ref_codes, int64_t ref_len, const npt_annotation* annot) {
   if (!m) return NPT_EINVAL;
   m->part.clear(); m->n_batches = 0; m->next_index = m->user_base;
+  m->local.reset();
   return mg_parallel(m, [&](int d) { return npt_begin_chrom(m->ctx[d], chrom_index, ref_codes, ref_len, annot); });
 }
 
+}  // extern "C"
+
 // Reads [lo_d, lo_{d+1}) of the batch go to device d: contiguous ranges of the submit order with about the same number of
-// bases each.  Every device thread rebases its share's offsets (12 bytes per read) and calls npt_submit.
-int npt_mg_submit(npt_mg* m, const npt_batch* b) {
-  if (!m || !b) return mg_fail(m, NPT_EINVAL, "null argument");
-  if (b->location != NPT_MEM_HOST) return mg_fail(m, NPT_EINVAL, "npt_mg_submit takes host batches (the library splits them over its devices)");
-  const int64_t n = b->n;
+// bases each.  Every device thread rebases its share's offsets (12 bytes per read) and calls npt_submit / npt_submit_packed.
+// A packed share must start on an even seq4 byte (two seq4 bytes share one seq2 byte): its first read moves up to the next
+// read that does.
+static int mg_submit(npt_mg* m, const npt_batch* b, const npt_packed_batch* pb) {
+  const int64_t n = b ? b->n : pb->n;
   if (n < 0) return mg_fail(m, NPT_EINVAL, "batch size out of range");
   if (n == 0) return NPT_OK;
+  const uint32_t* coff = b ? b->cigar_off : pb->cigar_off;
+  const uint64_t* soff = b ? b->seq_off : pb->seq_off;
   const int D = (int)m->ctx.size();
   std::vector<int64_t> lo(D + 1, 0);
   lo[D] = n;
-  const uint64_t total = b->seq_off[n];
+  const uint64_t total = soff[n];
   for (int d = 1; d < D; d++) {
     const uint64_t want = total / D * d;
-    lo[d] = std::lower_bound(b->seq_off, b->seq_off + n, want) - b->seq_off;
+    lo[d] = std::lower_bound(soff, soff + n, want) - soff;
     lo[d] = std::max(lo[d], lo[d - 1]);
+    if (pb) while (lo[d] < n && (soff[lo[d]] & 1)) lo[d]++;
   }
   const int slot = (int)(m->n_batches % 3);
   const int64_t base = m->next_index;
   const int rc = mg_parallel(m, [&](int d) -> int {
     npt_ctx* ctx = m->ctx[d];
     const int64_t a = lo[d], cnt = lo[d + 1] - lo[d];
-    if (cnt == 0) return NPT_OK;
+    if (cnt <= 0) return NPT_OK;
     CK(cudaSetDevice(ctx->device));
     npt_mg::Scratch& s = m->scratch[(size_t)d * 3 + slot];
     if (s.cap < (size_t)cnt + 1) {
@@ -394,14 +412,33 @@ int npt_mg_submit(npt_mg* m, const npt_batch* b) {
       CK(cudaHostAlloc(&s.soff, cap * 8, cudaHostAllocDefault));
       s.cap = cap;
     }
-    const uint32_t c0 = b->cigar_off[a];
-    const uint64_t s0 = b->seq_off[a];
-    for (int64_t i = 0; i <= cnt; i++) { s.coff[i] = b->cigar_off[a + i] - c0; s.soff[i] = b->seq_off[a + i] - s0; }
-    npt_batch sub = *b;
-    sub.n = cnt; sub.pos = b->pos + a; sub.flag = b->flag + a; sub.src = b->src + a;
-    sub.cigar_off = s.coff; sub.cigar = b->cigar + c0; sub.seq_off = s.soff; sub.seq4 = b->seq4 + s0;
+    const uint32_t c0 = coff[a], c1 = coff[a + cnt];
+    const uint64_t s0 = soff[a], s1 = soff[a + cnt];
+    for (int64_t i = 0; i <= cnt; i++) { s.coff[i] = coff[a + i] - c0; s.soff[i] = soff[a + i] - s0; }
     ctx->idx_base = base + a;   // global submit index of the share's first read
-    return npt_submit(ctx, &sub);
+    if (b) {
+      npt_batch sub = *b;
+      sub.n = cnt; sub.pos = b->pos + a; sub.flag = b->flag + a; sub.src = b->src + a;
+      sub.cigar_off = s.coff; sub.cigar = b->cigar + c0; sub.seq_off = s.soff; sub.seq4 = b->seq4 + s0;
+      return npt_submit(ctx, &sub);
+    }
+    // the share's part of the wide-element and exception lists, indices rebased to the share
+    const uint32_t* w0 = std::lower_bound(pb->wide_idx, pb->wide_idx + pb->n_wide, c0);
+    const uint32_t* w1 = std::lower_bound(pb->wide_idx, pb->wide_idx + pb->n_wide, c1);
+    const uint64_t* e0 = std::lower_bound(pb->exc_byte, pb->exc_byte + pb->n_exc, s0);
+    const uint64_t* e1 = std::lower_bound(pb->exc_byte, pb->exc_byte + pb->n_exc, s1);
+    const size_t nw = (size_t)(w1 - w0), ne = (size_t)(e1 - e0);
+    if (s.wcap < nw + 1) { if (s.widx) cudaFreeHost(s.widx); s.widx = nullptr; s.wcap = 0; CK(cudaHostAlloc(&s.widx, (nw + 1 + nw / 2) * 4, cudaHostAllocDefault)); s.wcap = nw + 1 + nw / 2; }
+    if (s.ecap < ne + 1) { if (s.eidx) cudaFreeHost(s.eidx); s.eidx = nullptr; s.ecap = 0; CK(cudaHostAlloc(&s.eidx, (ne + 1 + ne / 2) * 8, cudaHostAllocDefault)); s.ecap = ne + 1 + ne / 2; }
+    for (size_t i = 0; i < nw; i++) s.widx[i] = w0[i] - c0;
+    for (size_t i = 0; i < ne; i++) s.eidx[i] = e0[i] - s0;
+    npt_packed_batch sub = *pb;
+    sub.n = cnt; sub.pos = pb->pos + a; sub.flag = pb->flag + a; sub.src = pb->src + a;
+    sub.cigar_off = s.coff; sub.cigar16 = pb->cigar16 + c0;
+    sub.n_wide = (int64_t)nw; sub.wide_idx = s.widx; sub.wide_word = pb->wide_word + (w0 - pb->wide_idx);
+    sub.seq_off = s.soff; sub.seq2 = pb->seq2 + s0 / 2;   // s0 is even (or the share is the first one)
+    sub.n_exc = (int64_t)ne; sub.exc_byte = s.eidx; sub.exc_val = pb->exc_val + (e0 - pb->exc_byte);
+    return npt_submit_packed(ctx, &sub);
   });
   if (rc) return rc;
   std::vector<int64_t> cnts(D);
@@ -410,6 +447,20 @@ int npt_mg_submit(npt_mg* m, const npt_batch* b) {
   m->n_batches++;
   m->next_index += n;
   return NPT_OK;
+}
+
+extern "C" {
+
+int npt_mg_submit(npt_mg* m, const npt_batch* b) {
+  if (!m || !b) return mg_fail(m, NPT_EINVAL, "null argument");
+  if (b->location != NPT_MEM_HOST) return mg_fail(m, NPT_EINVAL, "npt_mg_submit takes host batches (the library splits them over its devices)");
+  return mg_submit(m, b, nullptr);
+}
+
+int npt_mg_submit_packed(npt_mg* m, const npt_packed_batch* pb) {
+  if (!m || !pb) return mg_fail(m, NPT_EINVAL, "null argument");
+  if (pb->n_wide < 0 || pb->n_exc < 0) return mg_fail(m, NPT_EINVAL, "packed batch: wide / exception lists inconsistent");
+  return mg_submit(m, nullptr, pb);
 }
 
 int npt_mg_wait(npt_mg* m) {

@@ -303,6 +303,17 @@ class MultiEngine:
         self._keep.append(batch)
         self._ck(self.L.npt_mg_submit(self.h, C.byref(s)))
 
+    def submit_packed(self, pb):
+        s = abi.npt_packed_batch()
+        s.n = pb.n
+        s.pos, s.flag, s.src = pb.pos.ctypes.data, pb.flag.ctypes.data, pb.src.ctypes.data
+        s.cigar_off, s.cigar16 = pb.cigar_off.ctypes.data, pb.cigar16.ctypes.data
+        s.n_wide, s.wide_idx, s.wide_word = len(pb.wide_idx), pb.wide_idx.ctypes.data, pb.wide_word.ctypes.data
+        s.seq_off, s.seq2 = pb.seq_off.ctypes.data, pb.seq2.ctypes.data
+        s.n_exc, s.exc_byte, s.exc_val = len(pb.exc_byte), pb.exc_byte.ctypes.data, pb.exc_val.ctypes.data
+        self._keep.append(pb)
+        self._ck(self.L.npt_mg_submit_packed(self.h, C.byref(s)))
+
     def end_chrom(self):
         self._ck(self.L.npt_mg_end_chrom(self.h))
         self._keep = []
@@ -326,12 +337,16 @@ class MultiEngine:
         return dict(step_ms=s.value, key_exchange_ms=k.value, reduce_ms=r.value)
 
 
-def run_mg(cfg, devices, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL):
+def run_mg(cfg, devices, ref_codes, annotation, batches, chrom_index=0, what=abi.NPT_FETCH_ALL, packed=False):
     e = MultiEngine(cfg, devices)
     try:
         e.begin_chrom(chrom_index, ref_codes, annotation)
         for b in batches:
-            e.submit(b)
+            if packed:
+                from .packed import pack
+                e.submit_packed(pack(b))
+            else:
+                e.submit(b)
         e.end_chrom()
         r = e.fetch(what)
         r["_timing"] = e.step_ms()

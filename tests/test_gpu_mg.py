@@ -56,3 +56,31 @@ def test_mg_two_chromosomes_on_one_context():
             assert_same(dev, oracle.run(oracle.make_config(**kw), g, w.annotation, [b]))
     finally:
         e.close()
+
+
+def test_mg_packed_batches_split_on_even_bytes():
+    """npt_mg_submit_packed: shares of a packed batch start on an even seq4 byte; wide-element and exception lists are cut and
+    rebased per share"""
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    batches = [synth.generate(w, 500, 7001, num_sources=2), synth.generate(w, 501, 3, first_index=7001, num_sources=2)]
+    rng = np.random.default_rng(2)
+    k = rng.integers(0, len(batches[0].seq4), 300)
+    batches[0].seq4[k] = rng.integers(0, 256, 300).astype(np.uint8)   # non-ACGT codes -> exceptions in every share
+    kw = dict(bin=100, break_thresh=1000, record_depth=1, num_sources=2, max_coverage_clusters=256)
+    dev = engine.run_mg(engine.make_config(**kw), [0, 0, 0], g, w.annotation, batches, packed=True)
+    ora = oracle.run(oracle.make_config(**kw), g, w.annotation, batches)
+    assert_same(dev, ora)
+
+
+def test_mg_a_device_without_reads_and_an_error_that_does_not_hang():
+    w = workloads.SARS2
+    g = synth.genome_codes(w)
+    one = synth.generate(w, 9, 1)
+    kw = dict(bin=100, break_thresh=1000, record_depth=1)
+    dev = engine.run_mg(engine.make_config(**kw), [0, 0], g, w.annotation, [one])   # the second context never sees a read
+    assert_same(dev, oracle.run(oracle.make_config(**kw), g, w.annotation, [one]))
+    # a capacity error on the contexts must come back as an error from npt_mg_end_chrom, not as a hang of the group
+    b = synth.generate(w, 10, 4000)
+    with pytest.raises(engine.NptError):
+        engine.run_mg(engine.make_config(**dict(kw, bin=1, max_subclusters=16)), [0, 0], g, w.annotation, [b])
