@@ -215,6 +215,19 @@ def cov229e_real() -> Workload:
                       donor=HCOV229E.donor, acceptors=HCOV229E.acceptors, acceptor_w=HCOV229E.acceptor_w)
 
 
+def nc045512_real() -> Workload:
+    """data/SARS-Cov2/NC: NC_045512.2 (29 903 bp, 33-A tail) + its Coordinates.csv, where ORF7b (27756-27887) overlaps ORF7a."""
+    return from_files("sars2_nc045512_real", golden_path("nc045512", "NC_045512.fasta.gz"), golden_path("nc045512", "Coordinates.csv"),
+                      donor=SARS2.donor, acceptors=[28270, 26483, 25395, 27398, 27766, 27898, 21566, 26247, 27051], acceptor_w=SARS2.acceptor_w)
+
+
+def u13369_real() -> Workload:
+    """data/U13369: the human ribosomal DNA repeat (42 999 bp, IUPAC codes in the sequence, no polyA tail) + its 8-row table
+    (5'ETS, 18S, ITS1, 5.8S, ITS2, 28S, 3'ETS, repeat region); reads modelled as precursor fragments spliced between the genes."""
+    return from_files("rdna_u13369_real", golden_path("u13369", "Human_ribosomal_DNA_complete_repeating_unit.fasta.gz"),
+                      golden_path("u13369", "Coordinates.csv"), donor=3650, acceptors=[6623, 7935, 12970, 5528], acceptor_w=[0.4, 0.3, 0.2, 0.1])
+
+
 def ref_char_to_code(seq: str) -> np.ndarray:
     """Reference letters → BAM 4-bit codes (=ACMGRSVTWYHKDBN), case-insensitive; anything else → N(15).
     This is the comparison domain of refSeq.getBase(..) == readSeq.getBase(..) (IdentityProfile1.java:534)."""

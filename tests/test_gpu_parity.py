@@ -44,6 +44,17 @@ def test_config1_as_specified_from_the_reference_files():
     assert [x.split("\t")[:3] for x in rows[1:]] == [x.split("\t")[:3] for x in want[1:]]
 
 
+@pytest.mark.parametrize("which", ["nc045512", "u13369"])
+def test_other_reference_pairs_the_reference_ships(which):
+    """NC_045512.2 with its overlapping ORF7a / ORF7b rows, and the 43 kb rDNA repeat U13369 with IUPAC codes in the reference
+    and no leader row (data files of the reference, copied under tests/golden/)"""
+    w = workloads.nc045512_real() if which == "nc045512" else workloads.u13369_real()
+    S = 1 if which == "nc045512" else 2
+    b = synth.generate(w, 20200301, 30000, num_sources=S)
+    dev, ora = _both(dict(bin=10 if S == 1 else 100, break_thresh=1000 if S == 1 else 500, record_depth=1, num_sources=S, max_coverage_clusters=1024), w, [b])
+    assert_same(dev, ora)
+
+
 def test_config2_flags_200k():
     """the benchmark's own flag set (bin=100, breakThresh=1000, depth recording) on 200 k reads"""
     w = workloads.SARS2

@@ -84,3 +84,25 @@ def test_config1_on_the_real_files_two_restatements_agree():
     b = synth.generate(w, 20200301, 1500)
     _compare(dict(bin=10, break_thresh=1000, record_depth=1), w.annotation, [b], w=w)
     _compare(dict(bin=10, break_thresh=1000, record_depth=0), w.annotation, [b.slice(0, 300)], w=w)
+
+
+def test_other_reference_pairs_the_reference_ships():
+    """data/SARS-Cov2/NC (ORF7b overlapping ORF7a, 3'UTR row ending at 29 903 = 33 bases past seqlen - polyA) and data/U13369
+    (43 kb rDNA repeat, IUPAC codes in the reference, no leader row): parsed by the reference's rules, the two restatements
+    agree on reads generated against them, and adjust3UTR moves NC's last row like VIC01's"""
+    from tests.test_oracle_crosscheck import _compare
+    nc = workloads.nc045512_real()
+    assert nc.genome_len == 29903 and nc.polya_len == 33
+    a = nc.annotation
+    assert a.genes[7:9] == ["ORF7a", "ORF7b"] and a.start[8] < a.end[7] and a.end[-1] == 29903
+    b = synth.generate(nc, 20200301, 1200)
+    _compare(dict(bin=10, break_thresh=1000, record_depth=1), a, [b], w=nc)
+    res = oracle.run(oracle.make_config(bin=10, break_thresh=1000), synth.genome_codes(nc), a, [b])
+    rows = render.annot_rows(res, a, seqlen=nc.genome_len, polya=nc.polya_len)
+    assert rows[-1].split("\t")[:3] == ["3UTR", "29675", "29870"] and rows[9].split("\t")[0] == "ORF7b"
+    u = workloads.u13369_real()
+    assert u.genome_len == 42999 and u.polya_len == 0 and u.annotation.genes[0] == "5ETS" and len(u.annotation.genes) == 8
+    g = synth.genome_codes(u)
+    assert set(np.unique(g).tolist()) - {1, 2, 4, 8}          # R / Y / N in the reference sequence
+    bu = synth.generate(u, 5, 1200, num_sources=2)
+    _compare(dict(bin=100, break_thresh=500, record_depth=1, num_sources=2), u.annotation, [bu], w=u)
