@@ -130,6 +130,17 @@ __global__ void __launch_bounds__(FW_WARPS_MAX * 32, 1) fast_walk_kernel(const D
 // end.  The position bits make neighbours in the sorted order cover neighbouring parts of the reference, so that the reads of
 // one tile of a wide cluster (genomic fragments anywhere in 20 kb) touch few reference-grid entries.
 constexpr int ACC_POS_BITS = 10;
+// +1 at *p for every lane that is here with the same address: one RED per distinct address of the converged lanes.  Start,
+// end and junction positions of a batch fall on a few dozen addresses (ncu r02b: cov_key_kernel waits on REDs to hot lines).
+__device__ __forceinline__ void red_inc_aggregated(int* p) {
+#ifdef NPT_NO_RED_AGG
+  atomicAdd(p, 1);
+#else
+  const unsigned conv = __activemask();
+  const unsigned grp = __match_any_sync(conv, (unsigned long long)p);
+  if ((__ffs(grp) - 1) == (int)(threadIdx.x & 31)) atomicAdd(p, __popc(grp));
+#endif
+}
 __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys, unsigned* vals, int pos_shift) {
   if (__ldcg(b.bctr + 1)) return;  // break lists incomplete, nothing was clustered: the host re-runs this batch
   const long long arr_stride = (long long)c.cov_cap * c.S * c.stride;
@@ -149,8 +160,8 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
         int* mend = cov + 3 * arr_stride;
         // CigarCluster.setStartEnd :360-365 with the (trimmed) start / end of the read
         const int sp = b.start_pos[r], ep = b.end_pos[r];
-        if (sp >= 0 && sp < c.stride) atomicAdd(mstart + sp, 1);
-        if (ep >= 0 && ep < c.stride) atomicAdd(mend + ep, 1);
+        if (sp >= 0 && sp < c.stride) red_inc_aggregated(mstart + sp);
+        if (ep >= 0 && ep < c.stride) red_inc_aggregated(mend + ep);
         const unsigned meta = __ldg(b.fmeta + r);
         const int njunc = (meta >> 8) & 0xFF, nextra = (meta >> 16) & 0xFF, ndbl = (meta >> 24) & 0xFF;
         for (int d = 0; d < ndbl; d++) {   // positions emitted by two D elements
@@ -162,8 +173,8 @@ __global__ void cov_key_kernel(const DevCfg c, const BatchDev b, unsigned* keys,
           const uint4 h2 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 4));
           const uint4 h3 = __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 8));
           const uint4 h4 = nextra > 2 ? __ldg((const uint4*)(b.frare + r * FW_RARE_WORDS + 12)) : make_uint4(0u, 0u, 0u, 0u);
-          if (njunc > 0) { atomicAdd(mend + h2.x, 1); atomicAdd(mstart + h2.y, 1); }
-          if (njunc > 1) { atomicAdd(mend + h2.z, 1); atomicAdd(mstart + h2.w, 1); }
+          if (njunc > 0) { red_inc_aggregated(mend + h2.x); red_inc_aggregated(mstart + h2.y); }
+          if (njunc > 1) { red_inc_aggregated(mend + h2.z); red_inc_aggregated(mstart + h2.w); }
           for (int e = 0; e < nextra; e++) {
             const unsigned a = e == 0 ? h3.x : (e == 1 ? h3.z : (e == 2 ? h4.x : h4.z)), p = e == 0 ? h3.y : (e == 1 ? h3.w : (e == 2 ? h4.y : h4.w));
             if (a & 0x80000000u) {          // a position emitted by two D elements
