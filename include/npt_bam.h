@@ -90,6 +90,11 @@ typedef struct nptb_packed {
 } nptb_packed;
 int nptb_pack(nptb_reader* r, const nptb_batch* b, nptb_packed* out);
 
+/* Test hook: one raw DEFLATE stream (the payload of a BGZF block) through the packer's own table-driven decoder (mode 1,
+ * bam/fast_inflate.h: it refuses what it does not handle and the packer then uses zlib) or through zlib (mode 0).
+ * Returns the number of bytes written, or -1. */
+long nptb_inflate_raw(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, int mode);
+
 #ifdef __cplusplus
 }
 #endif

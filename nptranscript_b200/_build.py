@@ -90,7 +90,7 @@ def build_synth(force=False):
 def build_bam(force=False):
     """BAM (BGZF) -> SoA packer: host C++ + zlib, no CUDA."""
     src = os.path.join(HERE, "bam", "bam_pack.cpp")
-    deps = [src, os.path.join(ROOT, "include", "npt_bam.h")]
+    deps = [src, os.path.join(os.path.dirname(src), "fast_inflate.h"), os.path.join(ROOT, "include", "npt_bam.h")]
     if not force and not _stale(LIBBAM, deps):
         return LIBBAM
     with _locked(LIBBAM):

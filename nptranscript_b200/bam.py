@@ -36,7 +36,7 @@ class PackedStruct(C.Structure):
                 ("n_exc", C.c_int64), ("exc_byte", C.c_void_p), ("exc_val", C.c_void_p)]
 
 
-SYMBOLS = ["nptb_open", "nptb_close", "nptb_n_refs", "nptb_ref_name", "nptb_ref_len", "nptb_next_batch", "nptb_last_error", "nptb_pack"]
+SYMBOLS = ["nptb_open", "nptb_close", "nptb_n_refs", "nptb_ref_name", "nptb_ref_len", "nptb_next_batch", "nptb_last_error", "nptb_pack", "nptb_inflate_raw"]
 
 
 def lib():
@@ -59,6 +59,8 @@ def lib():
         L.nptb_last_error.restype = C.c_char_p
         L.nptb_pack.argtypes = [C.c_void_p, C.POINTER(BatchStruct), C.POINTER(PackedStruct)]
         L.nptb_pack.restype = C.c_int
+        L.nptb_inflate_raw.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        L.nptb_inflate_raw.restype = C.c_long
         _lib = L
     return _lib
 
