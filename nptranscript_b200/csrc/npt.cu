@@ -807,11 +807,11 @@ int npt_begin_chrom(npt_ctx* ctx, int32_t chrom_index, const uint8_t* ref_codes,
   const int max_cl = cf.max_clusters > 0 ? cf.max_clusters : (1 << 16);
   const int max_sb = cf.max_subclusters > 0 ? cf.max_subclusters : (1 << 21);
   const int max_pr = cf.max_break_pairs > 0 ? cf.max_break_pairs : (1 << 20);
-  // dense coverage rows (COV_ARRAYS int32 rows of seqlen + 2 per cluster and source): default = what fits 4 GB, between 256
+  // dense coverage rows (COV_ARRAYS int32 rows of seqlen + 2 per cluster and source): default = what fits 12 GB (10 000 clusters of a 30 kb genome, one source), between 256
   // clusters and max_clusters; the caller may ask for as many as HBM holds (rows are kept zero between chromosomes, so a
   // large capacity costs memory but no time)
   const size_t row_bytes = (size_t)COV_ARRAYS * cf.num_sources * ((size_t)ref_len + 2) * 4;
-  const int auto_cov = (int)std::min<size_t>((size_t)max_cl, std::max<size_t>(256, ((size_t)4 << 30) / row_bytes));
+  const int auto_cov = (int)std::min<size_t>((size_t)max_cl, std::max<size_t>(256, ((size_t)12 << 30) / row_bytes));
   const int max_cov = cf.record_depth ? (cf.max_coverage_clusters > 0 ? cf.max_coverage_clusters : auto_cov) : 0;
   const unsigned ncl = pow2_at_least(2ull * max_cl), nsb = pow2_at_least(2ull * max_sb), npr = calc_breaks1 ? pow2_at_least(2ull * max_pr) : 1;
   CK(ctx->d_cl.ensure(ncl)); CK(ctx->d_sb.ensure(nsb)); CK(ctx->d_pr.ensure(npr));

@@ -63,7 +63,7 @@ def test_config5_host_chromosome(chrom):
 
 
 def test_many_clusters_default_coverage_capacity_and_reuse():
-    """bin=1 on fuzzed reads: thousands of clusters with coverage rows.  The default capacity (what fits 4 GB, here the
+    """bin=1 on fuzzed reads: thousands of clusters with coverage rows.  The default capacity (what fits 12 GB, here the
     whole cluster table) holds them; the second chromosome on the same context finds the rows zero again (they are cleared
     after use at end of chromosome instead of memset per chromosome); an explicit small capacity is an error, not a drop"""
     from tests.fuzz import random_batch
