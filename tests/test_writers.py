@@ -170,3 +170,32 @@ def test_gff_and_bed_lines(tmp_path):
             assert int(c[2]) - int(c[1]) == int(c[11].split(",")[-1]) + int(c[10].split(",")[-1])   # last block ends at the transcript's end
     paths = rep.write(str(tmp_path), gff_thresh=(2, 1), max_transcripts=3, npy=False)
     assert {"0.gff.gz", "1.gff.gz", "00.bed.gz", "01.bed.gz"} <= {os.path.basename(p) for p in paths}
+
+
+def test_rows_known_answer_derived_by_hand_from_the_java_lines():
+    """KAT1 of SURVEY §8c (one read 10S65M28190N1600M30S at position 5 on the all-A reference, --bin 10): every field of the
+    three rows worked out by hand from CigarClusters.process1 (:138-196), CigarCluster.exonCount / numIsoforms (:702-735),
+    Annotation.getTypeInd (:233-236) and isLeader (:214-216)."""
+    w = workloads.SARS2
+    g = np.full(w.genome_len, 1, np.uint8)
+    b = synth.from_reads([(5, 0, 0, "10S65M28190N1600M30S", "A" * 1705)])
+    kw = dict(bin=10, break_thresh=1000, record_depth=0, track_break_sums=1)
+    res = oracle.run(oracle.make_config(**kw), g, w.annotation, [b])
+    rep = writers.ChromosomeReport(res, w.annotation, "MT007544.1", 0, engine.make_config(**kw), w.genome_len, src=b.src, read_names=["r0"],
+                                   source_names=["a.bam"])
+    genes, trans, fc = rep.rows()
+    key = "leader_leader,N_3UTR"           # up(5) _ up(69),down(28260) _ up(29859)   (IdentityProfile1.java:266-292)
+    # cnt.id, chrom, breaks[0], breaks[last], geneNme ("-": empty span), round(4/2), "1", leader break (6*10 < 266-10), h2 = breaks/10,
+    # cnt.id, geneNames.size(), "NA", cnt.sum(), count0
+    assert trans == ["\t".join(["ID0.0.t0", "MT007544.1", "5", "29859", "-", "2", "1", "1", "0,6,2826,2985", "ID0.0.t0", "0", "NA", "1", "1"])]
+    # cc.id, chrom, startPos, endPos, type (5 <= 100 and 29859 >= 29893-100), exonCount "2", numIsoforms round((1-2)/2) = 0, leader break,
+    # secondKey, geneNme, 0, totLen -1 (printed before writeDepthH5 sets it), readCountSum, count0
+    assert genes == ["\t".join(["ID0.0", "MT007544.1", "5", "29859", "5_3", "2", "0", "1", key, "-", "0", "-1", "1", "1"])]
+    # secondKey, chrom per block, starts, ends, "+;+", (69-5)+(29859-28260), count0
+    assert fc == ["\t".join([key, "MT007544.1;MT007544.1", "5;28260", "69;29859", "+;+", "1663", "1"])]
+    gff, bed = rep.gff_bed(gff_thresh=(1,), max_transcripts=1)
+    assert gff[0][0] == "MT007544.1\tnp\ttranscript\t5\t29859\t.\t+\t.\tID=ID0.0.t0;Parent=ID0.0;gene_id=ID0.0;gene_type=5_3;type=ORF;gene_name=" + key + ";count=1"
+    assert gff[0][1].startswith("MT007544.1\tnp\texon\t5\t69\t.\t+\t.\tID=ID0.0.t0.e.0;Parent=ID0.0.t0;gene_id=ID0.0.t0;")
+    assert gff[0][3] == "MT007544.1\tnp\tgene\t5\t29859\t.\t+\t.\tID=ID0.0;gene_id=ID0.0;gene_type=5_3;type=ORF;gene_name=" + key + ";count=1"
+    # chrom, start-1, end-1, transcript.gene, depth, strand, thick start/end, colour of source 0, floor(4/2), block sizes, block starts
+    assert bed[0] == ["MT007544.1\t4\t29858\tID0.0.t0.ID0.0.t0\t1\t+\t4\t29858\t0,0,0\t2\t64,1599\t0,28255"]
